@@ -1,0 +1,93 @@
+"""Deterministic math + RNG shared by oracle and device (include/dhmc_math.h)."""
+import numpy as np
+import pytest
+
+mp = pytest.importorskip("mpmath")
+
+
+def _max_ulp(got, ref):
+    worst = 0.0
+    for g, r in zip(got, ref):
+        r64 = float(r)
+        if r64 == 0 or not np.isfinite(r64):
+            continue
+        worst = max(worst, float(abs((mp.mpf(float(g)) - r) / np.spacing(abs(r64)))))
+    return worst
+
+
+def test_exp_log_accuracy(po):
+    mp.mp.prec = 200
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-700, 700, 4000), rng.uniform(-1, 1, 4000)])
+    assert _max_ulp(po.math("exp", x), [mp.exp(mp.mpf(float(v))) for v in x]) < 1.5
+    x = np.concatenate([np.exp(rng.uniform(-700, 700, 4000)), rng.uniform(0.5, 2, 4000),
+                        [5e-324, 1e-310, 2.3e-308]])
+    assert _max_ulp(po.math("log", x), [mp.log(mp.mpf(float(v))) for v in x]) < 1.5
+    x = rng.uniform(-0.9, 5, 4000)
+    assert _max_ulp(po.math("log1p", x), [mp.log1p(mp.mpf(float(v))) for v in x]) < 4
+    u = rng.uniform(0, 1, 4000)
+    assert _max_ulp(po.math("sin2pi", u), [mp.sin(2 * mp.pi * mp.mpf(float(v))) for v in u]) < 3
+    assert _max_ulp(po.math("cos2pi", u), [mp.cos(2 * mp.pi * mp.mpf(float(v))) for v in u]) < 3
+
+
+def test_special_values(po):
+    inf, nan = np.inf, np.nan
+    e = po.math("exp", [-inf, inf, 710.0, -746.0, 0.0])
+    assert list(e) == [0.0, inf, inf, 0.0, 1.0]
+    assert np.isnan(po.math("exp", [nan])[0])
+    l = po.math("log", [0.0, inf, 1.0])
+    assert list(l) == [-inf, inf, 0.0]
+    assert np.isnan(po.math("log", [-1.0])[0])
+    la = po.math("logaddexp", [-inf, -inf, 0.0, 1.0], [-inf, 1.0, -inf, 1.0])
+    assert la[0] == -inf and la[1] == 1.0 and la[2] == 0.0
+    assert abs(la[3] - (1.0 + np.log(2.0))) < 1e-15
+    # agrees with numpy to absolute 1e-15 on a broad range
+    rng = np.random.default_rng(1)
+    a, b = rng.uniform(-60, 10, 2000), rng.uniform(-60, 10, 2000)
+    assert np.max(np.abs(po.math("logaddexp", a, b) - np.logaddexp(a, b))) < 5e-15
+
+
+def test_philox_known_answers(po):
+    # Random123 kat_vectors, philox4x32-10
+    assert [hex(v) for v in po.philox([0, 0, 0, 0], [0, 0])] == \
+        ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    assert [hex(v) for v in po.philox([0xffffffff] * 4, [0xffffffff] * 2)] == \
+        ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    assert [hex(v) for v in po.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
+                                      [0xa4093822, 0x299f31d0])] == \
+        ['0xd16cfe09', '0x94fdcceb', '0x5001e420', '0x24126ea1']
+
+
+def test_rng_distributions(po):
+    z = po.normals(7, 3, 2, 5, 100000)
+    assert abs(z.mean()) < 0.015 and abs(z.std() - 1) < 0.01
+    assert abs(np.mean(z ** 4) - 3) < 0.1
+    # distinct (chain, t, stream) give distinct streams; same inputs are reproducible
+    assert np.array_equal(z, po.normals(7, 3, 2, 5, 100000))
+    assert not np.array_equal(z[:100], po.normals(7, 4, 2, 5, 100))
+    assert not np.array_equal(z[:100], po.normals(7, 3, 2, 6, 100))
+    q = po.random_position(1, 0, 50000)
+    assert q.min() > -2 and q.max() < 2 and abs(q.mean()) < 0.03
+    e = np.array([po.randexp(1, 2, 3, j) for j in range(20000)])
+    assert e.min() > 0 and abs(e.mean() - 1) < 0.03
+
+
+def test_canonical_reduction_width(po):
+    rng = np.random.default_rng(3)
+    a, b = rng.normal(size=1000), rng.normal(size=1000)
+    ref = float(np.dot(a, b))
+    for T in (0, 32, 64, 128, 256):
+        assert abs(po.canon_dot(T, a, b) - ref) < 1e-12
+    # explicit restatement of the canonical order for T = 32
+    part = np.zeros(32)
+    for v in range(32):
+        acc = 0.0
+        for i in range(v, 1000, 32):
+            acc = acc + a[i] * b[i]
+        part[v] = acc
+    off = 1
+    while off < 32:
+        for v in range(0, 32, 2 * off):
+            part[v] = part[v] + part[v + off]
+        off *= 2
+    assert po.canon_dot(32, a, b) == part[0]
