@@ -1,0 +1,158 @@
+/* dhmc.h — C ABI of the B200-native many-chain NUTS engine (libdhmc_b200.so).
+ *
+ * Drop-in boundary for the sampler path of tpapp/DynamicHMC.jl:
+ * host code (Julia via ccall, or the Python mirror in dynamichmc.jl_b200/)
+ * keeps the mcmc_with_warmup / LogDensityProblems surface and calls these entry
+ * points; everything numeric runs in hand-written sm_100a CUDA.  Plain pointers
+ * and sizes only.  All functions return a status (0 = ok) unless noted.
+ *
+ * Conventions
+ *  - B = n_chains on this handle, D = dim.  Every per-chain vector argument is
+ *    [D, B] column-major (chain-major: element i of chain c at c*D + i), which
+ *    is Julia's Matrix{Float64}(D, B); draws are [D, N, B] column-major so that
+ *    results[k].posterior_matrix (mcmc.jl:230,275) is a zero-copy view.
+ *  - dhmc_tree_stats is bit-compatible with TreeStatisticsNUTS (NUTS.jl:208-221).
+ *  - Host pointers unless the function name ends in _dev.
+ *  - One handle = one device + one stream; calls are synchronous and not
+ *    thread-safe per handle (the reference call is single-threaded too).
+ *  - Numerical per-chain failures never abort other chains: they set bits in the
+ *    per-chain status word and the call returns DHMC_ENUMERIC (the Julia shim
+ *    re-throws DynamicHMCError, utilities.jl:17-27, with the chain ids).
+ */
+#ifndef DHMC_H
+#define DHMC_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  DHMC_OK = 0,
+  DHMC_EARG = 1,     /* -> ArgumentError (@argcheck sites: NUTS.jl:190-191,
+                        stepsize.jl:31-33,108-111, mcmc.jl:191-192) */
+  DHMC_ENUMERIC = 2, /* -> DynamicHMCError (hamiltonian.jl:203,213,215;
+                        stepsize.jl:58,78) for at least one chain */
+  DHMC_ECUDA = 3,
+  DHMC_ENOMEM = 4
+};
+
+/* per-chain status bits (dhmc_chain_status) */
+enum {
+  DHMC_CHAIN_BAD_INITIAL = 1,   /* evaluate_ℓ(strict) failed, hamiltonian.jl:212-215 */
+  DHMC_CHAIN_SEARCH_FAILED = 2, /* find_initial_stepsize, stepsize.jl:58 / :78 */
+  DHMC_CHAIN_NONFINITE_Q = 4,   /* evaluate_ℓ: non-finite position, hamiltonian.jl:203 */
+  DHMC_CHAIN_BAD_ACCEPTANCE = 8 /* adapt_stepsize @argcheck 0 ≤ a ≤ 1, stepsize.jl:148 */
+};
+
+/* log-density family ids: see include/dhmc_models.h */
+enum { DHMC_METRIC_NOTHING = 0, DHMC_METRIC_DIAGONAL = 1 };
+
+typedef struct dhmc_handle dhmc_handle;
+
+/* Flattened NUTS(; max_depth, min_Δ) (NUTS.jl:178-195) + problem shape. */
+typedef struct {
+  int32_t device;            /* CUDA device ordinal */
+  int32_t family;            /* DHMC_FAMILY_* (LogDensityProblems model id) */
+  int64_t dim;               /* LogDensityProblems.dimension(ℓ) */
+  int64_t n_chains;          /* chains resident on this handle (local shard) */
+  int64_t chain_offset;      /* global id of local chain 0 (RNG key), §8e */
+  uint64_t seed;             /* RNG seed (stands in for the rng argument) */
+  int32_t max_depth;         /* NUTS.max_depth, 0 < . <= 12 in this build */
+  int32_t threads_per_chain; /* 0 = auto; 32..256, power of two */
+  double min_delta;          /* NUTS.min_Δ < 0 */
+  int32_t ctas_per_sm;       /* 0 = auto */
+  int32_t reserved;
+} dhmc_config;
+
+/* TreeStatisticsNUTS — NUTS.jl:208-221 (56 bytes) */
+typedef struct {
+  double pi;              /* π: logdensity(H, ζ) of the selected point */
+  int64_t depth;
+  int64_t left, right;    /* termination::InvalidTree, trees.jl:180-202 */
+  double acceptance_rate;
+  int64_t steps;
+  uint32_t directions;    /* Directions.flags, trees.jl:19-21 */
+  uint32_t pad;
+} dhmc_tree_stats;
+
+/* DualAveraging(; δ, γ, κ, t₀) — stepsize.jl:98-118 */
+typedef struct { double delta, gamma, kappa; int32_t t0; int32_t pad; } dhmc_dual_averaging;
+
+/* ---- lifecycle ------------------------------------------------------- */
+int dhmc_create(const dhmc_config* cfg, dhmc_handle** out);
+int dhmc_destroy(dhmc_handle* h);
+/* Message of the last failing call on h (h == NULL: last dhmc_create failure).
+ * Valid until the next call. */
+const char* dhmc_last_error(dhmc_handle* h);
+/* threads per chain (canonical reduction width T) and elements per thread */
+int dhmc_get_layout(dhmc_handle* h, int32_t* threads_per_chain, int32_t* elems_per_thread);
+
+/* ---- problem: replaces the ℓ argument (LogDensityProblems object) ------ */
+/* params: DIAG_NORMAL [mu(D), prec(D)]; STD_NORMAL / FUNNEL: n == 0. */
+int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n);
+
+/* ---- state: initialization = (q, κ, ϵ), mcmc.jl:111-132 ---------------- */
+/* q: [D,B]; evaluates ℓ, ∇ℓ strictly (initialize_warmup_state, mcmc.jl:129-132). */
+int dhmc_set_position(dhmc_handle* h, const double* q);
+/* random_position, mcmc.jl:108: q ~ U[-2,2]^D per chain from the handle's RNG. */
+int dhmc_random_position(dhmc_handle* h);
+/* κ = GaussianKineticEnergy(Diagonal(minv)) (hamiltonian.jl:80); minv [D,B],
+ * or [D] broadcast to all chains when broadcast != 0; NULL = identity (:87). */
+int dhmc_set_metric(dhmc_handle* h, const double* minv, int broadcast);
+/* ϵ per chain [B], or one value for all chains when broadcast != 0. */
+int dhmc_set_stepsize(dhmc_handle* h, const double* eps, int broadcast);
+/* Momentum of the phase point used by dhmc_leapfrog / dhmc_phase_logdensity. */
+int dhmc_set_momentum(dhmc_handle* h, const double* p);
+/* Any output pointer may be NULL.  q, grad, minv, p: [D,B]; lq, eps: [B]. */
+int dhmc_get_state(dhmc_handle* h, double* q, double* lq, double* grad, double* minv,
+                   double* eps, double* p);
+int dhmc_chain_status(dhmc_handle* h, int32_t* status /* [B] */);
+/* Number of transitions already drawn per chain (RNG counter); get/set make the
+ * (q, κ, ϵ, counter) tuple a checkpoint (mcmc_keep_warmup/mcmc_steps, §8f). */
+int dhmc_get_transition_count(dhmc_handle* h, uint32_t* t);
+int dhmc_set_transition_count(dhmc_handle* h, uint32_t t);
+
+/* ---- fine-grained path (parity tests) --------------------------------- */
+/* leapfrog(H, z, ±ϵ) n_steps times on every chain — hamiltonian.jl:273-282.
+ * sign = +1 / -1 (NUTS.jl:28-31). */
+int dhmc_leapfrog(dhmc_handle* h, int32_t n_steps, int32_t sign);
+/* logdensity(H, z) per chain — hamiltonian.jl:251-256.  out: [B]. */
+int dhmc_phase_logdensity(dhmc_handle* h, double* out);
+/* One NUTS transition per chain at the current (q, κ, ϵ), no adaptation —
+ * sample_tree, NUTS.jl:232-241.  p [D,B] and directions [B] override the RNG
+ * draws when non-NULL (the reference's p= / directions= keywords). */
+int dhmc_sample_tree(dhmc_handle* h, const double* p, const uint32_t* directions,
+                     dhmc_tree_stats* stats /* [B] */);
+
+/* ---- coarse path: warmup stages and inference -------------------------- */
+/* warmup(::InitialStepsizeSearch) — mcmc.jl:134-148, stepsize.jl:46-85. */
+int dhmc_find_initial_stepsize(dhmc_handle* h, double initial_eps, double log_threshold,
+                               int32_t maxiter_crossing);
+/* warmup(::TuningNUTS{M}) — mcmc.jl:258-286.  da == NULL: FixedStepsize
+ * (stepsize.jl:181-189).  metric: DHMC_METRIC_NOTHING | _DIAGONAL.  lambda is
+ * accepted for interface parity; it is the identity for Diagonal (mcmc.jl:223).
+ * Outputs may be NULL: posterior [D,N,B], stats/eps_used/logdens [N,B]. */
+int dhmc_warmup_stage(dhmc_handle* h, int32_t N, int32_t metric, const dhmc_dual_averaging* da,
+                      double lambda, double* posterior, dhmc_tree_stats* stats,
+                      double* eps_used, double* logdens);
+/* mcmc — mcmc.jl:366-381: N transitions at the adapted (κ, ϵ). */
+int dhmc_mcmc(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats,
+              double* logdens);
+/* Same with DEVICE output pointers (draws stay in HBM for an NCCL all-gather). */
+int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats,
+                  double* logdens);
+
+/* ---- measurement hooks ------------------------------------------------- */
+/* Σ tree_statistics.steps over all chains and draws of the last sampling call. */
+int dhmc_last_total_steps(dhmc_handle* h, int64_t* steps);
+/* Device time (CUDA events on the handle's stream) of the last sampling /
+ * leapfrog kernel, and the number of kernels this handle has launched. */
+int dhmc_last_kernel_ms(dhmc_handle* h, double* ms);
+int dhmc_kernel_launches(dhmc_handle* h, int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DHMC_H */

@@ -1,0 +1,211 @@
+// hostsim.cpp — host simulation of the DEVICE state machine, for `-m "not gpu"` tests.
+//
+// Compiles the product's control code (dynamichmc.jl_b200/csrc/nuts_machine.cuh,
+// the flattened NUTS tree the GPU runs) with g++ against a plain-loop backend so
+// that its bookkeeping (explicit stack, slot pool, RNG order, early exits) can
+// be compared bit-for-bit with the recursive oracle on a machine without a GPU.
+// This is a TEST HARNESS: it is not linked into libdhmc_b200.so and the product
+// has no CPU fallback.
+#include <cstring>
+#include <vector>
+
+#include "../../dynamichmc.jl_b200/csrc/nuts_machine.cuh"
+#include "../../include/dhmc_models.h"
+
+using vec = std::vector<double>;
+using namespace dhmc;
+
+namespace {
+
+template <class F>
+double canon_sum(int T, int D, F term) {
+  double part[1024];
+  for (int v = 0; v < T; ++v) {
+    double acc = 0.0;
+    for (int i = v; i < D; i += T) acc = acc + term(i);
+    part[v] = acc;
+  }
+  for (int off = 1; off < T; off <<= 1)
+    for (int v = 0; v < T; v += 2 * off) part[v] = part[v] + part[v + off];
+  return part[0];
+}
+
+struct HostBackend {
+  int D, T, family;
+  const double* params;
+  vec q, p, g, minv, rhoL, Rnew;
+  double lq = 0;
+  std::vector<vec> slots;
+  Entry entries[kMaxLevels + 2];
+  vec wmean, wm2;
+  int max_slots_used = 0;
+
+  HostBackend(int D_, int T_, int fam, const double* pr, int nslots)
+      : D(D_), T(T_), family(fam), params(pr), q(D_), p(D_), g(D_), minv(D_, 1.0), rhoL(D_),
+        Rnew(D_), slots(nslots, vec(D_)), wmean(D_), wm2(D_) {}
+
+  uint64_t reserved_mask() const { return 0; }
+  double cur_lq() const { return lq; }
+  void set_cur_lq(double v) { lq = v; }
+  void st_q(int s) { slots[s] = q; }
+  void st_p(int s) { slots[s] = p; }
+  void st_g(int s) { slots[s] = g; }
+  void st_rho(int s) { slots[s] = rhoL; }
+  void ld_q(int s) { q = slots[s]; }
+  void ld_p(int s) { p = slots[s]; }
+  void ld_g(int s) { g = slots[s]; }
+  void swap_cur(int sq, int sp, int sg) { q.swap(slots[sq]); p.swap(slots[sp]); g.swap(slots[sg]); }
+  void rho_from_p() { rhoL = p; }
+  void rho_commit() { rhoL = Rnew; }
+  void put_entry(int j, const Entry& e) { entries[j] = e; }
+  Entry get_entry(int j) const { return entries[j]; }
+
+  void draw_momentum(dm_rng_key key, uint32_t t, const double* p_override) {
+    for (int i = 0; i < D; ++i)
+      p[i] = p_override ? p_override[i]
+                        : dm_sqrt(1.0 / minv[i]) * dm_normal_elem(key, DHMC_STREAM_P, t, (uint32_t)i);
+  }
+  void draw_search_momentum(dm_rng_key key, const double* p_override) {
+    for (int i = 0; i < D; ++i)
+      p[i] = p_override ? p_override[i]
+                        : dm_sqrt(1.0 / minv[i]) * dm_normal_elem(key, DHMC_STREAM_PSEARCH, 0, (uint32_t)i);
+  }
+  double kinetic() const {
+    return canon_sum(T, D, [&](int i) { double ps = minv[i] * p[i]; return p[i] * ps; }) / 2.0;
+  }
+  double phase_logdensity() const {
+    if (!dm_isfinite(lq)) return -dm_inf();
+    double K = kinetic();
+    return lq - (dm_isfinite(K) ? K : dm_inf());
+  }
+  // model: fills g from q, returns sanitised ℓq (evaluate_ℓ, hamiltonian.jl:202-217)
+  double eval_model(bool* gbad) {
+    double l = 0;
+    switch (family) {
+      case DHMC_FAMILY_STD_NORMAL: {
+        double s = canon_sum(T, D, [&](int i) { return dhmc_std_term(q[i]); });
+        for (int i = 0; i < D; ++i) g[i] = dhmc_std_grad(q[i]);
+        l = dhmc_std_lq(s);
+        break;
+      }
+      case DHMC_FAMILY_DIAG_NORMAL: {
+        const double* mu = params; const double* pr = params + D;
+        vec t(D);
+        for (int i = 0; i < D; ++i) t[i] = dhmc_diag_scaled(q[i], mu[i], pr[i]);
+        double s = canon_sum(T, D, [&](int i) { return dhmc_diag_term(q[i], mu[i], t[i]); });
+        for (int i = 0; i < D; ++i) g[i] = dhmc_diag_grad(t[i]);
+        l = dhmc_diag_lq(s);
+        break;
+      }
+      default: {
+        double v = q[0], ev = dm_exp(-v);
+        double S = canon_sum(T, D, [&](int i) { return dhmc_funnel_term(i, q[i]); });
+        for (int i = 0; i < D; ++i) g[i] = dhmc_funnel_grad(i, q[i], v, ev, S, D);
+        l = dhmc_funnel_lq(v, ev, S, D);
+      }
+    }
+    bool bad = false;
+    for (int i = 0; i < D; ++i) bad = bad || !dm_isfinite(g[i]);
+    *gbad = bad;
+    if ((dm_isfinite(l) && !bad) || l == -dm_inf()) return l;
+    return -dm_inf();
+  }
+  double leapfrog(double eps, int* flags) {
+    const double h = eps / 2;
+    for (int i = 0; i < D; ++i) p[i] = p[i] + h * g[i];
+    bool qbad = false;
+    for (int i = 0; i < D; ++i) {
+      double vel = minv[i] * p[i];
+      q[i] = q[i] + eps * vel;
+      qbad = qbad || !dm_isfinite(q[i]);
+    }
+    bool gbad;
+    lq = eval_model(&gbad);
+    if (qbad) { *flags |= 1; lq = -dm_inf(); }
+    for (int i = 0; i < D; ++i) p[i] = p[i] + h * g[i];
+    return phase_logdensity();
+  }
+  bool merge_check(int sEf, int sEl, int sEr, int sLf, bool L_leaf) {
+    const vec& Ef = slots[sEf]; const vec& El = slots[sEl]; const vec& Er = slots[sEr];
+    const vec& Lf = L_leaf ? p : slots[sLf];
+    const vec& Lr = L_leaf ? p : rhoL;
+    vec A(D), Bv(D);
+    for (int i = 0; i < D; ++i) { A[i] = Er[i] + Lf[i]; Bv[i] = El[i] + Lr[i]; Rnew[i] = Er[i] + Lr[i]; }
+    auto dot = [&](const vec& a, const vec& r) {
+      return canon_sum(T, D, [&](int i) { double ps = minv[i] * a[i]; return ps * r[i]; });
+    };
+    double d1 = dot(Ef, A), d2 = dot(Lf, A), d3 = dot(El, Bv), d4 = dot(p, Bv), d5 = dot(Ef, Rnew),
+           d6 = dot(p, Rnew);
+    return d1 < 0 || d2 < 0 || d3 < 0 || d4 < 0 || d5 < 0 || d6 < 0;
+  }
+  void welford_reset() { std::fill(wmean.begin(), wmean.end(), 0.0); std::fill(wm2.begin(), wm2.end(), 0.0); }
+  void welford_push(int n) {
+    for (int i = 0; i < D; ++i) {
+      double d = q[i] - wmean[i];
+      wmean[i] = wmean[i] + d / (double)n;
+      wm2[i] = wm2[i] + d * (q[i] - wmean[i]);
+    }
+  }
+  void welford_finish(int n) { for (int i = 0; i < D; ++i) minv[i] = wm2[i] / (double)(n - 1); }
+};
+
+struct Sink {
+  HostBackend& b; double* post; dhmc_tree_stats* stats; double* logd; double* eps_used;
+  void operator()(int n, const dhmc_tree_stats& ts, double e) {
+    if (post) std::memcpy(post + (size_t)n * b.D, b.q.data(), sizeof(double) * b.D);
+    if (stats) stats[n] = ts;
+    if (logd) logd[n] = b.lq;
+    if (eps_used) eps_used[n] = e;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int hs_slots_needed(int max_depth) { return slots_needed(max_depth); }
+
+// N transitions of one chain starting at q with metric minv and step size eps.
+// adapt4 = {delta, gamma, kappa, t0} or NULL; metric = DHMC_METRIC_*.
+// Returns the chain status bits; eps_out = final ϵ; minv is updated in place.
+int hs_run(int family, int D, const double* params, int T, double* minv, int max_depth,
+           double min_delta, uint64_t seed, uint64_t chain, uint32_t t0, int N, double* q,
+           double eps, const double* adapt4, int metric, const double* p_override,
+           const uint32_t* dir_override, double* post, dhmc_tree_stats* stats, double* logd,
+           double* eps_used, double* eps_out, double* lq_out, double* g_out) {
+  const int ns = slots_needed(max_depth);
+  HostBackend b(D, T, family, params, ns);
+  b.q.assign(q, q + D);
+  b.minv.assign(minv, minv + D);
+  bool gbad;
+  b.lq = b.eval_model(&gbad);
+  NutsMachine<HostBackend> m(b, dm_make_key(seed, chain), max_depth, min_delta, ns);
+  AdaptConfig cfg{};
+  cfg.adapt = adapt4 != nullptr;
+  if (adapt4) { cfg.delta = adapt4[0]; cfg.gamma = adapt4[1]; cfg.kappa = adapt4[2]; cfg.t0 = (int)adapt4[3]; }
+  cfg.metric = metric;
+  Sink sink{b, post, stats, logd, eps_used};
+  double e = m.run(t0, N, eps, cfg, p_override, dir_override, sink);
+  if (eps_out) *eps_out = e;
+  std::memcpy(q, b.q.data(), sizeof(double) * D);
+  std::memcpy(minv, b.minv.data(), sizeof(double) * D);
+  if (lq_out) *lq_out = b.lq;
+  if (g_out) std::memcpy(g_out, b.g.data(), sizeof(double) * D);
+  return m.status;
+}
+
+int hs_find_initial_stepsize(int family, int D, const double* params, int T, const double* minv,
+                             uint64_t seed, uint64_t chain, const double* q, const double* p_override,
+                             double initial_eps, double log_threshold, int maxiter, double* eps_out) {
+  const int ns = slots_needed(10);
+  HostBackend b(D, T, family, params, ns);
+  b.q.assign(q, q + D);
+  b.minv.assign(minv, minv + D);
+  bool gbad;
+  b.lq = b.eval_model(&gbad);
+  NutsMachine<HostBackend> m(b, dm_make_key(seed, chain), 10, -1000.0, ns);
+  *eps_out = m.find_initial_stepsize(initial_eps, log_threshold, maxiter, p_override);
+  return m.status;
+}
+
+}  // extern "C"
