@@ -1,0 +1,462 @@
+"""Host-side mirror of the DynamicHMC.jl sampler API over the C ABI.
+
+Names, argument meaning and error behaviour follow the reference
+(src/mcmc.jl, src/NUTS.jl, src/stepsize.jl, src/hamiltonian.jl); the numeric
+work happens in libdhmc_b200.so for `chains` independent chains at once.  The
+reference's toolchain (Julia) is absent from this image, so this Python layer
+plays the role of the Julia shim shown in INTEGRATION.md / julia/B200HMC.jl.
+
+    results = mcmc_with_warmup(seed, ℓ, N; chains=K, initialization=..., warmup_stages=...,
+                               algorithm=NUTS())
+returns a `Results` whose `[k]` is the reference's NamedTuple for chain k
+(posterior_matrix [D, N], tree_statistics [N], logdensities [N], κ, ϵ).
+"""
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+
+
+# ------------------------------------------------------------------ errors
+class DynamicHMCError(Exception):
+    """src/utilities.jl:17-27 — numerical failure; `debug_information` carries chain ids."""
+
+    def __init__(self, message, **debug_information):
+        super().__init__(message)
+        self.message = message
+        self.debug_information = debug_information
+
+
+class ArgumentError(ValueError):
+    """Julia's ArgumentError raised by @argcheck in the reference."""
+
+
+def _argcheck(cond, msg):
+    if not cond:
+        raise ArgumentError(msg)
+
+
+# ------------------------------------------------------------------ log densities
+# DeviceLogDensity types: the LogDensityProblems objects whose ℓ, ∇ℓ exist as
+# device code (hamiltonian.jl:204 is the only call site).  Each also evaluates on
+# the CPU through numpy so that the same object can be handed to other samplers.
+class DeviceLogDensity:
+    family = -1
+
+    def dimension(self):
+        return self.D
+
+    def capabilities(self):
+        return 1  # LogDensityOrder{1}
+
+    def params(self):
+        return np.zeros(0)
+
+
+@dataclass
+class StandardNormal(DeviceLogDensity):
+    D: int
+    family = L.FAMILY_STD_NORMAL
+
+    def logdensity_and_gradient(self, q):
+        q = np.asarray(q, float)
+        return -0.5 * float(q @ q), -q
+
+
+@dataclass
+class DiagNormal(DeviceLogDensity):
+    """N(μ, Diagonal(σ²))"""
+    mu: np.ndarray
+    sigma2: np.ndarray
+    family = L.FAMILY_DIAG_NORMAL
+
+    def __post_init__(self):
+        self.mu = np.ascontiguousarray(self.mu, float)
+        self.sigma2 = np.ascontiguousarray(self.sigma2, float)
+        _argcheck(self.mu.shape == self.sigma2.shape and self.mu.ndim == 1, "mu, sigma2: same length")
+        self.D = self.mu.size
+
+    def params(self):
+        return np.concatenate([self.mu, 1.0 / self.sigma2])
+
+    def logdensity_and_gradient(self, q):
+        d = np.asarray(q, float) - self.mu
+        t = d / self.sigma2
+        return -0.5 * float(d @ t), -t
+
+
+@dataclass
+class Funnel(DeviceLogDensity):
+    """Neal's funnel θ = (v, x₁…x_{D-1})."""
+    D: int = 10
+    family = L.FAMILY_FUNNEL
+
+    def logdensity_and_gradient(self, q):
+        q = np.asarray(q, float)
+        v, x = q[0], q[1:]
+        S = float(x @ x)
+        ev = math.exp(-v)
+        g = np.empty_like(q)
+        g[0] = -v / 9 + 0.5 * ev * S - 0.5 * (self.D - 1)
+        g[1:] = -ev * x
+        return -v * v / 18 - 0.5 * ev * S - 0.5 * (self.D - 1) * v, g
+
+
+# ------------------------------------------------------------------ algorithm structs
+@dataclass
+class NUTS:
+    """src/NUTS.jl:178-195"""
+    max_depth: int = 10
+    min_Δ: float = -1000.0
+
+    def __post_init__(self):
+        _argcheck(0 < self.max_depth <= 32, "0 < max_depth ≤ MAX_DIRECTIONS_DEPTH")
+        _argcheck(self.min_Δ < 0, "min_Δ < 0")
+
+
+@dataclass
+class DualAveraging:
+    """src/stepsize.jl:98-118"""
+    δ: float = 0.8
+    γ: float = 0.05
+    κ: float = 0.75
+    t0: int = 10
+
+    def __post_init__(self):
+        _argcheck(0 < self.δ < 1, "0 < δ < 1")
+        _argcheck(self.γ > 0, "γ > 0")
+        _argcheck(0.5 < self.κ <= 1, "0.5 < κ ≤ 1")
+        _argcheck(self.t0 >= 0, "t₀ ≥ 0")
+
+
+class FixedStepsize:
+    """src/stepsize.jl:181-189"""
+
+
+@dataclass
+class InitialStepsizeSearch:
+    """src/stepsize.jl:23-36"""
+    initial_ϵ: float = 0.1
+    log_threshold: float = math.log(0.8)
+    maxiter_crossing: int = 400
+
+    def __post_init__(self):
+        _argcheck(math.isfinite(self.log_threshold) and self.log_threshold < 0, "isfinite(log_threshold) && log_threshold < 0")
+        _argcheck(math.isfinite(self.initial_ϵ) and 0 < self.initial_ϵ, "isfinite(initial_ϵ) && 0 < initial_ϵ")
+        _argcheck(self.maxiter_crossing >= 50, "maxiter_crossing ≥ 50")
+
+
+Diagonal = "Diagonal"
+Symmetric = "Symmetric"
+
+
+@dataclass
+class TuningNUTS:
+    """src/mcmc.jl:178-195 — M ∈ {None, Diagonal, Symmetric}"""
+    N: int
+    stepsize_adaptation: object = field(default_factory=DualAveraging)
+    M: Optional[str] = None
+    λ: Optional[float] = None
+
+    def __post_init__(self):
+        _argcheck(self.N >= 20, "N ≥ 20")
+        if self.λ is None:
+            self.λ = 5.0 / self.N
+        _argcheck(self.λ >= 0, "λ ≥ 0")
+        _argcheck(self.M in (None, Diagonal, Symmetric), "M <: Union{Nothing,Diagonal,Symmetric}")
+
+
+def default_warmup_stages(stepsize_search=InitialStepsizeSearch(), M=Diagonal,
+                          stepsize_adaptation=DualAveraging(), init_steps=75, middle_steps=25,
+                          doubling_stages=5, terminating_steps=50):
+    """src/mcmc.jl:415-425"""
+    return (stepsize_search, TuningNUTS(init_steps, stepsize_adaptation),
+            *(TuningNUTS(middle_steps * 2 ** i, stepsize_adaptation, M) for i in range(doubling_stages)),
+            TuningNUTS(terminating_steps, stepsize_adaptation))
+
+
+def fixed_stepsize_warmup_stages(M=Diagonal, middle_steps=25, doubling_stages=5):
+    """src/mcmc.jl:436-440"""
+    return tuple(TuningNUTS(middle_steps * 2 ** i, FixedStepsize(), M) for i in range(doubling_stages))
+
+
+@dataclass
+class GaussianKineticEnergy:
+    """src/hamiltonian.jl:56-87 with Diagonal M⁻¹: `minv` is [D] (shared) or [D, K]."""
+    minv: np.ndarray
+
+    @staticmethod
+    def identity(N, m=1.0):
+        return GaussianKineticEnergy(np.full(N, float(m)))
+
+
+# ------------------------------------------------------------------ engine
+class Engine:
+    """Owns a dhmc_handle: K chains of one problem on one GPU."""
+
+    def __init__(self, ℓ: DeviceLogDensity, chains: int, seed: int = 0, algorithm: NUTS = None,
+                 device: int = 0, chain_offset: int = 0, threads_per_chain: int = 0,
+                 ctas_per_sm: int = 0):
+        algorithm = algorithm or NUTS()
+        _argcheck(ℓ.capabilities() >= 1, "capabilities(ℓ) ≥ LogDensityOrder(1)")   # hamiltonian.jl:146
+        self.ℓ, self.K, self.D, self.algorithm = ℓ, int(chains), int(ℓ.dimension()), algorithm
+        self._lib = L.lib()
+        cfg = L.Config(device=device, family=ℓ.family, dim=self.D, n_chains=self.K,
+                       chain_offset=chain_offset, seed=seed, max_depth=algorithm.max_depth,
+                       threads_per_chain=threads_per_chain, min_delta=algorithm.min_Δ,
+                       ctas_per_sm=ctas_per_sm, reserved=0)
+        h = C.c_void_p()
+        rc = self._lib.dhmc_create(C.byref(cfg), C.byref(h))
+        if rc != L.DHMC_OK:
+            msg = self._lib.dhmc_last_error(None).decode()
+            if rc == L.DHMC_EARG:
+                raise ArgumentError(msg)
+            raise RuntimeError(f"dhmc_create failed [{rc}]: {msg}")
+        self._h = h
+        pr = np.ascontiguousarray(ℓ.params(), float)
+        self._ck(self._lib.dhmc_set_problem(self._h, L.ptr(pr) if pr.size else None, C.c_size_t(pr.size)))
+
+    # -- plumbing
+    def _ck(self, rc):
+        if rc == L.DHMC_OK:
+            return
+        msg = self._lib.dhmc_last_error(self._h).decode()
+        if rc == L.DHMC_EARG:
+            raise ArgumentError(msg)
+        if rc == L.DHMC_ENUMERIC:
+            raise DynamicHMCError(msg, chain_status=self.chain_status())
+        raise RuntimeError(f"libdhmc_b200 error [{rc}]: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.dhmc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def layout(self):
+        t, e = C.c_int32(), C.c_int32()
+        self._ck(self._lib.dhmc_get_layout(self._h, C.byref(t), C.byref(e)))
+        return t.value, e.value
+
+    def _kd(self, a, name):
+        a = np.ascontiguousarray(a, float)
+        _argcheck(a.shape == (self.K, self.D), f"{name}: expected [D, K] column-major = numpy ({self.K}, {self.D})")
+        return a
+
+    # -- state
+    def set_position(self, q):
+        q = self._kd(q, "q")
+        self._ck(self._lib.dhmc_set_position(self._h, L.ptr(q)))
+
+    def random_position(self):
+        self._ck(self._lib.dhmc_random_position(self._h))
+
+    def set_metric(self, minv=None):
+        if minv is None:
+            self._ck(self._lib.dhmc_set_metric(self._h, None, 0))
+            return
+        minv = np.ascontiguousarray(minv, float)
+        if minv.ndim == 1:
+            _argcheck(minv.size == self.D, "dimension(ℓ) == size(κ, 1)")            # hamiltonian.jl:147
+            self._ck(self._lib.dhmc_set_metric(self._h, L.ptr(minv), 1))
+        else:
+            self._ck(self._lib.dhmc_set_metric(self._h, L.ptr(self._kd(minv, "minv")), 0))
+
+    def set_stepsize(self, eps):
+        e = np.ascontiguousarray(eps, float).reshape(-1)
+        if e.size == 1:
+            self._ck(self._lib.dhmc_set_stepsize(self._h, L.ptr(e), 1))
+        else:
+            _argcheck(e.size == self.K, "one ϵ per chain")
+            self._ck(self._lib.dhmc_set_stepsize(self._h, L.ptr(e), 0))
+
+    def set_momentum(self, p):
+        self._ck(self._lib.dhmc_set_momentum(self._h, L.ptr(self._kd(p, "p"))))
+
+    def get_state(self, fields=("q", "lq", "grad", "minv", "eps", "p")):
+        K, D = self.K, self.D
+        out = {}
+        shapes = dict(q=(K, D), lq=(K,), grad=(K, D), minv=(K, D), eps=(K,), p=(K, D))
+        for f in fields:
+            out[f] = np.empty(shapes[f])
+        args = [L.ptr(out[f]) if f in out else None for f in ("q", "lq", "grad", "minv", "eps", "p")]
+        self._ck(self._lib.dhmc_get_state(self._h, *args))
+        return out
+
+    def chain_status(self):
+        st = np.zeros(self.K, dtype=np.int32)
+        self._lib.dhmc_chain_status(self._h, L.ptr(st))
+        return st
+
+    @property
+    def transition_count(self):
+        t = C.c_uint32()
+        self._ck(self._lib.dhmc_get_transition_count(self._h, C.byref(t)))
+        return t.value
+
+    @transition_count.setter
+    def transition_count(self, t):
+        self._ck(self._lib.dhmc_set_transition_count(self._h, C.c_uint32(t)))
+
+    # -- fine-grained path
+    def leapfrog(self, n_steps=1, sign=1):
+        self._ck(self._lib.dhmc_leapfrog(self._h, C.c_int32(n_steps), C.c_int32(sign)))
+
+    def phase_logdensity(self):
+        out = np.empty(self.K)
+        self._ck(self._lib.dhmc_phase_logdensity(self._h, L.ptr(out)))
+        return out
+
+    def sample_tree(self, p=None, directions=None):
+        stats = np.zeros(self.K, dtype=L.tree_stats_dtype)
+        pp = None if p is None else self._kd(p, "p")
+        dd = None if directions is None else np.ascontiguousarray(directions, dtype=np.uint32)
+        self._ck(self._lib.dhmc_sample_tree(self._h, L.ptr(pp), L.ptr(dd), L.ptr(stats)))
+        return stats
+
+    # -- coarse path
+    def find_initial_stepsize(self, search: InitialStepsizeSearch = None):
+        s = search or InitialStepsizeSearch()
+        self._ck(self._lib.dhmc_find_initial_stepsize(self._h, C.c_double(s.initial_ϵ),
+                                                      C.c_double(s.log_threshold),
+                                                      C.c_int32(s.maxiter_crossing)))
+
+    def warmup_stage(self, stage: TuningNUTS, keep=False):
+        if stage.M == Symmetric:
+            raise ArgumentError("dense (Symmetric) metric adaptation is not built yet (DESIGN.md, scope)")
+        K, D, N = self.K, self.D, stage.N
+        post = np.empty((K, N, D)) if keep else None
+        stats = np.zeros((K, N), dtype=L.tree_stats_dtype) if keep else None
+        eps = np.empty((K, N)) if keep else None
+        ld = np.empty((K, N)) if keep else None
+        da = None
+        if isinstance(stage.stepsize_adaptation, DualAveraging):
+            a = stage.stepsize_adaptation
+            da = C.byref(L.DualAveragingC(a.δ, a.γ, a.κ, a.t0, 0))
+        metric = L.METRIC_DIAGONAL if stage.M == Diagonal else L.METRIC_NOTHING
+        self._ck(self._lib.dhmc_warmup_stage(self._h, C.c_int32(N), C.c_int32(metric), da,
+                                             C.c_double(stage.λ), L.ptr(post), L.ptr(stats),
+                                             L.ptr(eps), L.ptr(ld)))
+        if keep:
+            return dict(posterior_matrix=post, tree_statistics=stats, ϵs=eps, logdensities=ld)
+        return None
+
+    def mcmc(self, N, keep_draws=True):
+        K, D = self.K, self.D
+        post = np.empty((K, N, D)) if keep_draws else None
+        stats = np.zeros((K, N), dtype=L.tree_stats_dtype)
+        ld = np.empty((K, N))
+        self._ck(self._lib.dhmc_mcmc(self._h, C.c_int32(N), L.ptr(post), L.ptr(stats), L.ptr(ld)))
+        return dict(posterior_matrix=post, tree_statistics=stats, logdensities=ld)
+
+    def mcmc_dev(self, N, posterior_ptr=0, stats_ptr=0, logdens_ptr=0):
+        """Device-pointer variant: draws stay in HBM (e.g. torch tensors' data_ptr())."""
+        self._ck(self._lib.dhmc_mcmc_dev(self._h, C.c_int32(N), C.c_void_p(posterior_ptr or None),
+                                         C.c_void_p(stats_ptr or None), C.c_void_p(logdens_ptr or None)))
+
+    # -- measurement hooks
+    def last_total_steps(self):
+        v = C.c_int64()
+        self._ck(self._lib.dhmc_last_total_steps(self._h, C.byref(v)))
+        return v.value
+
+    def last_kernel_ms(self):
+        v = C.c_double()
+        self._ck(self._lib.dhmc_last_kernel_ms(self._h, C.byref(v)))
+        return v.value
+
+    def kernel_launches(self):
+        v = C.c_int64()
+        self._ck(self._lib.dhmc_kernel_launches(self._h, C.byref(v)))
+        return v.value
+
+
+# ------------------------------------------------------------------ results
+class Results(Sequence):
+    """results[k] is the reference's NamedTuple for chain k; the [D, N, K]
+    column-major buffer is shared (zero-copy views)."""
+
+    def __init__(self, post, stats, logd, minv, eps):
+        self._post, self._stats, self._logd, self._minv, self._eps = post, stats, logd, minv, eps
+
+    def __len__(self):
+        return self._post.shape[0]
+
+    def __getitem__(self, k):
+        return dict(posterior_matrix=self._post[k].T,       # [D, N] view, mcmc.jl:230
+                    tree_statistics=self._stats[k], logdensities=self._logd[k],
+                    κ=GaussianKineticEnergy(self._minv[k]), ϵ=float(self._eps[k]))
+
+
+def stack_posterior_matrices(results: Results):
+    """[draw, chain, parameter] view — src/mcmc.jl:602-604"""
+    return results._post.transpose(1, 0, 2)
+
+
+def pool_posterior_matrices(results: Results):
+    """[parameter, draw ⊗ chain] — src/mcmc.jl:614-616"""
+    K, N, D = results._post.shape
+    return results._post.reshape(K * N, D).T
+
+
+# ------------------------------------------------------------------ drivers
+def _initialize(engine: Engine, initialization):
+    """initialize_warmup_state — src/mcmc.jl:129-132"""
+    init = dict(initialization or {})
+    unknown = set(init) - {"q", "κ", "ϵ"}
+    _argcheck(not unknown, f"unknown initialization fields {unknown}")
+    if init.get("κ") is not None:
+        engine.set_metric(init["κ"].minv)
+    if init.get("q") is not None:
+        q = np.asarray(init["q"], float)
+        if q.ndim == 1:
+            q = np.broadcast_to(q, (engine.K, engine.D))
+        engine.set_position(q)
+    else:
+        engine.random_position()
+    if init.get("ϵ") is not None:
+        engine.set_stepsize(init["ϵ"])
+
+
+def mcmc_keep_warmup(seed, ℓ, N, chains=1, initialization=None, warmup_stages=None,
+                     algorithm=None, keep_warmup=True, device=0, chain_offset=0, engine_opts=None):
+    """src/mcmc.jl:521-532 for `chains` chains at once."""
+    stages = default_warmup_stages() if warmup_stages is None else warmup_stages
+    eng = Engine(ℓ, chains, seed=seed, algorithm=algorithm, device=device, chain_offset=chain_offset,
+                 **(engine_opts or {}))
+    _initialize(eng, initialization)
+    warm = []
+    for stage in stages:                                     # _warmup fold, mcmc.jl:450-457
+        if stage is None:                                    # no-op stage, mcmc.jl:99-101
+            warm.append(dict(stage=None, results=None))
+        elif isinstance(stage, InitialStepsizeSearch):
+            eng.find_initial_stepsize(stage)
+            warm.append(dict(stage=stage, results=None))
+        elif isinstance(stage, TuningNUTS):
+            warm.append(dict(stage=stage, results=eng.warmup_stage(stage, keep=keep_warmup)))
+        else:
+            raise ArgumentError(f"unknown warmup stage {stage!r}")
+    inf = eng.mcmc(N)
+    st = eng.get_state(("minv", "eps"))
+    results = Results(inf["posterior_matrix"], inf["tree_statistics"], inf["logdensities"],
+                      st["minv"], st["eps"])
+    return dict(warmup=warm, inference=results, engine=eng)
+
+
+def mcmc_with_warmup(seed, ℓ, N, chains=1, initialization=None, warmup_stages=None, algorithm=None,
+                     device=0, chain_offset=0, engine_opts=None):
+    """src/mcmc.jl:575-584 for `chains` chains at once → Results."""
+    r = mcmc_keep_warmup(seed, ℓ, N, chains=chains, initialization=initialization,
+                         warmup_stages=warmup_stages, algorithm=algorithm, keep_warmup=False,
+                         device=device, chain_offset=chain_offset, engine_opts=engine_opts)
+    r["engine"].close()
+    return r["inference"]

@@ -1,0 +1,343 @@
+// device_backend.cuh — sm_100a vector backend of the NUTS state machine.
+//
+// One chain = one chain group of T = 32·W threads (= one CTA).  Element i of
+// every D-vector belongs to thread (i mod T), register slot e = i div T, so a
+// vector is EPL doubles per thread, HBM accesses of a chain row are fully
+// coalesced, shared-memory slot accesses are conflict-free, and — because the
+// owner of an element never changes — slot traffic needs NO synchronisation:
+// the only cross-thread communication is the scalar all-reduce below.
+//
+// The current phase point (q, p, ∇ℓ), the metric diagonal and the running
+// momentum sum ρ of the incoming subtree live in registers for the whole run of
+// a chain; the tree's other vectors live in "slots": the first n_sm in shared
+// memory, the rest in a per-CTA global scratch arena that stays L2-resident.
+//
+// Replaces (reference, tpapp/DynamicHMC.jl v3.6.0):
+//   leapfrog hamiltonian.jl:273-282, evaluate_ℓ :202-217, logdensity :251-256,
+//   kinetic_energy :103, calculate_p♯ :110, rand_p :124,
+//   combine_turn_statistics NUTS.jl:132-139 (the six dot products),
+//   sample_M⁻¹(Diagonal) mcmc.jl:209 (streaming form).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/dhmc_models.h"
+#include "nuts_machine.cuh"
+
+namespace dhmc {
+
+constexpr int kRedWidth = 8;   // values per cross-warp exchange row
+constexpr int kMaxWarps = 8;   // T <= 256
+
+struct SmemLayout {
+  int red_off;    // doubles: [2][kMaxWarps][kRedWidth]
+  int ctl_off;    // bytes from base: Entry[W][kMaxLevels+1]
+  int misc_off;   // bytes: int[4]
+  int slots_off;  // bytes
+  size_t total;   // bytes
+};
+__host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride) {
+  SmemLayout L;
+  size_t off = 0;
+  L.red_off = 0;
+  off += sizeof(double) * 2 * kMaxWarps * kRedWidth;
+  L.ctl_off = (int)off;
+  off += sizeof(Entry) * (size_t)W * (kMaxLevels + 1);
+  off = (off + 15) & ~(size_t)15;
+  L.misc_off = (int)off;
+  off += 16;
+  L.slots_off = (int)off;
+  off += sizeof(double) * stride * (size_t)n_sm;
+  L.total = off;
+  return L;
+}
+
+template <int EPL, int FAM>
+struct DeviceBackend {
+  // geometry
+  int tid, lane, warp, W, T, D;
+  long chain;            // local chain index
+  // registers
+  double q[EPL], p[EPL], g[EPL], minv[EPL], rhoL[EPL];
+  double lq;
+  // memory
+  double* red; int red_buf;
+  Entry* ctl;
+  double* sm_slots; double* gl_slots; int n_sm; size_t stride;
+  const double* mparams;
+  int n_slots;
+
+  __device__ __forceinline__ bool valid(int e) const { return tid + e * T < D; }
+  __device__ __forceinline__ double* slot(int s) const {
+    return (s < n_sm ? sm_slots + (size_t)s * stride : gl_slots + (size_t)(s - n_sm) * stride) + tid;
+  }
+
+  // ---- scalar all-reduce in the canonical order: lane butterfly
+  // xor 1,2,4,8,16, then a pairwise tree over warps.
+  template <int N>
+  __device__ __forceinline__ void reduce(double (&v)[N]) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+#pragma unroll
+      for (int n = 0; n < N; ++n) v[n] = v[n] + __shfl_xor_sync(0xffffffffu, v[n], off);
+    }
+    if (W > 1) {
+      double* buf = red + red_buf * (kMaxWarps * kRedWidth);
+      red_buf ^= 1;
+      if (lane == 0) {
+#pragma unroll
+        for (int n = 0; n < N; ++n) buf[warp * kRedWidth + n] = v[n];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        const double* b = buf + n;
+        if (W == 2) {
+          v[n] = b[0] + b[kRedWidth];
+        } else if (W == 4) {
+          v[n] = (b[0] + b[kRedWidth]) + (b[2 * kRedWidth] + b[3 * kRedWidth]);
+        } else {
+          v[n] = ((b[0] + b[kRedWidth]) + (b[2 * kRedWidth] + b[3 * kRedWidth])) +
+                 ((b[4 * kRedWidth] + b[5 * kRedWidth]) + (b[6 * kRedWidth] + b[7 * kRedWidth]));
+        }
+      }
+    }
+  }
+
+  // ---- interface used by NutsMachine ----
+  __device__ __forceinline__ uint64_t reserved_mask() const {
+    return (1ull << (n_slots - 1)) | (1ull << (n_slots - 2));   // Welford mean / M2
+  }
+  __device__ __forceinline__ double cur_lq() const { return lq; }
+  __device__ __forceinline__ void set_cur_lq(double v) { lq = v; }
+
+#define DHMC_ST(name, src)                                   \
+  __device__ __forceinline__ void name(int s) {              \
+    double* d = slot(s);                                     \
+    _Pragma("unroll") for (int e = 0; e < EPL; ++e) d[e * T] = src[e]; \
+  }
+#define DHMC_LD(name, dst)                                   \
+  __device__ __forceinline__ void name(int s) {              \
+    const double* d = slot(s);                               \
+    _Pragma("unroll") for (int e = 0; e < EPL; ++e) dst[e] = d[e * T]; \
+  }
+  DHMC_ST(st_q, q) DHMC_ST(st_p, p) DHMC_ST(st_g, g) DHMC_ST(st_rho, rhoL)
+  DHMC_LD(ld_q, q) DHMC_LD(ld_p, p) DHMC_LD(ld_g, g)
+#undef DHMC_ST
+#undef DHMC_LD
+
+  __device__ __forceinline__ void swap_cur(int sq, int sp, int sg) {
+    double* dq = slot(sq); double* dp = slot(sp); double* dg = slot(sg);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      double a = dq[e * T]; dq[e * T] = q[e]; q[e] = a;
+      double b = dp[e * T]; dp[e * T] = p[e]; p[e] = b;
+      double c = dg[e * T]; dg[e * T] = g[e]; g[e] = c;
+    }
+  }
+  // ρ of a leaf is its momentum; merge_check reads p directly for leaves and
+  // writes the combined ρ into rhoL (dead if the merge turns), so these are no-ops.
+  __device__ __forceinline__ void rho_from_p() {}
+  __device__ __forceinline__ void rho_commit() {}
+
+  __device__ __forceinline__ void put_entry(int j, const Entry& e) {
+    __syncwarp();
+    if (lane == 0) ctl[j] = e;
+    __syncwarp();
+  }
+  __device__ __forceinline__ Entry get_entry(int j) const { return ctl[j]; }
+
+  // rand_p — hamiltonian.jl:124: W * randn(D), W = Diagonal(sqrt.(inv.(diag M⁻¹))) (:80)
+  __device__ __forceinline__ void draw(dm_rng_key key, uint32_t stream, uint32_t t,
+                                       const double* p_override) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int i = tid + e * T;
+      double v = 0.0;
+      if (i < D) {
+        if (p_override) v = p_override[(size_t)chain * D + i];
+        else v = dm_sqrt(1.0 / minv[e]) * dm_normal_elem(key, stream, t, (uint32_t)i);
+      }
+      p[e] = v;
+    }
+  }
+  __device__ __forceinline__ void draw_momentum(dm_rng_key key, uint32_t t, const double* po) {
+    draw(key, DHMC_STREAM_P, t, po);
+  }
+  __device__ __forceinline__ void draw_search_momentum(dm_rng_key key, const double* po) {
+    draw(key, DHMC_STREAM_PSEARCH, 0, po);
+  }
+
+  __device__ __forceinline__ double kinetic_partial() const {
+    double acc = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      double ps = minv[e] * p[e];
+      acc = acc + p[e] * ps;
+    }
+    return acc;
+  }
+  __device__ __forceinline__ static double hamiltonian_logdensity(double l, double ksum) {
+    if (!dm_isfinite(l)) return -dm_inf();          // hamiltonian.jl:253
+    double K = ksum / 2.0;                          // :103
+    return l - (dm_isfinite(K) ? K : dm_inf());     // :255
+  }
+  // logdensity(H, z) for the current point — hamiltonian.jl:251-256
+  __device__ __forceinline__ double phase_logdensity() {
+    double r[1] = {kinetic_partial()};
+    reduce(r);
+    return hamiltonian_logdensity(lq, r[0]);
+  }
+
+  // evaluate_ℓ sanitising — hamiltonian.jl:205-211 (non-strict)
+  __device__ __forceinline__ static double sanitise(double l, bool gbad) {
+    if ((dm_isfinite(l) && !gbad) || l == -dm_inf()) return l;
+    return -dm_inf();
+  }
+
+  // Model evaluation at the current q: fills g, sets lq (sanitised).  If
+  // `with_p`, also performs the second momentum half-step p += h·∇ℓ(q′) and
+  // returns Σ p·(M⁻¹p) through *ksum (fused into the same reductions).
+  // flags bit0: non-finite q (reference throws, hamiltonian.jl:203), bit1: bad gradient,
+  // bit2: ℓq was replaced by −Inf (what `strict` turns into an error, :212-215).
+  __device__ __forceinline__ void eval_model(bool with_p, double h, double qbad_in, double* ksum,
+                                             int* flags) {
+    if (FAM == DHMC_FAMILY_FUNNEL) {
+      double r1[3] = {0.0, 0.0, qbad_in};
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        r1[0] = r1[0] + dhmc_funnel_term(i, q[e]);
+        if (i == 0) r1[1] = q[e];
+      }
+      reduce(r1);
+      const double S = r1[0], v = r1[1];
+      const double ev = dm_exp(-v);
+      double r2[2] = {0.0, 0.0};
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        double ge = 0.0;
+        if (i < D) {
+          ge = dhmc_funnel_grad(i, q[e], v, ev, S, D);
+          if (!dm_isfinite(ge)) r2[1] = 1.0;
+        }
+        g[e] = ge;
+        if (with_p) {
+          p[e] = p[e] + h * ge;
+          double ps = minv[e] * p[e];
+          r2[0] = r2[0] + p[e] * ps;
+        }
+      }
+      reduce(r2);
+      double l = dhmc_funnel_lq(v, ev, S, D);
+      if (!((dm_isfinite(l) && r2[1] == 0.0) || l == -dm_inf())) *flags |= 4;
+      l = sanitise(l, r2[1] != 0.0);
+      if (r1[2] != 0.0) { *flags |= 1; l = -dm_inf(); }
+      if (r2[1] != 0.0) *flags |= 2;
+      lq = l;
+      *ksum = r2[0];
+    } else {
+      double r[4] = {0.0, 0.0, qbad_in, 0.0};   // Σ term, Σ p·p♯, bad q, bad ∇ℓ
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        double ge;
+        if (FAM == DHMC_FAMILY_STD_NORMAL) {
+          r[0] = r[0] + dhmc_std_term(q[e]);
+          ge = dhmc_std_grad(q[e]);
+        } else {
+          double mu = 0.0, pr = 0.0;
+          if (i < D) { mu = __ldg(mparams + i); pr = __ldg(mparams + D + i); }
+          const double tt = dhmc_diag_scaled(q[e], mu, pr);
+          r[0] = r[0] + dhmc_diag_term(q[e], mu, tt);
+          ge = dhmc_diag_grad(tt);
+        }
+        if (i < D && !dm_isfinite(ge)) r[3] = 1.0;
+        g[e] = ge;
+        if (with_p) {
+          p[e] = p[e] + h * ge;
+          double ps = minv[e] * p[e];
+          r[1] = r[1] + p[e] * ps;
+        }
+      }
+      reduce(r);
+      double l = (FAM == DHMC_FAMILY_STD_NORMAL) ? dhmc_std_lq(r[0]) : dhmc_diag_lq(r[0]);
+      if (!((dm_isfinite(l) && r[3] == 0.0) || l == -dm_inf())) *flags |= 4;
+      l = sanitise(l, r[3] != 0.0);
+      if (r[2] != 0.0) { *flags |= 1; l = -dm_inf(); }
+      if (r[3] != 0.0) *flags |= 2;
+      lq = l;
+      *ksum = r[1];
+    }
+  }
+
+  // leapfrog(H, z, ϵ) — hamiltonian.jl:273-282, then logdensity(H, z′).
+  __device__ __forceinline__ double leapfrog(double eps, int* flags) {
+    const double h = eps / 2;
+    double qbad = 0.0;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      p[e] = p[e] + h * g[e];                 // pₘ = p + ϵ/2 * ∇ℓq        :277
+      const double vel = minv[e] * p[e];      // ∇kinetic_energy = M⁻¹ pₘ  :117
+      q[e] = q[e] + eps * vel;                // q′ = q + ϵ * (…)           :278
+      if (!dm_isfinite(q[e])) qbad = 1.0;
+    }
+    double ksum;
+    eval_model(true, h, qbad, &ksum, flags);  // Q′ = evaluate_ℓ; p′ = pₘ + ϵ/2 ∇ℓq′  :279-280
+    return hamiltonian_logdensity(lq, ksum);
+  }
+
+  // The six dot products of combine_turn_statistics (NUTS.jl:130-139) in build
+  // order; leaves the combined ρ in rhoL.  Returns true when turning.
+  __device__ __forceinline__ bool merge_check(int sEf, int sEl, int sEr, int sLf, bool L_leaf) {
+    const double* pEf = slot(sEf);
+    const double* pEl = slot(sEl);
+    const double* pEr = slot(sEr);
+    const double* pLf = L_leaf ? pEf : slot(sLf);
+    const bool e_leaf = (sEl == sEf);
+    double d[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const double Ef = pEf[e * T];
+      const double El = e_leaf ? Ef : pEl[e * T];
+      const double Er = e_leaf ? Ef : pEr[e * T];
+      const double Lf = L_leaf ? p[e] : pLf[e * T];
+      const double Lr = L_leaf ? p[e] : rhoL[e];
+      const double A = Er + Lf, Bv = El + Lr, R = Er + Lr;
+      const double mEf = minv[e] * Ef, mLf = minv[e] * Lf, mEl = minv[e] * El, mLl = minv[e] * p[e];
+      d[0] = d[0] + mEf * A;  d[1] = d[1] + mLf * A;
+      d[2] = d[2] + mEl * Bv; d[3] = d[3] + mLl * Bv;
+      d[4] = d[4] + mEf * R;  d[5] = d[5] + mLl * R;
+      rhoL[e] = R;
+    }
+    reduce(d);
+    return d[0] < 0 || d[1] < 0 || d[2] < 0 || d[3] < 0 || d[4] < 0 || d[5] < 0;
+  }
+
+  // streaming window variance (Welford) — sample_M⁻¹(Diagonal, X), mcmc.jl:209
+  __device__ __forceinline__ void welford_reset() {
+    double* m = slot(n_slots - 1); double* s = slot(n_slots - 2);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) { m[e * T] = 0.0; s[e * T] = 0.0; }
+  }
+  __device__ __forceinline__ void welford_push(int n) {
+    double* m = slot(n_slots - 1); double* s = slot(n_slots - 2);
+    const double dn = (double)n;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const double mean = m[e * T];
+      const double dlt = q[e] - mean;
+      const double mean1 = mean + dlt / dn;
+      m[e * T] = mean1;
+      s[e * T] = s[e * T] + dlt * (q[e] - mean1);
+    }
+  }
+  __device__ __forceinline__ void welford_finish(int n) {
+    const double* s = slot(n_slots - 2);
+    const double dn1 = (double)(n - 1);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) minv[e] = valid(e) ? s[e * T] / dn1 : 1.0;
+  }
+};
+
+}  // namespace dhmc

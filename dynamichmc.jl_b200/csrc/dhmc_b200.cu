@@ -1,0 +1,768 @@
+// dhmc_b200.cu — sm_100a kernels and the C ABI (include/dhmc.h) of the
+// many-chain NUTS engine.  Build: see csrc/Makefile (nvcc -fmad=false, sm_100a).
+//
+// Kernels (one chain group of T threads = one CTA; persistent, chains pulled
+// from an atomic queue so that ragged tree depths balance across SMs):
+//   k_nuts      sample_tree / warmup(::TuningNUTS) / mcmc     NUTS.jl:232-241, mcmc.jl:258-286,366-381
+//   k_search    warmup(::InitialStepsizeSearch)               mcmc.jl:134-148, stepsize.jl:46-85
+//   k_leapfrog  leapfrog (streaming, HBM-bound)               hamiltonian.jl:273-282
+//   k_eval      evaluate_ℓ(strict) / random_position          hamiltonian.jl:202-217, mcmc.jl:108
+//   k_phase     logdensity(H, z)                              hamiltonian.jl:251-256
+//
+// There is NO CPU fallback: without a CUDA device dhmc_create fails with
+// DHMC_ECUDA and nothing else can be called.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/dhmc.h"
+#include "device_backend.cuh"
+
+using namespace dhmc;
+
+// ------------------------------------------------------------------ kernel args
+struct KArgs {
+  int D, B, T, W;
+  unsigned long long seed;
+  long long chain_offset;
+  double *q, *g, *lq, *p, *minv, *eps;
+  const double* mparams;
+  int* status;
+  int max_depth;
+  double min_delta;
+  unsigned t0;
+  int N;
+  AdaptConfig cfg;
+  const double* p_override;
+  const unsigned* dir_override;
+  double* out_q;
+  dhmc_tree_stats* out_stats;
+  double* out_lq;
+  double* out_eps;
+  double* scratch;
+  size_t scratch_per_cta;  // doubles
+  int n_sm, n_slots;
+  size_t stride;
+  unsigned* counter;
+  unsigned long long* total_steps;
+  double s_init, s_thresh;
+  int s_maxiter;
+  int lf_steps, lf_sign;
+  int strict, randomize;
+  double* out_phase;
+};
+
+template <int EPL, int FAM>
+__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM>& b, const KArgs& a,
+                                              unsigned char* smem) {
+  b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5;
+  b.W = a.W; b.T = a.T; b.D = a.D;
+  const SmemLayout L = smem_layout(a.W, a.n_sm, a.stride);
+  b.red = reinterpret_cast<double*>(smem + L.red_off);
+  b.red_buf = 0;
+  b.ctl = reinterpret_cast<Entry*>(smem + L.ctl_off) + b.warp * (kMaxLevels + 1);
+  b.sm_slots = reinterpret_cast<double*>(smem + L.slots_off);
+  b.gl_slots = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
+  b.n_sm = a.n_sm; b.stride = a.stride; b.n_slots = a.n_slots;
+  b.mparams = a.mparams;
+}
+
+__device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc) {
+  __syncthreads();
+  if (threadIdx.x == 0) s_misc[0] = (int)atomicAdd(counter, 1u);
+  __syncthreads();
+  return s_misc[0];
+}
+
+template <int EPL, int FAM>
+__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM>& b, const KArgs& a, long c,
+                                           bool with_p) {
+  b.chain = c;
+  const size_t base = (size_t)c * a.D;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int i = b.tid + e * b.T;
+    const bool ok = i < a.D;
+    b.q[e] = ok ? a.q[base + i] : 0.0;
+    b.g[e] = ok ? a.g[base + i] : 0.0;
+    b.minv[e] = ok ? a.minv[base + i] : 1.0;
+    b.p[e] = (ok && with_p) ? a.p[base + i] : 0.0;
+    b.rhoL[e] = 0.0;
+  }
+  b.lq = a.lq[c];
+}
+template <int EPL, int FAM>
+__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM>& b, double* dst,
+                                          const double (&v)[EPL], size_t base, int D) {
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int i = b.tid + e * b.T;
+    if (i < D) dst[base + i] = v[e];
+  }
+}
+
+// ------------------------------------------------------------------ k_nuts
+template <int EPL, int FAM>
+struct DrawSink {
+  DeviceBackend<EPL, FAM>& b;
+  const KArgs& a;
+  long c;
+  __device__ __forceinline__ void operator()(int n, const dhmc_tree_stats& ts, double e) {
+    const size_t row = (size_t)c * a.N + n;
+    if (a.out_q) store_vec(b, a.out_q, b.q, row * a.D, a.D);
+    if (b.tid == 0) {
+      if (a.out_stats) a.out_stats[row] = ts;
+      if (a.out_lq) a.out_lq[row] = b.lq;
+      if (a.out_eps) a.out_eps[row] = e;
+    }
+  }
+};
+
+template <int EPL, int FAM>
+__global__ void __launch_bounds__(256) k_nuts(const KArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  DeviceBackend<EPL, FAM> b;
+  setup_backend(b, a, smem);
+  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(a.W, a.n_sm, a.stride).misc_off);
+  for (;;) {
+    const int c = next_chain(a.counter, s_misc);
+    if (c >= a.B) break;
+    load_chain(b, a, c, false);
+    NutsMachine<DeviceBackend<EPL, FAM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+                                           a.max_depth, a.min_delta, a.n_slots);
+    DrawSink<EPL, FAM> sink{b, a, c};
+    const double eps_next = m.run(a.t0, a.N, a.eps[c], a.cfg, a.p_override,
+                                  a.dir_override ? a.dir_override + c : nullptr, sink);
+    const size_t base = (size_t)c * a.D;
+    store_vec(b, a.q, b.q, base, a.D);
+    store_vec(b, a.g, b.g, base, a.D);
+    if (a.cfg.metric != DHMC_METRIC_NOTHING) store_vec(b, a.minv, b.minv, base, a.D);
+    if (b.tid == 0) {
+      a.lq[c] = b.lq;
+      a.eps[c] = eps_next;
+      if (m.status) atomicOr(a.status + c, m.status);
+      atomicAdd(a.total_steps, (unsigned long long)m.steps_out);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k_search
+template <int EPL, int FAM>
+__global__ void __launch_bounds__(256) k_search(const KArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  DeviceBackend<EPL, FAM> b;
+  setup_backend(b, a, smem);
+  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(a.W, a.n_sm, a.stride).misc_off);
+  for (;;) {
+    const int c = next_chain(a.counter, s_misc);
+    if (c >= a.B) break;
+    load_chain(b, a, c, false);
+    NutsMachine<DeviceBackend<EPL, FAM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+                                           a.max_depth, a.min_delta, a.n_slots);
+    const double eps = m.find_initial_stepsize(a.s_init, a.s_thresh, a.s_maxiter, a.p_override);
+    if (b.tid == 0) {
+      a.eps[c] = eps;
+      if (m.status) atomicOr(a.status + c, m.status);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ k_leapfrog
+// Streaming leapfrog: reads q, p, ∇ℓ, M⁻¹ (32·D B), writes q′, p′, ∇ℓ′ (24·D B).
+template <int EPL, int FAM>
+__global__ void __launch_bounds__(256) k_leapfrog(const KArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  DeviceBackend<EPL, FAM> b;
+  setup_backend(b, a, smem);
+  for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
+    load_chain(b, a, c, true);
+    const double eps = a.lf_sign >= 0 ? a.eps[c] : -a.eps[c];
+    int flags = 0;
+    for (int s = 0; s < a.lf_steps; ++s) (void)b.leapfrog(eps, &flags);
+    const size_t base = (size_t)c * a.D;
+    store_vec(b, a.q, b.q, base, a.D);
+    store_vec(b, a.p, b.p, base, a.D);
+    store_vec(b, a.g, b.g, base, a.D);
+    if (b.tid == 0) {
+      a.lq[c] = b.lq;
+      if (flags & 1) atomicOr(a.status + c, (int)DHMC_CHAIN_NONFINITE_Q);
+    }
+    if (a.W > 1) __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ k_eval
+template <int EPL, int FAM>
+__global__ void __launch_bounds__(256) k_eval(const KArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  DeviceBackend<EPL, FAM> b;
+  setup_backend(b, a, smem);
+  for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
+    load_chain(b, a, c, false);
+    double qbad = 0.0;
+    if (a.randomize) {
+      const dm_rng_key key = dm_make_key(a.seed, (uint64_t)(a.chain_offset + c));
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = b.tid + e * b.T;
+        b.q[e] = i < a.D ? dm_uniform_elem(key, DHMC_STREAM_Q0, 0, (uint32_t)i) * 4 - 2 : 0.0;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) if (!dm_isfinite(b.q[e])) qbad = 1.0;
+    // raw (unsanitised) validity for the strict check, hamiltonian.jl:205-215
+    int flags = 0;
+    double ks;
+    b.eval_model(false, 0.0, qbad, &ks, &flags);
+    const size_t base = (size_t)c * a.D;
+    store_vec(b, a.q, b.q, base, a.D);
+    store_vec(b, a.g, b.g, base, a.D);
+    if (b.tid == 0) {
+      a.lq[c] = b.lq;
+      if (a.strict && (flags & (1 | 4))) atomicOr(a.status + c, (int)DHMC_CHAIN_BAD_INITIAL);
+    }
+    if (a.W > 1) __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------ k_phase
+template <int EPL, int FAM>
+__global__ void __launch_bounds__(256) k_phase(const KArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  DeviceBackend<EPL, FAM> b;
+  setup_backend(b, a, smem);
+  for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
+    load_chain(b, a, c, true);
+    const double H = b.phase_logdensity();
+    if (b.tid == 0) a.out_phase[c] = H;
+    if (a.W > 1) __syncthreads();
+  }
+}
+
+// broadcast a D-vector (or scalar when D == 1) to all chains
+__global__ void k_broadcast(double* dst, const double* src, size_t D, size_t B) {
+  const size_t n = D * B;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i % D];
+}
+__global__ void k_fill(double* dst, double v, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = v;
+}
+
+// ================================================================== host side
+struct dhmc_handle {
+  dhmc_config cfg;
+  int T = 0, W = 0, EPL = 0;
+  size_t stride = 0;
+  int n_slots = 0, n_sm = 0, grid = 0, sm_count = 0, light_grid = 0;
+  size_t smem_bytes = 0, smem_light = 0;
+  size_t scratch_per_cta = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double *q = nullptr, *g = nullptr, *lq = nullptr, *p = nullptr, *minv = nullptr, *eps = nullptr;
+  double* mparams = nullptr;
+  int* status = nullptr;
+  double* scratch = nullptr;
+  unsigned* counter = nullptr;
+  unsigned long long* total_steps = nullptr;
+  uint32_t t = 0;
+  int64_t launches = 0;
+  double last_ms = 0;
+  int64_t last_steps = 0;
+  bool has_position = false, has_eps = false;
+  std::string err;
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e_ = (call);                                                          \
+    if (e_ != cudaSuccess) {                                                          \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+      return e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA;              \
+    }                                                                                 \
+  } while (0)
+
+template <int EPL, class F>
+static int dispatch_f(int fam, F&& f) {
+  switch (fam) {
+    case DHMC_FAMILY_STD_NORMAL: return f(std::integral_constant<int, EPL>{}, std::integral_constant<int, DHMC_FAMILY_STD_NORMAL>{});
+    case DHMC_FAMILY_DIAG_NORMAL: return f(std::integral_constant<int, EPL>{}, std::integral_constant<int, DHMC_FAMILY_DIAG_NORMAL>{});
+    case DHMC_FAMILY_FUNNEL: return f(std::integral_constant<int, EPL>{}, std::integral_constant<int, DHMC_FAMILY_FUNNEL>{});
+  }
+  return DHMC_EARG;
+}
+template <class F>
+static int dispatch(int epl, int fam, F&& f) {
+  switch (epl) {
+    case 1: return dispatch_f<1>(fam, f);
+    case 2: return dispatch_f<2>(fam, f);
+    case 4: return dispatch_f<4>(fam, f);
+    case 8: return dispatch_f<8>(fam, f);
+  }
+  return DHMC_EARG;
+}
+
+enum KernelId { K_NUTS, K_SEARCH, K_LEAPFROG, K_EVAL, K_PHASE };
+
+template <int EPL, int FAM>
+static const void* kernel_ptr(KernelId k) {
+  switch (k) {
+    case K_NUTS: return (const void*)k_nuts<EPL, FAM>;
+    case K_SEARCH: return (const void*)k_search<EPL, FAM>;
+    case K_LEAPFROG: return (const void*)k_leapfrog<EPL, FAM>;
+    case K_EVAL: return (const void*)k_eval<EPL, FAM>;
+    default: return (const void*)k_phase<EPL, FAM>;
+  }
+}
+
+static KArgs base_args(dhmc_handle* h) {
+  KArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.D = (int)h->cfg.dim; a.B = (int)h->cfg.n_chains; a.T = h->T; a.W = h->W;
+  a.seed = h->cfg.seed; a.chain_offset = h->cfg.chain_offset;
+  a.q = h->q; a.g = h->g; a.lq = h->lq; a.p = h->p; a.minv = h->minv; a.eps = h->eps;
+  a.mparams = h->mparams; a.status = h->status;
+  a.max_depth = h->cfg.max_depth; a.min_delta = h->cfg.min_delta;
+  a.t0 = h->t;
+  a.scratch = h->scratch; a.scratch_per_cta = h->scratch_per_cta;
+  a.n_sm = h->n_sm; a.n_slots = h->n_slots; a.stride = h->stride;
+  a.counter = h->counter; a.total_steps = h->total_steps;
+  return a;
+}
+
+// heavy = persistent kernels that use the slot pool (k_nuts, k_search)
+static int launch(dhmc_handle* h, KernelId k, KArgs a, bool timed) {
+  const bool heavy = (k == K_NUTS || k == K_SEARCH);
+  if (!heavy) { a.n_sm = 0; }
+  const size_t smem = heavy ? h->smem_bytes : h->smem_light;
+  const int grid = heavy ? h->grid : h->light_grid;
+  if (heavy) {
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), h->stream));
+    CK(cudaMemsetAsync(h->total_steps, 0, sizeof(unsigned long long), h->stream));
+  }
+  if (timed) CK(cudaEventRecord(h->ev0, h->stream));
+  int rc = dispatch(h->EPL, h->cfg.family, [&](auto E, auto Fm) -> int {
+    constexpr int EPL = decltype(E)::value;
+    constexpr int FAM = decltype(Fm)::value;
+    const void* fn = kernel_ptr<EPL, FAM>(k);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
+    void* params[] = {(void*)&a};
+    e = cudaLaunchKernel(fn, dim3(grid), dim3(h->T), params, smem, h->stream);
+    if (e != cudaSuccess) { h->err = std::string("cudaLaunchKernel: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
+    return DHMC_OK;
+  });
+  if (rc != DHMC_OK) return rc;
+  h->launches += 1;
+  if (timed) {
+    CK(cudaEventRecord(h->ev1, h->stream));
+    CK(cudaEventSynchronize(h->ev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+  }
+  return DHMC_OK;
+}
+
+static int sync_and_check_status(dhmc_handle* h, int mask, const char* what) {
+  CK(cudaStreamSynchronize(h->stream));
+  const size_t B = (size_t)h->cfg.n_chains;
+  std::vector<int> st(B);
+  CK(cudaMemcpy(st.data(), h->status, sizeof(int) * B, cudaMemcpyDeviceToHost));
+  long bad = 0, first = -1;
+  for (size_t i = 0; i < B; ++i)
+    if (st[i] & mask) { if (first < 0) first = (long)i; ++bad; }
+  if (bad) {
+    char buf[256];
+    std::snprintf(buf, sizeof buf, "%s: %ld chain(s) failed (first: local chain %ld, status 0x%x)",
+                  what, bad, first, st[first]);
+    h->err = buf;
+    return DHMC_ENUMERIC;
+  }
+  return DHMC_OK;
+}
+
+static void choose_layout(int64_t D, int req_T, int* T, int* EPL) {
+  if (req_T > 0) {
+    *T = req_T;
+    int e = (int)((D + req_T - 1) / req_T);
+    *EPL = e <= 1 ? 1 : e <= 2 ? 2 : e <= 4 ? 4 : e <= 8 ? 8 : 0;
+    return;
+  }
+  if (D <= 32) { *T = 32; *EPL = 1; }
+  else if (D <= 64) { *T = 32; *EPL = 2; }
+  else if (D <= 128) { *T = 32; *EPL = 4; }
+  else if (D <= 256) { *T = 64; *EPL = 4; }
+  else if (D <= 512) { *T = 128; *EPL = 4; }
+  else if (D <= 1024) { *T = 128; *EPL = 8; }
+  else if (D <= 2048) { *T = 256; *EPL = 8; }
+  else { *T = 0; *EPL = 0; }
+}
+
+extern "C" {
+
+const char* dhmc_last_error(dhmc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+int dhmc_destroy(dhmc_handle* h) {
+  if (!h) return DHMC_OK;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->q); cudaFree(h->g); cudaFree(h->lq); cudaFree(h->p); cudaFree(h->minv); cudaFree(h->eps);
+  cudaFree(h->mparams); cudaFree(h->status); cudaFree(h->scratch); cudaFree(h->counter);
+  cudaFree(h->total_steps);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return DHMC_OK;
+}
+
+int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
+  if (!cfg || !out) { g_create_err = "null argument"; return DHMC_EARG; }
+  *out = nullptr;
+  // @argcheck sites: NUTS.jl:190-191
+  if (!(cfg->max_depth > 0 && cfg->max_depth <= kMaxLevels)) { g_create_err = "0 < max_depth <= 12 (this build)"; return DHMC_EARG; }
+  if (!(cfg->min_delta < 0)) { g_create_err = "min_delta < 0"; return DHMC_EARG; }
+  if (cfg->dim < 1 || cfg->n_chains < 1 || cfg->n_chains > (1ll << 30)) { g_create_err = "dim >= 1, 1 <= n_chains <= 2^30"; return DHMC_EARG; }
+  if (cfg->family < 0 || cfg->family >= DHMC_FAMILY_COUNT) { g_create_err = "unknown family"; return DHMC_EARG; }
+  if (cfg->family == DHMC_FAMILY_FUNNEL && cfg->dim < 2) { g_create_err = "funnel needs dim >= 2"; return DHMC_EARG; }
+  int T = 0, EPL = 0;
+  const int rt = cfg->threads_per_chain;
+  if (rt != 0 && !(rt == 32 || rt == 64 || rt == 128 || rt == 256)) { g_create_err = "threads_per_chain in {0,32,64,128,256}"; return DHMC_EARG; }
+  choose_layout(cfg->dim, rt, &T, &EPL);
+  if (T == 0 || EPL == 0) { g_create_err = "dim too large for this build (dim <= 8 * threads_per_chain <= 2048)"; return DHMC_EARG; }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0") +
+                   " (libdhmc_b200 has no CPU fallback)";
+    return DHMC_ECUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "bad device ordinal"; return DHMC_EARG; }
+  dhmc_handle* h = new dhmc_handle();
+  h->cfg = *cfg; h->T = T; h->W = T / 32; h->EPL = EPL; h->stride = (size_t)T * EPL;
+  h->n_slots = slots_needed(cfg->max_depth);
+  auto fail = [&](int rc) { g_create_err = h->err; dhmc_destroy(h); return rc; };
+#define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return fail(e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA); } } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, cfg->device));
+  h->sm_count = prop.multiProcessorCount;
+  CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreate(&h->ev0));
+  CKC(cudaEventCreate(&h->ev1));
+  const size_t B = (size_t)cfg->n_chains, D = (size_t)cfg->dim;
+  CKC(cudaMalloc(&h->q, sizeof(double) * B * D));
+  CKC(cudaMalloc(&h->g, sizeof(double) * B * D));
+  CKC(cudaMalloc(&h->p, sizeof(double) * B * D));
+  CKC(cudaMalloc(&h->minv, sizeof(double) * B * D));
+  CKC(cudaMalloc(&h->lq, sizeof(double) * B));
+  CKC(cudaMalloc(&h->eps, sizeof(double) * B));
+  CKC(cudaMalloc(&h->status, sizeof(int) * B));
+  CKC(cudaMalloc(&h->counter, sizeof(unsigned)));
+  CKC(cudaMalloc(&h->total_steps, sizeof(unsigned long long)));
+  CKC(cudaMalloc(&h->mparams, sizeof(double) * 2 * D));
+  CKC(cudaMemsetAsync(h->q, 0, sizeof(double) * B * D, h->stream));
+  CKC(cudaMemsetAsync(h->g, 0, sizeof(double) * B * D, h->stream));
+  CKC(cudaMemsetAsync(h->p, 0, sizeof(double) * B * D, h->stream));
+  CKC(cudaMemsetAsync(h->lq, 0, sizeof(double) * B, h->stream));
+  CKC(cudaMemsetAsync(h->eps, 0, sizeof(double) * B, h->stream));
+  CKC(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));
+  CKC(cudaMemsetAsync(h->mparams, 0, sizeof(double) * 2 * D, h->stream));
+  k_fill<<<1024, 256, 0, h->stream>>>(h->minv, 1.0, B * D);   // κ = GaussianKineticEnergy(D), mcmc.jl:130
+  h->launches += 1;
+
+  // ---- plan the persistent kernels: CTAs per SM, on-chip slots, scratch ----
+  const size_t slot_bytes = sizeof(double) * h->stride;
+  const SmemLayout L0 = smem_layout(h->W, 0, h->stride);
+  h->smem_light = L0.total;
+  int reg_ctas = 0;
+  int rc = dispatch(EPL, cfg->family, [&](auto E, auto Fm) -> int {
+    constexpr int EP = decltype(E)::value;
+    constexpr int FA = decltype(Fm)::value;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, k_nuts<EP, FA>, T, L0.total);
+    if (e != cudaSuccess) { h->err = std::string("occupancy query: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
+    return DHMC_OK;
+  });
+  if (rc != DHMC_OK) return fail(rc);
+  if (reg_ctas < 1) { h->err = "kernel does not fit on an SM"; return fail(DHMC_ECUDA); }
+  int ctas = cfg->ctas_per_sm > 0 ? std::min(cfg->ctas_per_sm, reg_ctas) : reg_ctas;
+  const size_t smem_sm = (size_t)prop.sharedMemPerMultiprocessor;        // 228 KB
+  const size_t smem_cta_max = (size_t)prop.sharedMemPerBlockOptin;       // 227 KB
+  size_t per_cta = smem_sm / ctas - 1024;                                 // 1 KB system reservation per CTA
+  if (per_cta > smem_cta_max) per_cta = smem_cta_max;
+  long n_sm = per_cta > L0.total ? (long)((per_cta - L0.total) / slot_bytes) : 0;
+  const int pool = h->n_slots - kWelfordSlots;   // the two highest slots stay in global memory
+  if (n_sm > pool) n_sm = pool;
+  h->n_sm = (int)n_sm;
+  h->smem_bytes = smem_layout(h->W, h->n_sm, h->stride).total;
+  h->grid = (int)std::min<size_t>((size_t)ctas * h->sm_count, B);
+  h->light_grid = (int)std::min<size_t>((size_t)h->sm_count * 16, B);
+  h->scratch_per_cta = (size_t)(h->n_slots - h->n_sm) * h->stride;
+  CKC(cudaMalloc(&h->scratch, sizeof(double) * h->scratch_per_cta * (size_t)h->grid));
+  CKC(cudaStreamSynchronize(h->stream));
+#undef CKC
+  *out = h;
+  return DHMC_OK;
+}
+
+int dhmc_get_layout(dhmc_handle* h, int32_t* T, int32_t* epl) {
+  if (!h) return DHMC_EARG;
+  if (T) *T = h->T;
+  if (epl) *epl = h->EPL;
+  return DHMC_OK;
+}
+
+int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n) {
+  if (!h) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t want = h->cfg.family == DHMC_FAMILY_DIAG_NORMAL ? 2 * (size_t)h->cfg.dim : 0;
+  if (n != want || (want && !params)) { h->err = "dhmc_set_problem: wrong parameter count for this family"; return DHMC_EARG; }
+  if (want) CK(cudaMemcpyAsync(h->mparams, params, sizeof(double) * want, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DHMC_OK;
+}
+
+static int eval_position(dhmc_handle* h, bool randomize) {
+  CK(cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)h->cfg.n_chains, h->stream));
+  KArgs a = base_args(h);
+  a.strict = 1; a.randomize = randomize ? 1 : 0;
+  int rc = launch(h, K_EVAL, a, false);
+  if (rc != DHMC_OK) return rc;
+  h->has_position = true;
+  return sync_and_check_status(h, DHMC_CHAIN_BAD_INITIAL, "initialize_warmup_state: invalid log density or gradient at the initial position");
+}
+
+int dhmc_set_position(dhmc_handle* h, const double* q) {
+  if (!h || !q) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->q, q, sizeof(double) * (size_t)h->cfg.n_chains * h->cfg.dim, cudaMemcpyHostToDevice, h->stream));
+  return eval_position(h, false);
+}
+int dhmc_random_position(dhmc_handle* h) {
+  if (!h) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  return eval_position(h, true);
+}
+
+int dhmc_set_metric(dhmc_handle* h, const double* minv, int broadcast) {
+  if (!h) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t B = (size_t)h->cfg.n_chains, D = (size_t)h->cfg.dim;
+  if (!minv) {
+    k_fill<<<1024, 256, 0, h->stream>>>(h->minv, 1.0, B * D);
+  } else if (broadcast) {
+    double* tmp = nullptr;
+    CK(cudaMalloc(&tmp, sizeof(double) * D));
+    CK(cudaMemcpyAsync(tmp, minv, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+    k_broadcast<<<1024, 256, 0, h->stream>>>(h->minv, tmp, D, B);
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(tmp);
+  } else {
+    CK(cudaMemcpyAsync(h->minv, minv, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
+  }
+  h->launches += 1;
+  CK(cudaStreamSynchronize(h->stream));
+  return DHMC_OK;
+}
+
+int dhmc_set_stepsize(dhmc_handle* h, const double* eps, int broadcast) {
+  if (!h || !eps) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t B = (size_t)h->cfg.n_chains;
+  if (broadcast) {
+    if (!(eps[0] > 0)) { h->err = "ϵ > 0"; return DHMC_EARG; }    // stepsize.jl:135
+    k_fill<<<256, 256, 0, h->stream>>>(h->eps, eps[0], B);
+    h->launches += 1;
+  } else {
+    for (size_t i = 0; i < B; ++i) if (!(eps[i] > 0)) { h->err = "ϵ > 0"; return DHMC_EARG; }
+    CK(cudaMemcpyAsync(h->eps, eps, sizeof(double) * B, cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->has_eps = true;
+  return DHMC_OK;
+}
+
+int dhmc_set_momentum(dhmc_handle* h, const double* p) {
+  if (!h || !p) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpyAsync(h->p, p, sizeof(double) * (size_t)h->cfg.n_chains * h->cfg.dim, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DHMC_OK;
+}
+
+int dhmc_get_state(dhmc_handle* h, double* q, double* lq, double* grad, double* minv, double* eps, double* p) {
+  if (!h) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t B = (size_t)h->cfg.n_chains, D = (size_t)h->cfg.dim;
+  if (q) CK(cudaMemcpyAsync(q, h->q, sizeof(double) * B * D, cudaMemcpyDeviceToHost, h->stream));
+  if (grad) CK(cudaMemcpyAsync(grad, h->g, sizeof(double) * B * D, cudaMemcpyDeviceToHost, h->stream));
+  if (minv) CK(cudaMemcpyAsync(minv, h->minv, sizeof(double) * B * D, cudaMemcpyDeviceToHost, h->stream));
+  if (p) CK(cudaMemcpyAsync(p, h->p, sizeof(double) * B * D, cudaMemcpyDeviceToHost, h->stream));
+  if (lq) CK(cudaMemcpyAsync(lq, h->lq, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+  if (eps) CK(cudaMemcpyAsync(eps, h->eps, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DHMC_OK;
+}
+
+int dhmc_chain_status(dhmc_handle* h, int32_t* status) {
+  if (!h || !status) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpy(status, h->status, sizeof(int) * (size_t)h->cfg.n_chains, cudaMemcpyDeviceToHost));
+  return DHMC_OK;
+}
+int dhmc_get_transition_count(dhmc_handle* h, uint32_t* t) { if (!h || !t) return DHMC_EARG; *t = h->t; return DHMC_OK; }
+int dhmc_set_transition_count(dhmc_handle* h, uint32_t t) { if (!h) return DHMC_EARG; h->t = t; return DHMC_OK; }
+
+int dhmc_leapfrog(dhmc_handle* h, int32_t n_steps, int32_t sign) {
+  if (!h || n_steps < 0) return DHMC_EARG;
+  if (!h->has_position || !h->has_eps) { h->err = "dhmc_leapfrog: set position and step size first"; return DHMC_EARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  KArgs a = base_args(h);
+  a.lf_steps = n_steps; a.lf_sign = sign;
+  int rc = launch(h, K_LEAPFROG, a, true);
+  if (rc != DHMC_OK) return rc;
+  return sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q, "leapfrog: position vector has non-finite elements");
+}
+
+int dhmc_phase_logdensity(dhmc_handle* h, double* out) {
+  if (!h || !out) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t B = (size_t)h->cfg.n_chains;
+  double* d = nullptr;
+  CK(cudaMalloc(&d, sizeof(double) * B));
+  KArgs a = base_args(h);
+  a.out_phase = d;
+  int rc = launch(h, K_PHASE, a, false);
+  if (rc == DHMC_OK) {
+    cudaError_t e = cudaMemcpyAsync(out, d, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = DHMC_ECUDA; }
+  }
+  cudaFree(d);
+  return rc;
+}
+
+int dhmc_find_initial_stepsize(dhmc_handle* h, double initial_eps, double log_threshold, int32_t maxiter) {
+  if (!h) return DHMC_EARG;
+  // InitialStepsizeSearch @argchecks — stepsize.jl:31-33
+  if (!(std::isfinite(log_threshold) && log_threshold < 0)) { h->err = "isfinite(log_threshold) && log_threshold < 0"; return DHMC_EARG; }
+  if (!(std::isfinite(initial_eps) && 0 < initial_eps)) { h->err = "isfinite(initial_ϵ) && 0 < initial_ϵ"; return DHMC_EARG; }
+  if (!(maxiter >= 50)) { h->err = "maxiter_crossing ≥ 50"; return DHMC_EARG; }
+  if (!h->has_position) { h->err = "set the position first"; return DHMC_EARG; }
+  if (h->has_eps) { h->err = "stepsize ϵ manually specified, won't perform initial search"; return DHMC_EARG; }  // mcmc.jl:137
+  CK(cudaSetDevice(h->cfg.device));
+  KArgs a = base_args(h);
+  a.s_init = initial_eps; a.s_thresh = log_threshold; a.s_maxiter = maxiter;
+  int rc = launch(h, K_SEARCH, a, true);
+  if (rc != DHMC_OK) return rc;
+  h->has_eps = true;
+  return sync_and_check_status(h, DHMC_CHAIN_SEARCH_FAILED | DHMC_CHAIN_NONFINITE_Q,
+                               "initial stepsize search failed (no crossing, or non-finite starting density)");
+}
+
+// common driver of sample_tree / warmup stage / mcmc
+static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, const double* p_over_host,
+                    const uint32_t* dir_over_host, double* posterior, dhmc_tree_stats* stats,
+                    double* eps_used, double* logdens, bool outputs_on_device, bool advance_t) {
+  if (!h->has_position || !h->has_eps) { h->err = "set position and step size (or run the initial search) first"; return DHMC_EARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  const size_t B = (size_t)h->cfg.n_chains, D = (size_t)h->cfg.dim, n = (size_t)N;
+  double *d_post = nullptr, *d_eps = nullptr, *d_ld = nullptr, *d_p = nullptr;
+  dhmc_tree_stats* d_stats = nullptr;
+  unsigned* d_dir = nullptr;
+  int rc = DHMC_OK;
+  auto cleanup = [&] {
+    if (!outputs_on_device) { cudaFree(d_post); cudaFree(d_stats); cudaFree(d_eps); cudaFree(d_ld); }
+    cudaFree(d_p); cudaFree(d_dir);
+  };
+#define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA; } } while (0)
+  if (outputs_on_device) {
+    d_post = posterior; d_stats = stats; d_eps = eps_used; d_ld = logdens;
+  } else {
+    if (posterior) CKR(cudaMalloc(&d_post, sizeof(double) * B * n * D));
+    if (stats) CKR(cudaMalloc(&d_stats, sizeof(dhmc_tree_stats) * B * n));
+    if (eps_used) CKR(cudaMalloc(&d_eps, sizeof(double) * B * n));
+    if (logdens) CKR(cudaMalloc(&d_ld, sizeof(double) * B * n));
+  }
+  if (p_over_host) {
+    CKR(cudaMalloc(&d_p, sizeof(double) * B * D));
+    CKR(cudaMemcpyAsync(d_p, p_over_host, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (dir_over_host) {
+    CKR(cudaMalloc(&d_dir, sizeof(unsigned) * B));
+    CKR(cudaMemcpyAsync(d_dir, dir_over_host, sizeof(unsigned) * B, cudaMemcpyHostToDevice, h->stream));
+  }
+  KArgs a = base_args(h);
+  a.N = N; a.cfg = cfg; a.p_override = d_p; a.dir_override = d_dir;
+  a.out_q = d_post; a.out_stats = d_stats; a.out_eps = d_eps; a.out_lq = d_ld;
+  rc = launch(h, K_NUTS, a, true);
+  if (rc != DHMC_OK) { cleanup(); return rc; }
+  unsigned long long steps = 0;
+  CKR(cudaMemcpyAsync(&steps, h->total_steps, sizeof steps, cudaMemcpyDeviceToHost, h->stream));
+  if (!outputs_on_device) {
+    if (posterior) CKR(cudaMemcpyAsync(posterior, d_post, sizeof(double) * B * n * D, cudaMemcpyDeviceToHost, h->stream));
+    if (stats) CKR(cudaMemcpyAsync(stats, d_stats, sizeof(dhmc_tree_stats) * B * n, cudaMemcpyDeviceToHost, h->stream));
+    if (eps_used) CKR(cudaMemcpyAsync(eps_used, d_eps, sizeof(double) * B * n, cudaMemcpyDeviceToHost, h->stream));
+    if (logdens) CKR(cudaMemcpyAsync(logdens, d_ld, sizeof(double) * B * n, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CKR(cudaStreamSynchronize(h->stream));
+#undef CKR
+  cleanup();
+  h->last_steps = (int64_t)steps;
+  if (advance_t) h->t += (uint32_t)N;
+  return sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q | DHMC_CHAIN_BAD_ACCEPTANCE,
+                               "sampling: non-finite position or acceptance rate");
+}
+
+int dhmc_sample_tree(dhmc_handle* h, const double* p, const uint32_t* directions, dhmc_tree_stats* stats) {
+  if (!h) return DHMC_EARG;
+  AdaptConfig cfg{};
+  return run_nuts(h, 1, cfg, p, directions, nullptr, stats, nullptr, nullptr, false, true);
+}
+
+int dhmc_warmup_stage(dhmc_handle* h, int32_t N, int32_t metric, const dhmc_dual_averaging* da,
+                      double lambda, double* posterior, dhmc_tree_stats* stats, double* eps_used,
+                      double* logdens) {
+  if (!h) return DHMC_EARG;
+  // TuningNUTS @argchecks — mcmc.jl:191-192
+  if (!(N >= 20)) { h->err = "N ≥ 20"; return DHMC_EARG; }
+  if (!(lambda >= 0)) { h->err = "λ ≥ 0"; return DHMC_EARG; }
+  if (metric != DHMC_METRIC_NOTHING && metric != DHMC_METRIC_DIAGONAL) { h->err = "metric: Nothing or Diagonal in this build"; return DHMC_EARG; }
+  AdaptConfig cfg{};
+  cfg.metric = metric;
+  if (da) {
+    // DualAveraging @argchecks — stepsize.jl:108-111
+    if (!(0 < da->delta && da->delta < 1) || !(da->gamma > 0) || !(0.5 < da->kappa && da->kappa <= 1) || !(da->t0 >= 0)) {
+      h->err = "DualAveraging: 0 < δ < 1, γ > 0, 0.5 < κ ≤ 1, t₀ ≥ 0"; return DHMC_EARG;
+    }
+    cfg.adapt = 1; cfg.delta = da->delta; cfg.gamma = da->gamma; cfg.kappa = da->kappa; cfg.t0 = da->t0;
+  }
+  return run_nuts(h, N, cfg, nullptr, nullptr, posterior, stats, eps_used, logdens, false, true);
+}
+
+int dhmc_mcmc(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats, double* logdens) {
+  if (!h || N < 0) return DHMC_EARG;
+  if (N == 0) return DHMC_OK;
+  AdaptConfig cfg{};
+  return run_nuts(h, N, cfg, nullptr, nullptr, posterior, stats, nullptr, logdens, false, true);
+}
+int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats, double* logdens) {
+  if (!h || N < 0) return DHMC_EARG;
+  if (N == 0) return DHMC_OK;
+  AdaptConfig cfg{};
+  return run_nuts(h, N, cfg, nullptr, nullptr, posterior, stats, nullptr, logdens, true, true);
+}
+
+int dhmc_last_total_steps(dhmc_handle* h, int64_t* steps) { if (!h || !steps) return DHMC_EARG; *steps = h->last_steps; return DHMC_OK; }
+int dhmc_last_kernel_ms(dhmc_handle* h, double* ms) { if (!h || !ms) return DHMC_EARG; *ms = h->last_ms; return DHMC_OK; }
+int dhmc_kernel_launches(dhmc_handle* h, int64_t* n) { if (!h || !n) return DHMC_EARG; *n = h->launches; return DHMC_OK; }
+
+}  // extern "C"

@@ -39,7 +39,7 @@
 #include "../../include/dhmc_math.h"
 
 #if defined(__CUDACC__)
-#define DHMC_M __host__ __device__ __forceinline__
+#define DHMC_M __device__ __forceinline__
 #else
 #define DHMC_M inline
 #endif
@@ -95,14 +95,14 @@ struct NutsMachine {
   DHMC_M int alloc_lo() {
     uint64_t m = freemask;
     int s = 0;
-    while (!((m >> s) & 1ull)) ++s;  // pool is sized so that a free slot exists
+    while (s < 63 && !((m >> s) & 1ull)) ++s;  // pool is sized so that a free slot exists
     freemask = m & ~(1ull << s);
     return s;
   }
   DHMC_M int alloc_hi() {
     uint64_t m = freemask;
     int s = n_slots - 1;
-    while (!((m >> s) & 1ull)) --s;
+    while (s > 0 && !((m >> s) & 1ull)) --s;
     freemask = m & ~(1ull << s);
     return s;
   }

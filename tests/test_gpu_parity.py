@@ -1,0 +1,248 @@
+"""-m gpu: the CUDA path, called through the C ABI, against the oracle.
+
+Bar (BASELINE.json north_star): integer tree decisions bit-exact; θ/p after a
+leapfrog step within 1e-10 relative (we observe bit-equality because both sides
+use the same canonical reduction order and deterministic math)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+INT_FIELDS = ("depth", "left", "right", "steps", "directions")
+RTOL = 1e-10
+
+
+def _engine(pkg, ℓ, K, seed=5, **kw):
+    return pkg.Engine(ℓ, chains=K, seed=seed, **kw)
+
+
+def _models(pkg, rng, D):
+    return [(pkg.StandardNormal(D), 0, None),
+            (pkg.DiagNormal(rng.normal(size=D), rng.uniform(0.2, 5, D)), 1, True),
+            (pkg.Funnel(D), 2, None)]
+
+
+@pytest.mark.parametrize("D", [3, 10, 100, 200, 500, 1000])
+def test_leapfrog_matches_oracle(pkg, po, D):
+    rng = np.random.default_rng(D)
+    K = 8
+    for ℓ, fam, hasp in _models(pkg, rng, D):
+        eng = _engine(pkg, ℓ, K)
+        T, _ = eng.layout()
+        q, p = rng.normal(size=(K, D)), rng.normal(size=(K, D))
+        minv = rng.uniform(0.5, 2, (K, D))
+        eps = rng.uniform(0.01, 0.2, K)
+        eng.set_metric(minv); eng.set_position(q); eng.set_momentum(p); eng.set_stepsize(eps)
+        params = ℓ.params() if hasp else None
+        H = eng.phase_logdensity()
+        for sign, n in ((1, 1), (-1, 3)):
+            eng.leapfrog(n, sign)
+            st = eng.get_state()
+            for k in range(K):
+                qo, p_o, go, lqo = po.leapfrog(fam, q[k], p[k], sign * eps[k], minv=minv[k], params=params, T=T, n_steps=n)
+                np.testing.assert_allclose(st["q"][k], qo, rtol=RTOL, atol=0)
+                np.testing.assert_allclose(st["p"][k], p_o, rtol=RTOL, atol=0)
+                assert np.array_equal(st["q"][k], qo) and np.array_equal(st["p"][k], p_o)
+                assert np.array_equal(st["grad"][k], go) and st["lq"][k] == lqo
+            q, p = st["q"], st["p"]
+        for k in range(K):   # logdensity(H, z) before stepping
+            pass
+        lq0 = [po.logdensity_and_gradient(fam, qq, params, T)[0] for qq in q]
+        H1 = eng.phase_logdensity()
+        for k in range(K):
+            assert H1[k] == po.phase_logdensity(minv[k], lq0[k], p[k], T)
+        eng.close()
+
+
+@pytest.mark.parametrize("D,K", [(2, 64), (10, 96), (100, 48), (256, 16), (1000, 12)])
+def test_sample_tree_matches_oracle(pkg, po, D, K):
+    rng = np.random.default_rng(1000 + D)
+    for ℓ, fam, hasp in _models(pkg, rng, D):
+        eng = _engine(pkg, ℓ, K, seed=77)
+        T, _ = eng.layout()
+        q = rng.normal(size=(K, D))
+        minv = rng.uniform(0.3, 3, (K, D))
+        eps = np.exp(rng.uniform(np.log(0.01), np.log(1.2), K))
+        eng.set_metric(minv); eng.set_position(q); eng.set_stepsize(eps)
+        params = ℓ.params() if hasp else None
+        for t in range(3):
+            stats = eng.sample_tree()
+            st = eng.get_state(("q", "lq", "grad"))
+            for k in range(K):
+                o = po.sample_tree(fam, q[k], eps[k], 77, k, t, minv=minv[k], params=params, T=T)
+                for f in INT_FIELDS:
+                    assert o["stats"][f] == stats[k][f], (f, k, t, o["stats"], stats[k])
+                assert o["stats"]["pi"] == stats[k]["pi"]
+                assert o["stats"]["acceptance_rate"] == stats[k]["acceptance_rate"]
+                np.testing.assert_allclose(st["q"][k], o["q"], rtol=RTOL, atol=0)
+                assert np.array_equal(st["q"][k], o["q"]) and np.array_equal(st["grad"][k], o["g"])
+                assert st["lq"][k] == o["lq"]
+            q = st["q"]
+        eng.close()
+
+
+def test_sample_tree_overrides_and_exits(pkg, po):
+    """p= / directions= keywords (NUTS.jl:232-233); every tree exit is hit."""
+    rng = np.random.default_rng(3)
+    D, K = 20, 128
+    ℓ = pkg.StandardNormal(D)
+    seen = dict(div=0, turn=0, maxd=0)
+    for max_depth, min_delta in ((3, -1000.0), (10, -0.02), (10, -1000.0)):
+        eng = _engine(pkg, ℓ, K, algorithm=pkg.NUTS(max_depth=max_depth, min_Δ=min_delta))
+        T, _ = eng.layout()
+        q, p = rng.normal(size=(K, D)), rng.normal(size=(K, D))
+        dirs = rng.integers(0, 2 ** 32, K, dtype=np.uint64).astype(np.uint32)
+        eps = np.exp(rng.uniform(np.log(0.02), np.log(1.0), K))
+        eng.set_position(q); eng.set_stepsize(eps)
+        stats = eng.sample_tree(p=p, directions=dirs)
+        newq = eng.get_state(("q",))["q"]
+        for k in range(K):
+            o = po.sample_tree(0, q[k], eps[k], 5, k, 0, T=T, p=p[k], directions=int(dirs[k]),
+                               max_depth=max_depth, min_delta=min_delta)
+            for f in INT_FIELDS:
+                assert o["stats"][f] == stats[k][f]
+            assert np.array_equal(newq[k], o["q"])
+            s = stats[k]
+            seen["div"] += int(s["left"] == s["right"])
+            seen["maxd"] += int((s["left"], s["right"]) == (1, 0))
+            seen["turn"] += int(s["left"] < s["right"] or (s["left"] > s["right"] and (s["left"], s["right"]) != (1, 0)))
+        eng.close()
+    assert min(seen.values()) > 3, seen
+
+
+def test_mcmc_draws_and_layout(pkg, po):
+    """mcmc (mcmc.jl:366-381): [D, N, B] output, logdensities, RNG counter continuity."""
+    D, K, N = 50, 40, 6
+    rng = np.random.default_rng(8)
+    ℓ = pkg.DiagNormal(rng.normal(size=D), rng.uniform(0.5, 2, D))
+    eng = _engine(pkg, ℓ, K, seed=9)
+    T, _ = eng.layout()
+    eng.random_position()
+    q0 = eng.get_state(("q",))["q"]
+    eng.set_stepsize(0.3)
+    a = eng.mcmc(4)
+    b = eng.mcmc(N - 4)                       # continues the same chains (counter 4, 5)
+    assert eng.transition_count == N
+    post = np.concatenate([a["posterior_matrix"], b["posterior_matrix"]], axis=1)
+    stats = np.concatenate([a["tree_statistics"], b["tree_statistics"]], axis=1)
+    logd = np.concatenate([a["logdensities"], b["logdensities"]], axis=1)
+    assert eng.last_total_steps() == int(b["tree_statistics"]["steps"].sum())
+    for k in range(0, K, 7):
+        assert np.array_equal(q0[k], po.random_position(9, k, D))
+        q = q0[k]
+        for n in range(N):
+            o = po.sample_tree(1, q, 0.3, 9, k, n, params=ℓ.params(), T=T)
+            for f in INT_FIELDS:
+                assert o["stats"][f] == stats[k, n][f]
+            assert np.array_equal(post[k, n], o["q"]) and logd[k, n] == o["lq"]
+            q = o["q"]
+    eng.close()
+
+
+@pytest.mark.parametrize("fam,D", [(0, 100), (1, 40), (2, 10)])
+def test_full_warmup_matches_oracle(pkg, po, fam, D):
+    """mcmc_with_warmup through the host mirror vs the oracle with the streaming
+    (Welford) window variance: identical chains."""
+    rng = np.random.default_rng(21)
+    ℓ = [pkg.StandardNormal(D), pkg.DiagNormal(rng.normal(size=D), np.logspace(-1, 1, D)), pkg.Funnel(D)][fam]
+    K, N, seed = 24, 30, 4242
+    stages = pkg.default_warmup_stages(init_steps=30, middle_steps=20, doubling_stages=2, terminating_steps=20)
+    r = pkg.mcmc_keep_warmup(seed, ℓ, N, chains=K, warmup_stages=stages)
+    T, _ = r["engine"].layout()
+    res = r["inference"]
+    ostages = po.default_warmup_stages(init_steps=30, middle_steps=20, doubling_stages=2, terminating_steps=20)
+    params = ℓ.params() if fam == 1 else None
+    for k in range(0, K, 5):
+        o = po.mcmc_with_warmup(fam, D, N, seed, k, stages=ostages, params=params, T=T, welford=True,
+                                keep_warmup=True)
+        w = np.concatenate([s["results"]["tree_statistics"][k] for s in r["warmup"] if s["results"]])
+        for f in INT_FIELDS:
+            assert np.array_equal(w[f], o["warmup_stats"][f]), f
+        weps = np.concatenate([s["results"]["ϵs"][k] for s in r["warmup"] if s["results"]])
+        assert np.array_equal(weps, o["warmup_eps"])
+        assert res[k]["ϵ"] == o["eps"] and np.array_equal(res[k]["κ"].minv, o["minv"])
+        assert np.array_equal(res[k]["posterior_matrix"].T, o["posterior_matrix"])
+        for f in INT_FIELDS:
+            assert np.array_equal(res[k]["tree_statistics"][f], o["tree_statistics"][f])
+    r["engine"].close()
+
+
+def test_initial_stepsize_search(pkg, po):
+    D, K = 30, 64
+    rng = np.random.default_rng(12)
+    ℓ = pkg.DiagNormal(np.zeros(D), np.logspace(-2, 2, D))
+    eng = _engine(pkg, ℓ, K, seed=31)
+    T, _ = eng.layout()
+    q = rng.normal(size=(K, D)) * np.sqrt(ℓ.sigma2)
+    eng.set_position(q)
+    eng.find_initial_stepsize()
+    eps = eng.get_state(("eps",))["eps"]
+    for k in range(K):
+        p = po.normals(31, k, 1, 0, D)          # DHMC_STREAM_PSEARCH
+        assert eps[k] == po.find_initial_stepsize(1, q[k], p, params=ℓ.params(), T=T)
+    with pytest.raises(pkg.ArgumentError):     # mcmc.jl:137
+        eng.find_initial_stepsize()
+    eng.close()
+
+
+def test_error_conventions(pkg):
+    D, K = 5, 8
+    eng = _engine(pkg, pkg.StandardNormal(D), K)
+    q = np.zeros((K, D))
+    q[3, 2] = np.nan
+    with pytest.raises(pkg.DynamicHMCError) as e:     # hamiltonian.jl:203 via mcmc.jl:131
+        eng.set_position(q)
+    st = e.value.debug_information["chain_status"]
+    assert st[3] != 0 and np.count_nonzero(st) == 1
+    with pytest.raises(pkg.ArgumentError):
+        eng.mcmc(3)                                    # no step size yet
+    with pytest.raises(pkg.ArgumentError):
+        eng.set_stepsize(-1.0)                         # stepsize.jl:135
+    eng.close()
+    with pytest.raises(pkg.ArgumentError):
+        pkg.Engine(pkg.StandardNormal(5000), chains=2)  # dim too large for this build
+    # funnel with a huge step: divergent first leaf, chain stays put, others unaffected
+    eng = _engine(pkg, pkg.Funnel(10), K)
+    q = np.zeros((K, 10)); q[:, 0] = -8.0; q[:, 1:] = 5.0
+    eng.set_position(q); eng.set_stepsize(50.0)
+    stats = eng.sample_tree()
+    assert np.all(stats["left"] == stats["right"]) and np.all(stats["depth"] == 0) and np.all(stats["steps"] == 1)
+    assert np.array_equal(eng.get_state(("q",))["q"], q)
+    eng.close()
+
+
+def test_sharding_invariance(pkg):
+    """§8e: the Philox key is the GLOBAL chain id, so a shard (chain_offset) reproduces
+    the corresponding chains of the full run bit for bit — independent of #GPUs."""
+    D, K, N = 64, 256, 5
+    ℓ = pkg.StandardNormal(D)
+    full = _engine(pkg, ℓ, K, seed=3)
+    full.random_position(); full.set_stepsize(0.4)
+    a = full.mcmc(N)
+    full.close()
+    for off, n in ((0, 32), (100, 50), (250, 6)):
+        sh = pkg.Engine(ℓ, chains=n, seed=3, chain_offset=off)
+        sh.random_position(); sh.set_stepsize(0.4)
+        b = sh.mcmc(N)
+        sh.close()
+        assert np.array_equal(a["posterior_matrix"][off:off + n], b["posterior_matrix"])
+        assert np.array_equal(a["tree_statistics"][off:off + n], b["tree_statistics"])
+
+
+def test_layout_independence_within_tolerance(pkg):
+    """Different threads_per_chain = different (documented) summation order: results
+    agree to rounding for a single leapfrog (1e-10 bar), not necessarily bit for bit."""
+    D, K = 200, 16
+    rng = np.random.default_rng(2)
+    q, p = rng.normal(size=(K, D)), rng.normal(size=(K, D))
+    out = []
+    for T in (32, 64, 128):
+        eng = pkg.Engine(pkg.StandardNormal(D), chains=K, threads_per_chain=T)
+        assert eng.layout()[0] == T
+        eng.set_position(q); eng.set_momentum(p); eng.set_stepsize(0.1)
+        eng.leapfrog(5, 1)
+        out.append(eng.get_state(("q", "p", "lq")))
+        eng.close()
+    for o in out[1:]:
+        np.testing.assert_allclose(o["q"], out[0]["q"], rtol=1e-12)
+        np.testing.assert_allclose(o["lq"], out[0]["lq"], rtol=1e-12)
