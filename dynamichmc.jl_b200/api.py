@@ -13,6 +13,7 @@ returns a `Results` whose `[k]` is the reference's NamedTuple for chain k
 """
 import ctypes as C
 import math
+import unicodedata
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
 
@@ -347,7 +348,8 @@ class Engine:
                                              C.c_double(stage.λ), L.ptr(post), L.ptr(stats),
                                              L.ptr(eps), L.ptr(ld)))
         if keep:
-            return dict(posterior_matrix=post, tree_statistics=stats, ϵs=eps, logdensities=ld)
+            return {"posterior_matrix": post, "tree_statistics": stats, "ϵs": eps, "eps_used": eps,
+                    "logdensities": ld}
         return None
 
     def mcmc(self, N, keep_draws=True):
@@ -392,9 +394,11 @@ class Results(Sequence):
         return self._post.shape[0]
 
     def __getitem__(self, k):
-        return dict(posterior_matrix=self._post[k].T,       # [D, N] view, mcmc.jl:230
-                    tree_statistics=self._stats[k], logdensities=self._logd[k],
-                    κ=GaussianKineticEnergy(self._minv[k]), ϵ=float(self._eps[k]))
+        # NB: string keys, not keywords — Python NFKC-normalises identifiers (ϵ → ε)
+        return {"posterior_matrix": self._post[k].T,        # [D, N] view, mcmc.jl:230
+                "tree_statistics": self._stats[k], "logdensities": self._logd[k],
+                "κ": GaussianKineticEnergy(self._minv[k]), "ϵ": float(self._eps[k]),
+                "eps": float(self._eps[k])}
 
 
 def stack_posterior_matrices(results: Results):
@@ -411,7 +415,9 @@ def pool_posterior_matrices(results: Results):
 # ------------------------------------------------------------------ drivers
 def _initialize(engine: Engine, initialization):
     """initialize_warmup_state — src/mcmc.jl:129-132"""
-    init = dict(initialization or {})
+    # keys may arrive as keywords (NFKC-normalised by Python: ϵ → ε) or as strings
+    init = {unicodedata.normalize("NFKC", k): v for k, v in dict(initialization or {}).items()}
+    init = {{"ε": "ϵ", "eps": "ϵ", "kappa": "κ"}.get(k, k): v for k, v in init.items()}
     unknown = set(init) - {"q", "κ", "ϵ"}
     _argcheck(not unknown, f"unknown initialization fields {unknown}")
     if init.get("κ") is not None:

@@ -1,5 +1,7 @@
 // oracle_capi.cpp — flat C entry points over oracle.hpp for ctypes
 // (oracle/pyoracle.py).  TEST INFRASTRUCTURE ONLY — see the header of oracle.hpp.
+#include <malloc.h>
+
 #include <atomic>
 #include <chrono>
 #include <cstring>
@@ -324,6 +326,12 @@ int orc_bench_mcmc(int family, int D, const double* params, int T, int max_depth
                    uint64_t seed, int n_chains, int n_threads, int N, int n_stages, const int* kind,
                    const int* stN, const int* metric, const int* da_on, const double* minv0,
                    const double* eps0, int64_t* total_steps, double* seconds, double* mean_out) {
+  // glibc's per-thread arenas grow/shrink their heaps with mprotect/madvise on this
+  // allocate-and-free-8KB-vectors pattern, which serialises threads on the mm lock;
+  // keep freed memory in the arenas instead (the reference's GC'd heap behaves likewise).
+  mallopt(M_TRIM_THRESHOLD, 1 << 30);
+  mallopt(M_TOP_PAD, 64 << 20);
+  mallopt(M_MMAP_THRESHOLD, 1 << 30);
   std::atomic<int> next{0};
   std::atomic<int64_t> steps{0};
   std::atomic<int> failed{0};
