@@ -51,10 +51,13 @@ __host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride
   return L;
 }
 
-template <int EPL, int FAM>
+template <int EPL, int FAM, int WARPS>
 struct DeviceBackend {
-  // geometry
-  int tid, lane, warp, W, T, D;
+  // geometry: T = 32·WARPS threads per chain, compile-time so that strides fold
+  static constexpr int W = WARPS;
+  static constexpr int T = 32 * WARPS;
+  static constexpr size_t stride = (size_t)T * EPL;
+  int tid, lane, warp, D;
   long chain;            // local chain index
   // registers
   double q[EPL], p[EPL], g[EPL], minv[EPL], rhoL[EPL];
@@ -62,7 +65,7 @@ struct DeviceBackend {
   // memory
   double* red; int red_buf;
   Entry* ctl;
-  double* sm_slots; double* gl_slots; int n_sm; size_t stride;
+  double* sm_slots; double* gl_slots; int n_sm;
   const double* mparams;
   int n_slots;
 
@@ -71,36 +74,83 @@ struct DeviceBackend {
     return (s < n_sm ? sm_slots + (size_t)s * stride : gl_slots + (size_t)(s - n_sm) * stride) + tid;
   }
 
-  // ---- scalar all-reduce in the canonical order: lane butterfly
-  // xor 1,2,4,8,16, then a pairwise tree over warps.
+  // ---- scalar all-reduce of N <= 8 values in the canonical order.
+  // Intra-warp: shuffle reduce-scatter with xor offsets 16, 8, 4, 2, 1 — at each
+  // stage a lane keeps half of its values and sends the other half, so N values
+  // cost about N + 3 shuffles instead of 5 N; every value still sees the same
+  // pairwise tree (lane l with l^16, then ^8, ...).  The lane that ends up with
+  // value `idx` publishes it to shared memory; all threads then read the W x N
+  // partials and combine warps with a pairwise tree (offsets 32, 64, ...).
+  template <int CW, int OFF>
+  __device__ __forceinline__ void rs_stage(double* w, int& idx) const {
+    if constexpr (CW >= 2) {
+      constexpr int H = CW / 2;
+      const bool upper = (lane & OFF) != 0;
+#pragma unroll
+      for (int j = 0; j < H; ++j) {
+        const double send = upper ? w[j] : w[j + H];
+        const double recv = __shfl_xor_sync(0xffffffffu, send, OFF);
+        const double keep = upper ? w[j + H] : w[j];
+        w[j] = keep + recv;
+      }
+      idx = idx * 2 + (upper ? 1 : 0);
+    } else {
+      w[0] = w[0] + __shfl_xor_sync(0xffffffffu, w[0], OFF);
+    }
+  }
   template <int N>
   __device__ __forceinline__ void reduce(double (&v)[N]) {
+    constexpr int P = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : 8;
+    static_assert(N <= kRedWidth, "at most 8 values per reduction");
+    double w[P];
 #pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
+    for (int j = 0; j < P; ++j) w[j] = j < N ? v[j] : 0.0;
+    int idx = 0;
+    rs_stage<P, 16>(w, idx);
+    rs_stage<(P >= 2 ? P / 2 : 1), 8>(w, idx);
+    rs_stage<(P >= 4 ? P / 4 : 1), 4>(w, idx);
+    rs_stage<1, 2>(w, idx);
+    rs_stage<1, 1>(w, idx);
+    double* buf = red + red_buf * (kMaxWarps * kRedWidth);
+    red_buf ^= 1;
+    buf[warp * kRedWidth + idx] = w[0];
+    if (W > 1) __syncthreads(); else __syncwarp();
 #pragma unroll
-      for (int n = 0; n < N; ++n) v[n] = v[n] + __shfl_xor_sync(0xffffffffu, v[n], off);
-    }
-    if (W > 1) {
-      double* buf = red + red_buf * (kMaxWarps * kRedWidth);
-      red_buf ^= 1;
-      if (lane == 0) {
-#pragma unroll
-        for (int n = 0; n < N; ++n) buf[warp * kRedWidth + n] = v[n];
+    for (int n = 0; n < N; ++n) {
+      const double* b = buf + n;
+      if (W == 1) {
+        v[n] = b[0];
+      } else if (W == 2) {
+        v[n] = b[0] + b[kRedWidth];
+      } else if (W == 4) {
+        v[n] = (b[0] + b[kRedWidth]) + (b[2 * kRedWidth] + b[3 * kRedWidth]);
+      } else {
+        v[n] = ((b[0] + b[kRedWidth]) + (b[2 * kRedWidth] + b[3 * kRedWidth])) +
+               ((b[4 * kRedWidth] + b[5 * kRedWidth]) + (b[6 * kRedWidth] + b[7 * kRedWidth]));
       }
-      __syncthreads();
-#pragma unroll
-      for (int n = 0; n < N; ++n) {
-        const double* b = buf + n;
-        if (W == 2) {
-          v[n] = b[0] + b[kRedWidth];
-        } else if (W == 4) {
-          v[n] = (b[0] + b[kRedWidth]) + (b[2 * kRedWidth] + b[3 * kRedWidth]);
-        } else {
-          v[n] = ((b[0] + b[kRedWidth]) + (b[2 * kRedWidth] + b[3 * kRedWidth])) +
-                 ((b[4 * kRedWidth] + b[5 * kRedWidth]) + (b[6 * kRedWidth] + b[7 * kRedWidth]));
-        }
-      }
     }
+  }
+
+  // ---- lane-parallel scalar math: all threads of a chain hold the same scalars,
+  // so independent transcendental evaluations are spread over lanes and shared
+  // by shuffle instead of being evaluated one after the other by every lane.
+  __device__ __forceinline__ void logaddexp2(double a0, double b0, double a1, double b1,
+                                             double* r0, double* r1) const {
+    const bool odd = (lane & 1) != 0;
+    const double r = dm_logaddexp(odd ? a1 : a0, odd ? b1 : b0);
+    *r0 = __shfl_sync(0xffffffffu, r, 0);
+    *r1 = __shfl_sync(0xffffffffu, r, 1);
+  }
+  // randexp draws j = base..base+31 of a transition are generated by the 32 lanes at once
+  double rexp_cache;
+  uint32_t rexp_base, rexp_t;
+  __device__ __forceinline__ double randexp(dm_rng_key key, uint32_t t, uint32_t j) {
+    const uint32_t base = j & ~31u;
+    if (base != rexp_base || t != rexp_t) {
+      rexp_cache = dm_randexp(key, t, base + (uint32_t)lane);
+      rexp_base = base; rexp_t = t;
+    }
+    return __shfl_sync(0xffffffffu, rexp_cache, (int)(j & 31u));
   }
 
   // ---- interface used by NutsMachine ----

@@ -57,18 +57,24 @@ struct KArgs {
   double* out_phase;
 };
 
-template <int EPL, int FAM>
-__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM>& b, const KArgs& a,
+// Register budget: minimum resident CTAs per SM the compiler must allow for.
+__host__ __device__ constexpr int min_ctas(int W, int EPL) {
+  return W == 1 ? 16 : W == 2 ? 8 : W == 4 ? (EPL >= 8 ? 3 : 4) : 2;
+}
+
+template <int EPL, int FAM, int W>
+__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W>& b, const KArgs& a,
                                               unsigned char* smem) {
   b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5;
-  b.W = a.W; b.T = a.T; b.D = a.D;
-  const SmemLayout L = smem_layout(a.W, a.n_sm, a.stride);
+  b.D = a.D;
+  const SmemLayout L = smem_layout(W, a.n_sm, b.stride);
   b.red = reinterpret_cast<double*>(smem + L.red_off);
   b.red_buf = 0;
+  b.rexp_cache = 0.0; b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;
   b.ctl = reinterpret_cast<Entry*>(smem + L.ctl_off) + b.warp * (kMaxLevels + 1);
   b.sm_slots = reinterpret_cast<double*>(smem + L.slots_off);
   b.gl_slots = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
-  b.n_sm = a.n_sm; b.stride = a.stride; b.n_slots = a.n_slots;
+  b.n_sm = a.n_sm; b.n_slots = a.n_slots;
   b.mparams = a.mparams;
 }
 
@@ -79,8 +85,8 @@ __device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc) {
   return s_misc[0];
 }
 
-template <int EPL, int FAM>
-__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM>& b, const KArgs& a, long c,
+template <int EPL, int FAM, int W>
+__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W>& b, const KArgs& a, long c,
                                            bool with_p) {
   b.chain = c;
   const size_t base = (size_t)c * a.D;
@@ -96,8 +102,8 @@ __device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM>& b, const KAr
   }
   b.lq = a.lq[c];
 }
-template <int EPL, int FAM>
-__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM>& b, double* dst,
+template <int EPL, int FAM, int W>
+__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W>& b, double* dst,
                                           const double (&v)[EPL], size_t base, int D) {
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
@@ -107,9 +113,9 @@ __device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM>& b, doub
 }
 
 // ------------------------------------------------------------------ k_nuts
-template <int EPL, int FAM>
+template <int EPL, int FAM, int W>
 struct DrawSink {
-  DeviceBackend<EPL, FAM>& b;
+  DeviceBackend<EPL, FAM, W>& b;
   const KArgs& a;
   long c;
   __device__ __forceinline__ void operator()(int n, const dhmc_tree_stats& ts, double e) {
@@ -123,19 +129,19 @@ struct DrawSink {
   }
 };
 
-template <int EPL, int FAM>
-__global__ void __launch_bounds__(256) k_nuts(const KArgs a) {
+template <int EPL, int FAM, int W>
+__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_nuts(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM> b;
+  DeviceBackend<EPL, FAM, W> b;
   setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(a.W, a.n_sm, a.stride).misc_off);
+  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride).misc_off);
   for (;;) {
     const int c = next_chain(a.counter, s_misc);
     if (c >= a.B) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
-    DrawSink<EPL, FAM> sink{b, a, c};
+    DrawSink<EPL, FAM, W> sink{b, a, c};
     const double eps_next = m.run(a.t0, a.N, a.eps[c], a.cfg, a.p_override,
                                   a.dir_override ? a.dir_override + c : nullptr, sink);
     const size_t base = (size_t)c * a.D;
@@ -152,17 +158,17 @@ __global__ void __launch_bounds__(256) k_nuts(const KArgs a) {
 }
 
 // ------------------------------------------------------------------ k_search
-template <int EPL, int FAM>
-__global__ void __launch_bounds__(256) k_search(const KArgs a) {
+template <int EPL, int FAM, int W>
+__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_search(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM> b;
+  DeviceBackend<EPL, FAM, W> b;
   setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(a.W, a.n_sm, a.stride).misc_off);
+  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride).misc_off);
   for (;;) {
     const int c = next_chain(a.counter, s_misc);
     if (c >= a.B) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
     const double eps = m.find_initial_stepsize(a.s_init, a.s_thresh, a.s_maxiter, a.p_override);
     if (b.tid == 0) {
@@ -174,10 +180,10 @@ __global__ void __launch_bounds__(256) k_search(const KArgs a) {
 
 // ------------------------------------------------------------------ k_leapfrog
 // Streaming leapfrog: reads q, p, ∇ℓ, M⁻¹ (32·D B), writes q′, p′, ∇ℓ′ (24·D B).
-template <int EPL, int FAM>
-__global__ void __launch_bounds__(256) k_leapfrog(const KArgs a) {
+template <int EPL, int FAM, int W>
+__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_leapfrog(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM> b;
+  DeviceBackend<EPL, FAM, W> b;
   setup_backend(b, a, smem);
   for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
     load_chain(b, a, c, true);
@@ -192,15 +198,15 @@ __global__ void __launch_bounds__(256) k_leapfrog(const KArgs a) {
       a.lq[c] = b.lq;
       if (flags & 1) atomicOr(a.status + c, (int)DHMC_CHAIN_NONFINITE_Q);
     }
-    if (a.W > 1) __syncthreads();
+    if (W > 1) __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------ k_eval
-template <int EPL, int FAM>
-__global__ void __launch_bounds__(256) k_eval(const KArgs a) {
+template <int EPL, int FAM, int W>
+__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_eval(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM> b;
+  DeviceBackend<EPL, FAM, W> b;
   setup_backend(b, a, smem);
   for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
     load_chain(b, a, c, false);
@@ -226,21 +232,21 @@ __global__ void __launch_bounds__(256) k_eval(const KArgs a) {
       a.lq[c] = b.lq;
       if (a.strict && (flags & (1 | 4))) atomicOr(a.status + c, (int)DHMC_CHAIN_BAD_INITIAL);
     }
-    if (a.W > 1) __syncthreads();
+    if (W > 1) __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------ k_phase
-template <int EPL, int FAM>
-__global__ void __launch_bounds__(256) k_phase(const KArgs a) {
+template <int EPL, int FAM, int W>
+__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_phase(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM> b;
+  DeviceBackend<EPL, FAM, W> b;
   setup_backend(b, a, smem);
   for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
     load_chain(b, a, c, true);
     const double H = b.phase_logdensity();
     if (b.tid == 0) a.out_phase[c] = H;
-    if (a.W > 1) __syncthreads();
+    if (W > 1) __syncthreads();
   }
 }
 
@@ -290,36 +296,50 @@ static std::string g_create_err;
     }                                                                                 \
   } while (0)
 
-template <int EPL, class F>
+template <int W, int EPL, class F>
 static int dispatch_f(int fam, F&& f) {
+  using IW = std::integral_constant<int, W>;
+  using IE = std::integral_constant<int, EPL>;
   switch (fam) {
-    case DHMC_FAMILY_STD_NORMAL: return f(std::integral_constant<int, EPL>{}, std::integral_constant<int, DHMC_FAMILY_STD_NORMAL>{});
-    case DHMC_FAMILY_DIAG_NORMAL: return f(std::integral_constant<int, EPL>{}, std::integral_constant<int, DHMC_FAMILY_DIAG_NORMAL>{});
-    case DHMC_FAMILY_FUNNEL: return f(std::integral_constant<int, EPL>{}, std::integral_constant<int, DHMC_FAMILY_FUNNEL>{});
+    case DHMC_FAMILY_STD_NORMAL: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_STD_NORMAL>{});
+    case DHMC_FAMILY_DIAG_NORMAL: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_DIAG_NORMAL>{});
+    case DHMC_FAMILY_FUNNEL: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_FUNNEL>{});
   }
   return DHMC_EARG;
 }
+// supported (warps per chain, elements per thread) layouts
+static bool layout_supported(int W, int epl) {
+  if (W == 1) return epl == 1 || epl == 2 || epl == 4 || epl == 8;
+  if (W == 2 || W == 4 || W == 8) return epl == 4 || epl == 8;
+  return false;
+}
 template <class F>
-static int dispatch(int epl, int fam, F&& f) {
-  switch (epl) {
-    case 1: return dispatch_f<1>(fam, f);
-    case 2: return dispatch_f<2>(fam, f);
-    case 4: return dispatch_f<4>(fam, f);
-    case 8: return dispatch_f<8>(fam, f);
+static int dispatch(int W, int epl, int fam, F&& f) {
+  switch (W * 16 + epl) {
+    case 1 * 16 + 1: return dispatch_f<1, 1>(fam, f);
+    case 1 * 16 + 2: return dispatch_f<1, 2>(fam, f);
+    case 1 * 16 + 4: return dispatch_f<1, 4>(fam, f);
+    case 1 * 16 + 8: return dispatch_f<1, 8>(fam, f);
+    case 2 * 16 + 4: return dispatch_f<2, 4>(fam, f);
+    case 2 * 16 + 8: return dispatch_f<2, 8>(fam, f);
+    case 4 * 16 + 4: return dispatch_f<4, 4>(fam, f);
+    case 4 * 16 + 8: return dispatch_f<4, 8>(fam, f);
+    case 8 * 16 + 4: return dispatch_f<8, 4>(fam, f);
+    case 8 * 16 + 8: return dispatch_f<8, 8>(fam, f);
   }
   return DHMC_EARG;
 }
 
 enum KernelId { K_NUTS, K_SEARCH, K_LEAPFROG, K_EVAL, K_PHASE };
 
-template <int EPL, int FAM>
+template <int EPL, int FAM, int W>
 static const void* kernel_ptr(KernelId k) {
   switch (k) {
-    case K_NUTS: return (const void*)k_nuts<EPL, FAM>;
-    case K_SEARCH: return (const void*)k_search<EPL, FAM>;
-    case K_LEAPFROG: return (const void*)k_leapfrog<EPL, FAM>;
-    case K_EVAL: return (const void*)k_eval<EPL, FAM>;
-    default: return (const void*)k_phase<EPL, FAM>;
+    case K_NUTS: return (const void*)k_nuts<EPL, FAM, W>;
+    case K_SEARCH: return (const void*)k_search<EPL, FAM, W>;
+    case K_LEAPFROG: return (const void*)k_leapfrog<EPL, FAM, W>;
+    case K_EVAL: return (const void*)k_eval<EPL, FAM, W>;
+    default: return (const void*)k_phase<EPL, FAM, W>;
   }
 }
 
@@ -349,10 +369,11 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, bool timed) {
     CK(cudaMemsetAsync(h->total_steps, 0, sizeof(unsigned long long), h->stream));
   }
   if (timed) CK(cudaEventRecord(h->ev0, h->stream));
-  int rc = dispatch(h->EPL, h->cfg.family, [&](auto E, auto Fm) -> int {
+  int rc = dispatch(h->W, h->EPL, h->cfg.family, [&](auto Wc, auto E, auto Fm) -> int {
+    constexpr int WW = decltype(Wc)::value;
     constexpr int EPL = decltype(E)::value;
     constexpr int FAM = decltype(Fm)::value;
-    const void* fn = kernel_ptr<EPL, FAM>(k);
+    const void* fn = kernel_ptr<EPL, FAM, WW>(k);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
     void* params[] = {(void*)&a};
@@ -393,8 +414,11 @@ static int sync_and_check_status(dhmc_handle* h, int mask, const char* what) {
 static void choose_layout(int64_t D, int req_T, int* T, int* EPL) {
   if (req_T > 0) {
     *T = req_T;
+    const int W = req_T / 32;
     int e = (int)((D + req_T - 1) / req_T);
-    *EPL = e <= 1 ? 1 : e <= 2 ? 2 : e <= 4 ? 4 : e <= 8 ? 8 : 0;
+    e = e <= 1 ? 1 : e <= 2 ? 2 : e <= 4 ? 4 : e <= 8 ? 8 : 0;
+    if (e && !layout_supported(W, e)) e = (e < 4 && layout_supported(W, 4)) ? 4 : (e < 8 && layout_supported(W, 8)) ? 8 : 0;
+    *EPL = e;
     return;
   }
   if (D <= 32) { *T = 32; *EPL = 1; }
@@ -484,10 +508,11 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   const SmemLayout L0 = smem_layout(h->W, 0, h->stride);
   h->smem_light = L0.total;
   int reg_ctas = 0;
-  int rc = dispatch(EPL, cfg->family, [&](auto E, auto Fm) -> int {
+  int rc = dispatch(T / 32, EPL, cfg->family, [&](auto Wc, auto E, auto Fm) -> int {
+    constexpr int WW = decltype(Wc)::value;
     constexpr int EP = decltype(E)::value;
     constexpr int FA = decltype(Fm)::value;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, k_nuts<EP, FA>, T, L0.total);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, k_nuts<EP, FA, WW>, T, L0.total);
     if (e != cudaSuccess) { h->err = std::string("occupancy query: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
     return DHMC_OK;
   });

@@ -94,15 +94,23 @@ struct NutsMachine {
   // ---- slot pool (bit set = free).  Low indices are the on-chip slots. ----
   DHMC_M int alloc_lo() {
     uint64_t m = freemask;
+#if defined(__CUDA_ARCH__)
+    int s = m ? __ffsll((long long)m) - 1 : 63;
+#else
     int s = 0;
     while (s < 63 && !((m >> s) & 1ull)) ++s;  // pool is sized so that a free slot exists
+#endif
     freemask = m & ~(1ull << s);
     return s;
   }
   DHMC_M int alloc_hi() {
     uint64_t m = freemask;
+#if defined(__CUDA_ARCH__)
+    int s = m ? 63 - __clzll((long long)m) : 0;
+#else
     int s = n_slots - 1;
     while (s > 0 && !((m >> s) & 1ull)) --s;
+#endif
     freemask = m & ~(1ull << s);
     return s;
   }
@@ -111,7 +119,7 @@ struct NutsMachine {
   // rand_bool_logprob — NUTS.jl:43-45 (no draw when logprob ≥ 0)
   DHMC_M bool rand_bool_logprob(double logprob) {
     if (logprob >= 0) return true;
-    double e = dm_randexp(key, t, n_exp++);
+    double e = b.randexp(key, t, n_exp++);
     return e > -logprob;
   }
 
@@ -185,13 +193,20 @@ struct NutsMachine {
           L_omega = delta; L_vlog = leaf_vlog; L_vsteps = 1; L_ifirst = pos;
           L_zlq = b.cur_lq(); L_zH = Hn; L_szq = -1; L_szg = -1; L_sfirst = -1; L_leaf = true;
           b.rho_from_p();
+#if defined(__CUDA_ARCH__)
+          const int c = __ffs((int)k) - 1;                // ctz(k): merges after this leaf
+#else
           int c = 0;
           while (!((k >> c) & 1u)) ++c;                   // ctz(k): merges after this leaf
+#endif
           for (int j = 0; j < c; ++j) {
             const Entry E = b.get_entry(--sp);
             const bool turning = b.merge_check(E.sfirst, E.slast, E.srho, L_sfirst, L_leaf);
             // v = combine_visited_statistics(v₋, v₊) precedes the checks, trees.jl:249
-            const double mv_log = dm_logaddexp(E.vlog, L_vlog);
+            // (ω of the merged tree is computed alongside: two independent logaddexp,
+            //  evaluated lane-parallel on the GPU)
+            double mv_log, om;
+            b.logaddexp2(E.vlog, L_vlog, E.omega, L_omega, &mv_log, &om);
             const int mv_steps = E.vsteps + L_vsteps;
             if (turning) {                                // trees.jl:254-255
               inv_l = E.ifirst; inv_r = pos;
@@ -200,7 +215,6 @@ struct NutsMachine {
               break;
             }
             // combine_proposals_and_logweights(…, is_doubling = false), trees.jl:258
-            const double om = dm_logaddexp(E.omega, L_omega);
             const double logprob2 = L_omega - om;         // biased_progressive_logprob2(false,…)
             if (rand_bool_logprob(logprob2)) {            // ζ₂ (later-built) selected
               release(E.szq); release(E.szg);
@@ -252,13 +266,14 @@ struct NutsMachine {
         }
       }
       // ---------------- back in sample_trajectory ----------------
-      v_log = dm_logaddexp(v_log, vacc_log);              // trees.jl:294
+      double om_top;
+      b.logaddexp2(v_log, vacc_log, omega_top, L_omega, &v_log, &om_top);   // trees.jl:294, :310
       v_steps += vacc_steps;
       if (invalid) { term_l = inv_l; term_r = inv_r; break; }   // trees.jl:297
       i_near = pos;                                       // trees.jl:303-307
       // combine_proposals_and_logweights(…, is_doubling = true), trees.jl:310
       {
-        const double om = dm_logaddexp(omega_top, L_omega);
+        const double om = om_top;
         const double logprob2 = L_omega - omega_top;      // biased: ω₂ − ω₁
         if (rand_bool_logprob(logprob2)) {
           if (L_szq < 0) {

@@ -49,9 +49,13 @@ struct ArgumentError : std::invalid_argument {  // @argcheck failures
 };
 
 // ---------------------------------------------------------------- reduction
-// Canonical sum: lane v accumulates term(i) for i = v, v+T, ... in increasing i
-// starting from +0.0; lanes are then combined by a pairwise tree (xor offsets
-// 1,2,4,...).  T == 0 selects plain sequential summation (tolerance checks).
+// Canonical sum (DESIGN.md "canonical reduction"): T virtual lanes; lane v
+// accumulates term(i) for i = v, v+T, ... in increasing i starting from +0.0.
+// Lanes are combined per group of 32 (a warp) by a pairwise tree with offsets
+// 16, 8, 4, 2, 1, then the per-warp sums by a pairwise tree with offsets
+// 32, 64, ...  This is exactly the order of the GPU's shuffle reduce-scatter
+// followed by its cross-warp exchange.  T == 0 selects plain sequential
+// summation (used only for tolerance checks).
 template <class F>
 double canon_sum(int T, int D, F term) {
   if (T <= 0) {
@@ -65,7 +69,10 @@ double canon_sum(int T, int D, F term) {
     for (int i = v; i < D; i += T) acc = acc + term(i);
     part[v] = acc;
   }
-  for (int off = 1; off < T; off <<= 1)
+  for (int base = 0; base < T; base += 32)
+    for (int off = 16; off >= 1; off >>= 1)
+      for (int v = base; v < base + off; ++v) part[v] = part[v] + part[v + off];
+  for (int off = 32; off < T; off <<= 1)
     for (int v = 0; v < T; v += 2 * off) part[v] = part[v] + part[v + off];
   return part[0];
 }

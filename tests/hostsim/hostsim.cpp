@@ -25,7 +25,10 @@ double canon_sum(int T, int D, F term) {
     for (int i = v; i < D; i += T) acc = acc + term(i);
     part[v] = acc;
   }
-  for (int off = 1; off < T; off <<= 1)
+  for (int base = 0; base < T; base += 32)
+    for (int off = 16; off >= 1; off >>= 1)
+      for (int v = base; v < base + off; ++v) part[v] = part[v] + part[v + off];
+  for (int off = 32; off < T; off <<= 1)
     for (int v = 0; v < T; v += 2 * off) part[v] = part[v] + part[v + off];
   return part[0];
 }
@@ -57,6 +60,10 @@ struct HostBackend {
   void swap_cur(int sq, int sp, int sg) { q.swap(slots[sq]); p.swap(slots[sp]); g.swap(slots[sg]); }
   void rho_from_p() { rhoL = p; }
   void rho_commit() { rhoL = Rnew; }
+  void logaddexp2(double a0, double b0, double a1, double b1, double* r0, double* r1) {
+    *r0 = dm_logaddexp(a0, b0); *r1 = dm_logaddexp(a1, b1);
+  }
+  double randexp(dm_rng_key key, uint32_t t, uint32_t j) { return dm_randexp(key, t, j); }
   void put_entry(int j, const Entry& e) { entries[j] = e; }
   Entry get_entry(int j) const { return entries[j]; }
 

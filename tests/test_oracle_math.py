@@ -78,16 +78,20 @@ def test_canonical_reduction_width(po):
     ref = float(np.dot(a, b))
     for T in (0, 32, 64, 128, 256):
         assert abs(po.canon_dot(T, a, b) - ref) < 1e-12
-    # explicit restatement of the canonical order for T = 32
-    part = np.zeros(32)
-    for v in range(32):
+    # explicit restatement of the canonical order for T = 64: lane-strided partials,
+    # per-warp pairwise tree with offsets 16,8,4,2,1, then warps with offsets 32,...
+    T = 64
+    part = np.zeros(T)
+    for v in range(T):
         acc = 0.0
-        for i in range(v, 1000, 32):
+        for i in range(v, 1000, T):
             acc = acc + a[i] * b[i]
         part[v] = acc
-    off = 1
-    while off < 32:
-        for v in range(0, 32, 2 * off):
-            part[v] = part[v] + part[v + off]
-        off *= 2
-    assert po.canon_dot(32, a, b) == part[0]
+    for base in range(0, T, 32):
+        off = 16
+        while off >= 1:
+            for v in range(base, base + off):
+                part[v] = part[v] + part[v + off]
+            off //= 2
+    part[0] = part[0] + part[32]
+    assert po.canon_dot(T, a, b) == part[0]
