@@ -167,8 +167,9 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- setup (untimed) ----------------
+    chain_offset, K = pkg.parallel.shard(world * K, world, rank)     # weak scaling: K chains per GPU
     eng = pkg.Engine(pkg.StandardNormal(D), chains=K, seed=2026, device=local_rank,
-                     chain_offset=rank * K, threads_per_chain=args.threads_per_chain,
+                     chain_offset=chain_offset, threads_per_chain=args.threads_per_chain,
                      ctas_per_sm=args.ctas_per_sm)
     T, EPL = eng.layout()
     eng.random_position()
@@ -245,11 +246,10 @@ def main():
     gather_ms = None
     if world > 1:
         last = draws[:, n - 1, :].contiguous()
-        out = torch.empty((world * K, D), dtype=torch.float64, device=dev)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        dist.all_gather_into_tensor(out, last)
+        out = pkg.parallel.gather_draws(last, world * K)
         e1.record()
         torch.cuda.synchronize()
         gather_ms = e0.elapsed_time(e1)

@@ -55,6 +55,7 @@ struct KArgs {
   int lf_steps, lf_sign;
   int strict, randomize;
   double* out_phase;
+  int chain_begin, chain_end;   // persistent kernels: chains [begin, end) of this launch
 };
 
 // Register budget: minimum resident CTAs per SM the compiler must allow for.
@@ -78,9 +79,9 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W>& b, con
   b.mparams = a.mparams;
 }
 
-__device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc) {
+__device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc, int begin) {
   __syncthreads();
-  if (threadIdx.x == 0) s_misc[0] = (int)atomicAdd(counter, 1u);
+  if (threadIdx.x == 0) s_misc[0] = begin + (int)atomicAdd(counter, 1u);
   __syncthreads();
   return s_misc[0];
 }
@@ -136,8 +137,8 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_nuts(const KArgs a
   setup_backend(b, a, smem);
   int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride).misc_off);
   for (;;) {
-    const int c = next_chain(a.counter, s_misc);
-    if (c >= a.B) break;
+    const int c = next_chain(a.counter, s_misc, a.chain_begin);
+    if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
     NutsMachine<DeviceBackend<EPL, FAM, W>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
@@ -165,8 +166,8 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_search(const KArgs
   setup_backend(b, a, smem);
   int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride).misc_off);
   for (;;) {
-    const int c = next_chain(a.counter, s_misc);
-    if (c >= a.B) break;
+    const int c = next_chain(a.counter, s_misc, a.chain_begin);
+    if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
     NutsMachine<DeviceBackend<EPL, FAM, W>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
@@ -269,8 +270,11 @@ struct dhmc_handle {
   int n_slots = 0, n_sm = 0, grid = 0, sm_count = 0, light_grid = 0;
   size_t smem_bytes = 0, smem_light = 0;
   size_t scratch_per_cta = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t chunk_ev[16] = {};
+  void* stage[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only device staging for host outputs
+  size_t stage_bytes[4] = {0, 0, 0, 0};
   double *q = nullptr, *g = nullptr, *lq = nullptr, *p = nullptr, *minv = nullptr, *eps = nullptr;
   double* mparams = nullptr;
   int* status = nullptr;
@@ -355,20 +359,32 @@ static KArgs base_args(dhmc_handle* h) {
   a.scratch = h->scratch; a.scratch_per_cta = h->scratch_per_cta;
   a.n_sm = h->n_sm; a.n_slots = h->n_slots; a.stride = h->stride;
   a.counter = h->counter; a.total_steps = h->total_steps;
+  a.chain_begin = 0; a.chain_end = (int)h->cfg.n_chains;
   return a;
 }
 
 // heavy = persistent kernels that use the slot pool (k_nuts, k_search)
-static int launch(dhmc_handle* h, KernelId k, KArgs a, bool timed) {
+// timing: 0 = none, 1 = record ev0 before / ev1 after and read the time (synchronises),
+// 2 = record ev0 only (first of a series), 3 = record ev1 only (last; caller reads),
+// 4 = middle of a series.  reset_steps: zero the Σ steps counter first.
+static int read_timer(dhmc_handle* h) {
+  CK(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_ms = ms;
+  return DHMC_OK;
+}
+static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_steps = true) {
   const bool heavy = (k == K_NUTS || k == K_SEARCH);
   if (!heavy) { a.n_sm = 0; }
   const size_t smem = heavy ? h->smem_bytes : h->smem_light;
-  const int grid = heavy ? h->grid : h->light_grid;
+  int grid = heavy ? h->grid : h->light_grid;
+  if (heavy) grid = std::max(1, std::min(grid, a.chain_end - a.chain_begin));
   if (heavy) {
     CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), h->stream));
-    CK(cudaMemsetAsync(h->total_steps, 0, sizeof(unsigned long long), h->stream));
+    if (reset_steps) CK(cudaMemsetAsync(h->total_steps, 0, sizeof(unsigned long long), h->stream));
   }
-  if (timed) CK(cudaEventRecord(h->ev0, h->stream));
+  if (timing == 1 || timing == 2) CK(cudaEventRecord(h->ev0, h->stream));
   int rc = dispatch(h->W, h->EPL, h->cfg.family, [&](auto Wc, auto E, auto Fm) -> int {
     constexpr int WW = decltype(Wc)::value;
     constexpr int EPL = decltype(E)::value;
@@ -383,13 +399,8 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, bool timed) {
   });
   if (rc != DHMC_OK) return rc;
   h->launches += 1;
-  if (timed) {
-    CK(cudaEventRecord(h->ev1, h->stream));
-    CK(cudaEventSynchronize(h->ev1));
-    float ms = 0;
-    CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
-    h->last_ms = ms;
-  }
+  if (timing == 1 || timing == 3) CK(cudaEventRecord(h->ev1, h->stream));
+  if (timing == 1) return read_timer(h);
   return DHMC_OK;
 }
 
@@ -443,6 +454,9 @@ int dhmc_destroy(dhmc_handle* h) {
   cudaFree(h->total_steps);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
+  for (auto& b : h->stage) cudaFree(b);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return DHMC_OK;
@@ -480,6 +494,8 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   CKC(cudaGetDeviceProperties(&prop, cfg->device));
   h->sm_count = prop.multiProcessorCount;
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  for (auto& e : h->chunk_ev) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
   const size_t B = (size_t)cfg->n_chains, D = (size_t)cfg->dim;
@@ -559,7 +575,7 @@ static int eval_position(dhmc_handle* h, bool randomize) {
   CK(cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)h->cfg.n_chains, h->stream));
   KArgs a = base_args(h);
   a.strict = 1; a.randomize = randomize ? 1 : 0;
-  int rc = launch(h, K_EVAL, a, false);
+  int rc = launch(h, K_EVAL, a, 0);
   if (rc != DHMC_OK) return rc;
   h->has_position = true;
   return sync_and_check_status(h, DHMC_CHAIN_BAD_INITIAL, "initialize_warmup_state: invalid log density or gradient at the initial position");
@@ -652,7 +668,7 @@ int dhmc_leapfrog(dhmc_handle* h, int32_t n_steps, int32_t sign) {
   CK(cudaSetDevice(h->cfg.device));
   KArgs a = base_args(h);
   a.lf_steps = n_steps; a.lf_sign = sign;
-  int rc = launch(h, K_LEAPFROG, a, true);
+  int rc = launch(h, K_LEAPFROG, a, 1);
   if (rc != DHMC_OK) return rc;
   return sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q, "leapfrog: position vector has non-finite elements");
 }
@@ -665,7 +681,7 @@ int dhmc_phase_logdensity(dhmc_handle* h, double* out) {
   CK(cudaMalloc(&d, sizeof(double) * B));
   KArgs a = base_args(h);
   a.out_phase = d;
-  int rc = launch(h, K_PHASE, a, false);
+  int rc = launch(h, K_PHASE, a, 0);
   if (rc == DHMC_OK) {
     cudaError_t e = cudaMemcpyAsync(out, d, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
@@ -686,14 +702,25 @@ int dhmc_find_initial_stepsize(dhmc_handle* h, double initial_eps, double log_th
   CK(cudaSetDevice(h->cfg.device));
   KArgs a = base_args(h);
   a.s_init = initial_eps; a.s_thresh = log_threshold; a.s_maxiter = maxiter;
-  int rc = launch(h, K_SEARCH, a, true);
+  int rc = launch(h, K_SEARCH, a, 1);
   if (rc != DHMC_OK) return rc;
   h->has_eps = true;
   return sync_and_check_status(h, DHMC_CHAIN_SEARCH_FAILED | DHMC_CHAIN_NONFINITE_Q,
                                "initial stepsize search failed (no crossing, or non-finite starting density)");
 }
 
-// common driver of sample_tree / warmup stage / mcmc
+// common driver of sample_tree / warmup stage / mcmc.
+// Host outputs of large runs are pipelined: the chains are cut into chunks, each
+// chunk is one k_nuts launch on the compute stream, and its draws/statistics are
+// copied D2H on the copy stream while the next chunk computes (pinned host
+// buffers make the copies truly asynchronous; pageable ones still work).
+static int ensure_stage(dhmc_handle* h, int i, size_t bytes) {
+  if (h->stage_bytes[i] >= bytes) return DHMC_OK;
+  cudaFree(h->stage[i]); h->stage[i] = nullptr; h->stage_bytes[i] = 0;
+  CK(cudaMalloc(&h->stage[i], bytes));
+  h->stage_bytes[i] = bytes;
+  return DHMC_OK;
+}
 static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, const double* p_over_host,
                     const uint32_t* dir_over_host, double* posterior, dhmc_tree_stats* stats,
                     double* eps_used, double* logdens, bool outputs_on_device, bool advance_t) {
@@ -704,18 +731,16 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, const double*
   dhmc_tree_stats* d_stats = nullptr;
   unsigned* d_dir = nullptr;
   int rc = DHMC_OK;
-  auto cleanup = [&] {
-    if (!outputs_on_device) { cudaFree(d_post); cudaFree(d_stats); cudaFree(d_eps); cudaFree(d_ld); }
-    cudaFree(d_p); cudaFree(d_dir);
-  };
+  auto cleanup = [&] { cudaFree(d_p); cudaFree(d_dir); };
 #define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA; } } while (0)
+#define CKS(call) do { int r_ = (call); if (r_ != DHMC_OK) { cleanup(); return r_; } } while (0)
   if (outputs_on_device) {
     d_post = posterior; d_stats = stats; d_eps = eps_used; d_ld = logdens;
   } else {
-    if (posterior) CKR(cudaMalloc(&d_post, sizeof(double) * B * n * D));
-    if (stats) CKR(cudaMalloc(&d_stats, sizeof(dhmc_tree_stats) * B * n));
-    if (eps_used) CKR(cudaMalloc(&d_eps, sizeof(double) * B * n));
-    if (logdens) CKR(cudaMalloc(&d_ld, sizeof(double) * B * n));
+    if (posterior) { CKS(ensure_stage(h, 0, sizeof(double) * B * n * D)); d_post = (double*)h->stage[0]; }
+    if (stats) { CKS(ensure_stage(h, 1, sizeof(dhmc_tree_stats) * B * n)); d_stats = (dhmc_tree_stats*)h->stage[1]; }
+    if (eps_used) { CKS(ensure_stage(h, 2, sizeof(double) * B * n)); d_eps = (double*)h->stage[2]; }
+    if (logdens) { CKS(ensure_stage(h, 3, sizeof(double) * B * n)); d_ld = (double*)h->stage[3]; }
   }
   if (p_over_host) {
     CKR(cudaMalloc(&d_p, sizeof(double) * B * D));
@@ -728,18 +753,31 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, const double*
   KArgs a = base_args(h);
   a.N = N; a.cfg = cfg; a.p_override = d_p; a.dir_override = d_dir;
   a.out_q = d_post; a.out_stats = d_stats; a.out_eps = d_eps; a.out_lq = d_ld;
-  rc = launch(h, K_NUTS, a, true);
-  if (rc != DHMC_OK) { cleanup(); return rc; }
+  const size_t out_bytes = posterior ? sizeof(double) * B * n * D : 0;
+  const int nchunks = (!outputs_on_device && B >= 4096 && out_bytes >= ((size_t)32 << 20)) ? 8 : 1;
+  for (int ci = 0; ci < nchunks; ++ci) {
+    const size_t c0 = B * ci / nchunks, c1 = B * (ci + 1) / nchunks, nc = c1 - c0;
+    a.chain_begin = (int)c0; a.chain_end = (int)c1;
+    const int timing = nchunks == 1 ? 1 : (ci == 0 ? 2 : (ci == nchunks - 1 ? 3 : 4));
+    rc = launch(h, K_NUTS, a, timing == 1 ? 2 : timing, ci == 0);
+    if (rc != DHMC_OK) { cleanup(); return rc; }
+    if (nchunks == 1) CKR(cudaEventRecord(h->ev1, h->stream));
+    if (!outputs_on_device) {
+      CKR(cudaEventRecord(h->chunk_ev[ci], h->stream));
+      CKR(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[ci], 0));
+      if (posterior) CKR(cudaMemcpyAsync(posterior + c0 * n * D, d_post + c0 * n * D, sizeof(double) * nc * n * D, cudaMemcpyDeviceToHost, h->copy_stream));
+      if (stats) CKR(cudaMemcpyAsync(stats + c0 * n, d_stats + c0 * n, sizeof(dhmc_tree_stats) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
+      if (eps_used) CKR(cudaMemcpyAsync(eps_used + c0 * n, d_eps + c0 * n, sizeof(double) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
+      if (logdens) CKR(cudaMemcpyAsync(logdens + c0 * n, d_ld + c0 * n, sizeof(double) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+  }
   unsigned long long steps = 0;
   CKR(cudaMemcpyAsync(&steps, h->total_steps, sizeof steps, cudaMemcpyDeviceToHost, h->stream));
-  if (!outputs_on_device) {
-    if (posterior) CKR(cudaMemcpyAsync(posterior, d_post, sizeof(double) * B * n * D, cudaMemcpyDeviceToHost, h->stream));
-    if (stats) CKR(cudaMemcpyAsync(stats, d_stats, sizeof(dhmc_tree_stats) * B * n, cudaMemcpyDeviceToHost, h->stream));
-    if (eps_used) CKR(cudaMemcpyAsync(eps_used, d_eps, sizeof(double) * B * n, cudaMemcpyDeviceToHost, h->stream));
-    if (logdens) CKR(cudaMemcpyAsync(logdens, d_ld, sizeof(double) * B * n, cudaMemcpyDeviceToHost, h->stream));
-  }
   CKR(cudaStreamSynchronize(h->stream));
+  CKR(cudaStreamSynchronize(h->copy_stream));
+  CKS(read_timer(h));
 #undef CKR
+#undef CKS
   cleanup();
   h->last_steps = (int64_t)steps;
   if (advance_t) h->t += (uint32_t)N;
