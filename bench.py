@@ -228,7 +228,6 @@ def main():
             eng._ck(lib.dhmc_set_position(h, C.c_void_p(q_host.data_ptr())))
             eng._ck(lib.dhmc_mcmc(h, C.c_int32(n), C.c_void_p(post_host.data_ptr()),
                                   C.c_void_p(stats_host.data_ptr()), C.c_void_p(logd_host.data_ptr())))
-            q_host.copy_(post_host[:, n - 1, :])        # next step restarts from the returned draw
             return eng.last_total_steps()
 
         for _ in range(max(1, args.warmup - 1)):

@@ -199,15 +199,37 @@ struct DeviceBackend {
   // rand_p — hamiltonian.jl:124: W * randn(D), W = Diagonal(sqrt.(inv.(diag M⁻¹))) (:80)
   __device__ __forceinline__ void draw(dm_rng_key key, uint32_t stream, uint32_t t,
                                        const double* p_override) {
+    if (p_override) {
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      const int i = tid + e * T;
-      double v = 0.0;
-      if (i < D) {
-        if (p_override) v = p_override[(size_t)chain * D + i];
-        else v = dm_sqrt(1.0 / minv[e]) * dm_normal_elem(key, stream, t, (uint32_t)i);
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        p[e] = i < D ? p_override[(size_t)chain * D + i] : 0.0;
       }
-      p[e] = v;
+      return;
+    }
+    if constexpr (EPL >= 2) {
+      // Elements (2j, 2j+1) share one Philox block / Box-Muller pair and sit in adjacent
+      // lanes (T is even).  The even lane evaluates the pairs of even register slots, the
+      // odd lane those of odd slots, and the halves are exchanged by one shuffle.
+      const int odd = lane & 1;
+#pragma unroll
+      for (int e = 0; e < EPL; e += 2) {
+        const int my_e = e + odd;
+        const uint32_t j = (uint32_t)(((tid & ~1) + my_e * T) >> 1);
+        double z0, z1;
+        dm_normal_pair(key, stream, t, j, &z0, &z1);
+        const double recv = __shfl_xor_sync(0xffffffffu, odd ? z0 : z1, 1);
+        const double ze = odd ? recv : z0;        // element tid + e*T
+        const double zo = odd ? z1 : recv;        // element tid + (e+1)*T
+        p[e] = (tid + e * T < D) ? dm_sqrt(1.0 / minv[e]) * ze : 0.0;
+        p[e + 1] = (tid + (e + 1) * T < D) ? dm_sqrt(1.0 / minv[e + 1]) * zo : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        p[e] = i < D ? dm_sqrt(1.0 / minv[e]) * dm_normal_elem(key, stream, t, (uint32_t)i) : 0.0;
+      }
     }
   }
   __device__ __forceinline__ void draw_momentum(dm_rng_key key, uint32_t t, const double* po) {
@@ -341,24 +363,55 @@ struct DeviceBackend {
   // order; leaves the combined ρ in rhoL.  Returns true when turning.
   __device__ __forceinline__ bool merge_check(int sEf, int sEl, int sEr, int sLf, bool L_leaf) {
     const double* pEf = slot(sEf);
+    const bool e_leaf = (sEl == sEf);
+    if (e_leaf && L_leaf) {
+      // two single leaves (half of all merges): E.first = E.last = E.ρ = p_E and
+      // L.first = L.last = L.ρ = p, so the three candidate sums coincide and the six
+      // dot products collapse to two — the very same floating-point operations.
+      double d[2] = {0.0, 0.0};
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const double Ef = pEf[e * T];
+        const double A = Ef + p[e];
+        const double mEf = minv[e] * Ef, mLl = minv[e] * p[e];
+        d[0] = d[0] + mEf * A;
+        d[1] = d[1] + mLl * A;
+        rhoL[e] = A;
+      }
+      reduce(d);
+      return d[0] < 0 || d[1] < 0;
+    }
     const double* pEl = slot(sEl);
     const double* pEr = slot(sEr);
-    const double* pLf = L_leaf ? pEf : slot(sLf);
-    const bool e_leaf = (sEl == sEf);
     double d[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (!L_leaf) {
+      const double* pLf = slot(sLf);
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      const double Ef = pEf[e * T];
-      const double El = e_leaf ? Ef : pEl[e * T];
-      const double Er = e_leaf ? Ef : pEr[e * T];
-      const double Lf = L_leaf ? p[e] : pLf[e * T];
-      const double Lr = L_leaf ? p[e] : rhoL[e];
-      const double A = Er + Lf, Bv = El + Lr, R = Er + Lr;
-      const double mEf = minv[e] * Ef, mLf = minv[e] * Lf, mEl = minv[e] * El, mLl = minv[e] * p[e];
-      d[0] = d[0] + mEf * A;  d[1] = d[1] + mLf * A;
-      d[2] = d[2] + mEl * Bv; d[3] = d[3] + mLl * Bv;
-      d[4] = d[4] + mEf * R;  d[5] = d[5] + mLl * R;
-      rhoL[e] = R;
+      for (int e = 0; e < EPL; ++e) {
+        const double Ef = pEf[e * T], El = pEl[e * T], Er = pEr[e * T], Lf = pLf[e * T];
+        const double Lr = rhoL[e];
+        const double A = Er + Lf, Bv = El + Lr, R = Er + Lr;
+        const double mEf = minv[e] * Ef, mLf = minv[e] * Lf, mEl = minv[e] * El, mLl = minv[e] * p[e];
+        d[0] = d[0] + mEf * A;  d[1] = d[1] + mLf * A;
+        d[2] = d[2] + mEl * Bv; d[3] = d[3] + mLl * Bv;
+        d[4] = d[4] + mEf * R;  d[5] = d[5] + mLl * R;
+        rhoL[e] = R;
+      }
+    } else {
+      // whole tree so far (three distinct vectors) against a single new leaf: only at depth 0
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const double Ef = pEf[e * T];
+        const double El = e_leaf ? Ef : pEl[e * T];
+        const double Er = e_leaf ? Ef : pEr[e * T];
+        const double Lf = p[e], Lr = p[e];
+        const double A = Er + Lf, Bv = El + Lr, R = Er + Lr;
+        const double mEf = minv[e] * Ef, mLf = minv[e] * Lf, mEl = minv[e] * El, mLl = minv[e] * p[e];
+        d[0] = d[0] + mEf * A;  d[1] = d[1] + mLf * A;
+        d[2] = d[2] + mEl * Bv; d[3] = d[3] + mLl * Bv;
+        d[4] = d[4] + mEf * R;  d[5] = d[5] + mLl * R;
+        rhoL[e] = R;
+      }
     }
     reduce(d);
     return d[0] < 0 || d[1] < 0 || d[2] < 0 || d[3] < 0 || d[4] < 0 || d[5] < 0;

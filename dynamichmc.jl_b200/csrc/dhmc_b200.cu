@@ -15,6 +15,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -60,7 +61,10 @@ struct KArgs {
 
 // Register budget: minimum resident CTAs per SM the compiler must allow for.
 __host__ __device__ constexpr int min_ctas(int W, int EPL) {
-  return W == 1 ? 16 : W == 2 ? 8 : W == 4 ? (EPL >= 8 ? 3 : 4) : 2;
+#ifndef DHMC_MINCTAS_W4E8
+#define DHMC_MINCTAS_W4E8 3
+#endif
+  return W == 1 ? 16 : W == 2 ? 8 : W == 4 ? (EPL >= 8 ? DHMC_MINCTAS_W4E8 : 4) : 2;
 }
 
 template <int EPL, int FAM, int W>
@@ -537,7 +541,10 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   int ctas = cfg->ctas_per_sm > 0 ? std::min(cfg->ctas_per_sm, reg_ctas) : reg_ctas;
   const size_t smem_sm = (size_t)prop.sharedMemPerMultiprocessor;        // 228 KB
   const size_t smem_cta_max = (size_t)prop.sharedMemPerBlockOptin;       // 227 KB
-  size_t per_cta = smem_sm / ctas - 1024;                                 // 1 KB system reservation per CTA
+  // leave part of the unified SM memory to L1 (register spills and the global-scratch slots go through it)
+  size_t l1_reserve = 0;
+  if (const char* ev = std::getenv("DHMC_L1_RESERVE_KB")) l1_reserve = (size_t)std::atol(ev) * 1024;
+  size_t per_cta = (smem_sm - std::min(l1_reserve, smem_sm / 2)) / ctas - 1024;   // 1 KB system reservation per CTA
   if (per_cta > smem_cta_max) per_cta = smem_cta_max;
   long n_sm = per_cta > L0.total ? (long)((per_cta - L0.total) / slot_bytes) : 0;
   const int pool = h->n_slots - kWelfordSlots;   // the two highest slots stay in global memory

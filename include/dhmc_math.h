@@ -32,6 +32,12 @@
 #else
 #define DHMC_HD static inline
 #endif
+/* heavy transcendental bodies: optionally out of line on the device (code size) */
+#if defined(__CUDACC__) && defined(DHMC_NOINLINE_MATH)
+#define DHMC_HDH __host__ __device__ __noinline__
+#else
+#define DHMC_HDH DHMC_HD
+#endif
 
 /* ------------------------------------------------------------------ bits */
 DHMC_HD uint64_t dm_bits(double x) {
@@ -99,7 +105,7 @@ DHMC_HD double dm_pow2i(int k) {
 #define DM_LN2_LO 1.90821492927058770002e-10 /* 0x3DEA39EF35793C76 */
 #define DM_INVLN2 1.44269504088896338700e+00
 
-DHMC_HD double dm_exp(double x) {
+DHMC_HDH double dm_exp(double x) {
   if (x != x) return x;
   if (x > 709.782712893384) return dm_inf();
   if (x < -745.1332191019412) return 0.0;
@@ -128,7 +134,7 @@ DHMC_HD double dm_exp(double x) {
 }
 
 /* ------------------------------------------------------------------- log */
-DHMC_HD double dm_log(double x) {
+DHMC_HDH double dm_log(double x) {
   if (x != x) return x;
   if (x < 0.0) return dm_nan();
   if (x == 0.0) return -dm_inf();
@@ -203,7 +209,7 @@ DHMC_HD double dm_log1pexp(double x) {
 /* -------------------------------------------------- sin/cos of 2*pi*u */
 #define DM_PIO4 7.85398163397448309616e-01
 /* u in [0,1): returns cos(2 pi u), sin(2 pi u); octant reduction is exact. */
-DHMC_HD void dm_sincos2pi(double u, double* sn, double* cs) {
+DHMC_HDH void dm_sincos2pi(double u, double* sn, double* cs) {
   double a = 8.0 * u;
   double jf = dm_floor(a);
   int j = ((int)jf) & 7;
@@ -258,7 +264,7 @@ DHMC_HD uint32_t dm_mulhi32(uint32_t a, uint32_t b) {
 #endif
 }
 
-DHMC_HD dm_u32x4 dm_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+DHMC_HDH dm_u32x4 dm_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
                                    uint32_t c3, uint32_t k0, uint32_t k1) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
   const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
