@@ -1,0 +1,140 @@
+#!/usr/bin/env python
+"""The other BASELINE.json configs (bench.py covers configs[1] = C2).
+
+  C1  100-dim std MvNormal, 4 chains, default warm-up + 1000 draws — CPU oracle (reference arm)
+  C3  Neal's funnel D=10, 262 144 chains, diagonal M⁻¹ — depth histogram, divergence rate
+  C5  1000-dim MvNormal, κ = 1e4, 65 536 chains per GPU, full default warm-up (dual averaging +
+      diagonal metric), NCCL all-gather of the final draw (torchrun for N > 1)
+
+Each config prints one JSON line.  Usage:  python benchmarks/run_configs.py C1 C3 C5 [--scale 0.25]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import __graft_entry__ as entry  # noqa: E402
+
+
+def c1():
+    po = entry.load_oracle()
+    D, K, N = 100, 4, 1000
+    t0 = time.perf_counter()
+    res = [po.mcmc_with_warmup(po.FAMILY_STD_NORMAL, D, N, seed=1 + k, chain=k, T=32, keep_warmup=True)
+           for k in range(K)]
+    dt = time.perf_counter() - t0
+    steps = sum(int(r["tree_statistics"]["steps"].sum() + r["warmup_stats"]["steps"].sum()) for r in res)
+    post = np.concatenate([r["posterior_matrix"] for r in res])
+    return {"config": "C1", "impl": "oracle port (CPU, 1 thread)", "dim": D, "chains": K, "draws": N,
+            "leapfrog_steps_per_sec": steps / dt, "draws_per_sec": K * (N + 900) / dt, "seconds": dt,
+            "posterior_mean_maxabs": float(np.abs(post.mean(0)).max()),
+            "posterior_var_maxdev": float(np.abs(post.var(0) - 1).max()),
+            "mean_eps": float(np.mean([r["eps"] for r in res]))}
+
+
+def _timed(eng, fn):
+    t0 = time.perf_counter()
+    out = fn()
+    return out, time.perf_counter() - t0, eng.last_total_steps(), eng.last_kernel_ms()
+
+
+def c3(scale):
+    pkg = entry.load_package()
+    D, K, N = 10, int(262144 * scale), 50
+    eng = pkg.Engine(pkg.Funnel(D), chains=K, seed=2026)
+    eng.random_position()
+    eng.find_initial_stepsize()
+    wall, steps, ms = 0.0, 0, 0.0
+    for st in pkg.default_warmup_stages()[1:]:
+        _, dt, s, m = _timed(eng, lambda: eng.warmup_stage(st))
+        wall += dt; steps += s; ms += m
+    out, dt, s, m = _timed(eng, lambda: eng.mcmc(N))
+    ts = out["tree_statistics"]
+    depth_hist = np.bincount(ts["depth"].ravel(), minlength=11).tolist()
+    div = float(np.mean(ts["left"] == ts["right"]))
+    post = out["posterior_matrix"]
+    line = {"config": "C3", "dim": D, "chains": K, "draws": N, "threads_per_chain": eng.layout()[0],
+            "warmup": {"transitions": 900, "leapfrog_steps": steps, "kernel_ms": ms, "wall_s": wall,
+                       "leapfrog_steps_per_sec": steps / (ms * 1e-3)},
+            "sampling": {"leapfrog_steps": s, "kernel_ms": m, "leapfrog_steps_per_sec": s / (m * 1e-3),
+                         "draws_per_sec": K * N / (m * 1e-3)},
+            "depth_histogram": depth_hist, "divergence_rate": div,
+            "mean_acceptance": float(ts["acceptance_rate"].mean()),
+            "v_mean": float(post[:, :, 0].mean()), "v_std": float(post[:, :, 0].std()),
+            "note": "v ~ N(0, 3) exactly; NUTS on the funnel under-explores the neck (v_std < 3 expected)"}
+    eng.close()
+    return line
+
+
+def c5(scale):
+    import torch
+    import torch.distributed as dist
+    pkg = entry.load_package()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D, Kg, N = 1000, int(65536 * scale), 4
+    sigma2 = 10.0 ** (4 * np.arange(D) / (D - 1))
+    off, K = pkg.parallel.shard(world * Kg, world, rank)
+    eng = pkg.Engine(pkg.DiagNormal(np.zeros(D), sigma2), chains=K, seed=2026, device=local, chain_offset=off)
+    eng.random_position()
+    t0 = time.perf_counter()
+    eng.find_initial_stepsize()
+    stage_rows, steps, ms = [], 0, eng.last_kernel_ms()
+    for st in pkg.default_warmup_stages()[1:]:
+        _, dt, s, m = _timed(eng, lambda: eng.warmup_stage(st))
+        stage_rows.append({"N": st.N, "M": st.M, "leapfrog_steps": s, "kernel_ms": m})
+        steps += s; ms += m
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    warm_wall = time.perf_counter() - t0
+    draws = torch.empty((K, N, D), dtype=torch.float64, device=f"cuda:{local}")
+    stats = torch.empty((K, N, 56), dtype=torch.uint8, device=f"cuda:{local}")
+    eng.mcmc_dev(N, draws.data_ptr(), stats.data_ptr(), 0)
+    s_samp, m_samp = eng.last_total_steps(), eng.last_kernel_ms()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    last = draws[:, N - 1, :].contiguous()
+    torch.cuda.synchronize()
+    e0.record()
+    full = pkg.parallel.gather_draws(last, world * Kg) if world > 1 else last
+    e1.record()
+    torch.cuda.synchronize()
+    st = eng.get_state(("minv", "eps"))
+    ratio = st["minv"] / sigma2
+    sd = (full.std(0).cpu().numpy() / np.sqrt(sigma2))
+    tot = torch.tensor([float(steps), float(s_samp)], dtype=torch.float64, device=f"cuda:{local}")
+    mx = torch.tensor([ms, m_samp, warm_wall], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tot); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    line = {"config": "C5", "n_gpus": world, "dim": D, "chains_total": world * Kg, "kappa": 1e4,
+            "warmup": {"transitions": 900, "leapfrog_steps": tot[0].item(), "kernel_ms_max": mx[0].item(),
+                       "wall_s_max": mx[2].item(), "leapfrog_steps_per_sec": tot[0].item() / (mx[0].item() * 1e-3),
+                       "stages_rank0": stage_rows},
+            "sampling": {"draws": N, "leapfrog_steps": tot[1].item(),
+                         "leapfrog_steps_per_sec": tot[1].item() / (mx[1].item() * 1e-3)},
+            "allgather": {"ms": e0.elapsed_time(e1), "bytes_per_rank": K * D * 8},
+            "adapted_metric_over_truth": {"median": float(np.median(ratio)), "p05": float(np.quantile(ratio, 0.05)),
+                                          "p95": float(np.quantile(ratio, 0.95))},
+            "mean_eps": float(st["eps"].mean()),
+            "final_draw_sd_over_sigma": {"min": float(sd.min()), "max": float(sd.max())}}
+    eng.close()
+    return line if rank == 0 else None
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("configs", nargs="+", choices=["C1", "C3", "C5"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the configured chain count")
+    a = ap.parse_args()
+    for c in a.configs:
+        r = c1() if c == "C1" else c3(a.scale) if c == "C3" else c5(a.scale)
+        if r is not None:
+            print(json.dumps(r), flush=True)
