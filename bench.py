@@ -130,7 +130,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dim", type=int, default=1000)
@@ -204,6 +204,13 @@ def main():
 
     # ---------------- roofline legs ----------------
     hbm_peak, peak_kind = peaks()
+    traffic = None
+    try:   # DRAM bytes per launch from the committed ncu --set full capture of this same command
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_nuts"]
+        if (tr["dim"], tr["chains"], tr["draws_per_step"]) == (D, K, n):
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     algo_bytes_per_leapfrog = 48 * D                      # read q,p,∇ℓ; write q′,p′,∇ℓ′
     # standalone streaming leapfrog kernel (HBM-bound): per-chain metric => 56·D B per step
     lf_ms = []
@@ -284,7 +291,8 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_nuts (whole NUTS transition, chain state resident on chip)",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "peak_kind": peak_kind, "traffic": None,
+                         "peak_kind": peak_kind, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": (tot_steps / args.steps) * algo_bytes_per_leapfrog,
                          "note": "achieved = leapfrog steps per launch x 48*D B / launch time; the kernel keeps q,p,grad "
                                  "in registers/shared memory across the tree, so actual DRAM traffic is far below the "
                                  "algorithmic bytes and frac may exceed 1 (SURVEY 8d)"},
