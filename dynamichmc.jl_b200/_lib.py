@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("DHMC_B200_LIB", os.path.join(_HERE, "csrc", "libdhmc_
 
 DHMC_OK, DHMC_EARG, DHMC_ENUMERIC, DHMC_ECUDA, DHMC_ENOMEM = 0, 1, 2, 3, 4
 FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL = 0, 1, 2
-METRIC_NOTHING, METRIC_DIAGONAL = 0, 1
+METRIC_NOTHING, METRIC_DIAGONAL, METRIC_SYMMETRIC = 0, 1, 2
 
 tree_stats_dtype = np.dtype(
     [("pi", "<f8"), ("depth", "<i8"), ("left", "<i8"), ("right", "<i8"),
@@ -18,7 +18,8 @@ tree_stats_dtype = np.dtype(
 
 EXPORTS = [
     "dhmc_create", "dhmc_destroy", "dhmc_last_error", "dhmc_get_layout", "dhmc_set_problem",
-    "dhmc_set_position", "dhmc_random_position", "dhmc_set_metric", "dhmc_set_stepsize",
+    "dhmc_set_position", "dhmc_random_position", "dhmc_set_metric", "dhmc_set_metric_dense",
+    "dhmc_get_metric_dense", "dhmc_metric_is_dense", "dhmc_set_stepsize",
     "dhmc_set_momentum", "dhmc_get_state", "dhmc_chain_status", "dhmc_get_transition_count",
     "dhmc_set_transition_count", "dhmc_leapfrog", "dhmc_phase_logdensity", "dhmc_sample_tree",
     "dhmc_find_initial_stepsize", "dhmc_warmup_stage", "dhmc_mcmc", "dhmc_mcmc_dev",

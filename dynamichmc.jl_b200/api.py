@@ -187,12 +187,18 @@ def fixed_stepsize_warmup_stages(M=Diagonal, middle_steps=25, doubling_stages=5)
 
 @dataclass
 class GaussianKineticEnergy:
-    """src/hamiltonian.jl:56-87 with Diagonal M⁻¹: `minv` is [D] (shared) or [D, K]."""
+    """src/hamiltonian.jl:56-87.  Diagonal M⁻¹ (:80): `minv` is [D] (all chains) or one row
+    per chain.  Symmetric M⁻¹ (:73, `dense=True`): `minv` is [D, D] (all chains) or [K, D, D]."""
     minv: np.ndarray
+    dense: bool = False
 
     @staticmethod
     def identity(N, m=1.0):
         return GaussianKineticEnergy(np.full(N, float(m)))
+
+    @staticmethod
+    def symmetric(Minv):
+        return GaussianKineticEnergy(np.ascontiguousarray(Minv, float), dense=True)
 
 
 # ------------------------------------------------------------------ engine
@@ -272,6 +278,32 @@ class Engine:
         else:
             self._ck(self._lib.dhmc_set_metric(self._h, L.ptr(self._kd(minv, "minv")), 0))
 
+    def set_metric_dense(self, Minv):
+        """κ = GaussianKineticEnergy(Symmetric(M⁻¹)) — hamiltonian.jl:73."""
+        M = np.ascontiguousarray(Minv, float)
+        if M.ndim == 2:
+            _argcheck(M.shape == (self.D, self.D), "dimension(ℓ) == size(κ, 1)")
+            self._ck(self._lib.dhmc_set_metric_dense(self._h, L.ptr(M), 1))
+        else:
+            _argcheck(M.shape == (self.K, self.D, self.D), "M⁻¹: [D, D] or one matrix per chain")
+            self._ck(self._lib.dhmc_set_metric_dense(self._h, L.ptr(M), 0))
+
+    def set_kinetic_energy(self, κ: "GaussianKineticEnergy"):
+        if κ.dense:
+            self.set_metric_dense(κ.minv)
+        else:
+            self.set_metric(κ.minv)
+
+    def metric_is_dense(self):
+        v = C.c_int32()
+        self._ck(self._lib.dhmc_metric_is_dense(self._h, C.byref(v)))
+        return bool(v.value)
+
+    def get_metric_dense(self):
+        out = np.empty((self.K, self.D, self.D))
+        self._ck(self._lib.dhmc_get_metric_dense(self._h, L.ptr(out)))
+        return out
+
     def set_stepsize(self, eps):
         e = np.ascontiguousarray(eps, float).reshape(-1)
         if e.size == 1:
@@ -332,8 +364,6 @@ class Engine:
                                                       C.c_int32(s.maxiter_crossing)))
 
     def warmup_stage(self, stage: TuningNUTS, keep=False):
-        if stage.M == Symmetric:
-            raise ArgumentError("dense (Symmetric) metric adaptation is not built yet (DESIGN.md, scope)")
         K, D, N = self.K, self.D, stage.N
         post = np.empty((K, N, D)) if keep else None
         stats = np.zeros((K, N), dtype=L.tree_stats_dtype) if keep else None
@@ -343,7 +373,7 @@ class Engine:
         if isinstance(stage.stepsize_adaptation, DualAveraging):
             a = stage.stepsize_adaptation
             da = C.byref(L.DualAveragingC(a.δ, a.γ, a.κ, a.t0, 0))
-        metric = L.METRIC_DIAGONAL if stage.M == Diagonal else L.METRIC_NOTHING
+        metric = {Diagonal: L.METRIC_DIAGONAL, Symmetric: L.METRIC_SYMMETRIC}.get(stage.M, L.METRIC_NOTHING)
         self._ck(self._lib.dhmc_warmup_stage(self._h, C.c_int32(N), C.c_int32(metric), da,
                                              C.c_double(stage.λ), L.ptr(post), L.ptr(stats),
                                              L.ptr(eps), L.ptr(ld)))
@@ -397,7 +427,7 @@ class Results(Sequence):
         # NB: string keys, not keywords — Python NFKC-normalises identifiers (ϵ → ε)
         return {"posterior_matrix": self._post[k].T,        # [D, N] view, mcmc.jl:230
                 "tree_statistics": self._stats[k], "logdensities": self._logd[k],
-                "κ": GaussianKineticEnergy(self._minv[k]), "ϵ": float(self._eps[k]),
+                "κ": GaussianKineticEnergy(self._minv[k], dense=self._minv[k].ndim == 2), "ϵ": float(self._eps[k]),
                 "eps": float(self._eps[k])}
 
 
@@ -421,7 +451,7 @@ def _initialize(engine: Engine, initialization):
     unknown = set(init) - {"q", "κ", "ϵ"}
     _argcheck(not unknown, f"unknown initialization fields {unknown}")
     if init.get("κ") is not None:
-        engine.set_metric(init["κ"].minv)
+        engine.set_kinetic_energy(init["κ"])
     if init.get("q") is not None:
         q = np.asarray(init["q"], float)
         if q.ndim == 1:
@@ -453,8 +483,9 @@ def mcmc_keep_warmup(seed, ℓ, N, chains=1, initialization=None, warmup_stages=
             raise ArgumentError(f"unknown warmup stage {stage!r}")
     inf = eng.mcmc(N)
     st = eng.get_state(("minv", "eps"))
+    minv = eng.get_metric_dense() if eng.metric_is_dense() else st["minv"]
     results = Results(inf["posterior_matrix"], inf["tree_statistics"], inf["logdensities"],
-                      st["minv"], st["eps"])
+                      minv, st["eps"])
     return dict(warmup=warm, inference=results, engine=eng)
 
 

@@ -32,10 +32,12 @@ struct SmemLayout {
   int red_off;    // doubles: [2][kMaxWarps][kRedWidth]
   int ctl_off;    // bytes from base: Entry[W][kMaxLevels+1]
   int misc_off;   // bytes: int[4]
+  int xs_off;     // bytes: staging vector for the dense mat-vec (dense metric only)
   int slots_off;  // bytes
   size_t total;   // bytes
 };
-__host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride) {
+// stride = doubles per slot (a slot of the dense metric holds a (p, p♯) pair), xs = doubles of staging
+__host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride, size_t xs = 0) {
   SmemLayout L;
   size_t off = 0;
   L.red_off = 0;
@@ -45,23 +47,34 @@ __host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride
   off = (off + 15) & ~(size_t)15;
   L.misc_off = (int)off;
   off += 16;
+  L.xs_off = (int)off;
+  off += sizeof(double) * xs;
   L.slots_off = (int)off;
   off += sizeof(double) * stride * (size_t)n_sm;
   L.total = off;
   return L;
 }
 
-template <int EPL, int FAM, int WARPS>
+// DENSE = Symmetric M⁻¹ per chain (hamiltonian.jl:73): p♯ = M⁻¹p is a D×D mat-vec
+// streamed from HBM, kept in registers next to p and stored with it — a momentum
+// slot holds the pair (p, p♯), so the state machine's bookkeeping is unchanged.
+template <int EPL, int FAM, int WARPS, bool DENSE = false>
 struct DeviceBackend {
   // geometry: T = 32·WARPS threads per chain, compile-time so that strides fold
   static constexpr int W = WARPS;
   static constexpr int T = 32 * WARPS;
-  static constexpr size_t stride = (size_t)T * EPL;
+  static constexpr bool kDense = DENSE;
+  static constexpr size_t vstride = (size_t)T * EPL;                    // doubles per vector
+  static constexpr size_t stride = DENSE ? 2 * vstride : vstride;      // doubles per slot
   int tid, lane, warp, D;
   long chain;            // local chain index
   // registers
   double q[EPL], p[EPL], g[EPL], minv[EPL], rhoL[EPL];
+  double ps[DENSE ? EPL : 1];      // p♯ of the current point (dense metric)
   double lq;
+  // dense metric: this chain's M⁻¹ (symmetric, [D][D]), Wᵀ (column-major lower W), co-moment
+  // accumulator (transposed lower) and the shared-memory staging vector
+  const double* Mrow; const double* Wt; double* covt; double* xs;
   // memory
   double* red; int red_buf;
   Entry* ctl;
@@ -170,10 +183,26 @@ struct DeviceBackend {
     const double* d = slot(s);                               \
     _Pragma("unroll") for (int e = 0; e < EPL; ++e) dst[e] = d[e * T]; \
   }
-  DHMC_ST(st_q, q) DHMC_ST(st_p, p) DHMC_ST(st_g, g) DHMC_ST(st_rho, rhoL)
-  DHMC_LD(ld_q, q) DHMC_LD(ld_p, p) DHMC_LD(ld_g, g)
+  DHMC_ST(st_q, q) DHMC_ST(st_g, g) DHMC_ST(st_rho, rhoL)
+  DHMC_LD(ld_q, q) DHMC_LD(ld_g, g)
 #undef DHMC_ST
 #undef DHMC_LD
+  __device__ __forceinline__ void st_p(int s) {
+    double* d = slot(s);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      d[e * T] = p[e];
+      if constexpr (DENSE) d[vstride + e * T] = ps[e];
+    }
+  }
+  __device__ __forceinline__ void ld_p(int s) {
+    const double* d = slot(s);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      p[e] = d[e * T];
+      if constexpr (DENSE) ps[e] = d[vstride + e * T];
+    }
+  }
 
   __device__ __forceinline__ void swap_cur(int sq, int sp, int sg) {
     double* dq = slot(sq); double* dp = slot(sp); double* dg = slot(sg);
@@ -181,6 +210,7 @@ struct DeviceBackend {
     for (int e = 0; e < EPL; ++e) {
       double a = dq[e * T]; dq[e * T] = q[e]; q[e] = a;
       double b = dp[e * T]; dp[e * T] = p[e]; p[e] = b;
+      if constexpr (DENSE) { double b2 = dp[vstride + e * T]; dp[vstride + e * T] = ps[e]; ps[e] = b2; }
       double c = dg[e * T]; dg[e * T] = g[e]; g[e] = c;
     }
   }
@@ -196,6 +226,52 @@ struct DeviceBackend {
   }
   __device__ __forceinline__ Entry get_entry(int j) const { return ctl[j]; }
 
+  __device__ __forceinline__ void group_sync() const {
+    if (W > 1) __syncthreads(); else __syncwarp();
+  }
+  // y = M⁻¹ x for this chain (Symmetric M⁻¹ * v, hamiltonian.jl:110): x is staged in shared
+  // memory, every thread accumulates its own rows over j = 0..D-1 in increasing j (the
+  // oracle's order); row j of M is read coalesced (M is symmetric).
+  __device__ __forceinline__ void matvec(const double (&x)[EPL], double (&y)[EPL]) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) xs[tid + e * T] = x[e];
+    group_sync();
+    double acc[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = 0.0;
+    const double* row = Mrow + tid;
+    for (int j = 0; j < D; ++j, row += D) {
+      const double xj = xs[j];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e)
+        if (tid + e * T < D) acc[e] = acc[e] + __ldg(row + e * T) * xj;
+    }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) y[e] = acc[e];
+    group_sync();
+  }
+  // y = W z with lower-triangular W stored transposed (hamiltonian.jl:124, :73)
+  __device__ __forceinline__ void trmv(const double (&z)[EPL], double (&y)[EPL]) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) xs[tid + e * T] = z[e];
+    group_sync();
+    double acc[EPL];
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) acc[e] = 0.0;
+    const double* col = Wt + tid;
+    for (int j = 0; j < D; ++j, col += D) {
+      const double zj = xs[j];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        if (i < D && j <= i) acc[e] = acc[e] + __ldg(col + e * T) * zj;
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) y[e] = acc[e];
+    group_sync();
+  }
+
   // rand_p — hamiltonian.jl:124: W * randn(D), W = Diagonal(sqrt.(inv.(diag M⁻¹))) (:80)
   __device__ __forceinline__ void draw(dm_rng_key key, uint32_t stream, uint32_t t,
                                        const double* p_override) {
@@ -205,6 +281,18 @@ struct DeviceBackend {
         const int i = tid + e * T;
         p[e] = i < D ? p_override[(size_t)chain * D + i] : 0.0;
       }
+      if constexpr (DENSE) matvec(p, ps);
+      return;
+    }
+    if constexpr (DENSE) {
+      double z[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        z[e] = i < D ? dm_normal_elem(key, stream, t, (uint32_t)i) : 0.0;
+      }
+      trmv(z, p);
+      matvec(p, ps);
       return;
     }
     if constexpr (EPL >= 2) {
@@ -243,8 +331,12 @@ struct DeviceBackend {
     double acc = 0.0;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
-      double ps = minv[e] * p[e];
-      acc = acc + p[e] * ps;
+      if constexpr (DENSE) {
+        acc = acc + p[e] * ps[e];
+      } else {
+        double psv = minv[e] * p[e];
+        acc = acc + p[e] * psv;
+      }
     }
     return acc;
   }
@@ -296,8 +388,10 @@ struct DeviceBackend {
         g[e] = ge;
         if (with_p) {
           p[e] = p[e] + h * ge;
-          double ps = minv[e] * p[e];
-          r2[0] = r2[0] + p[e] * ps;
+          if constexpr (!DENSE) {
+            double psv = minv[e] * p[e];
+            r2[0] = r2[0] + p[e] * psv;
+          }
         }
       }
       reduce(r2);
@@ -328,8 +422,10 @@ struct DeviceBackend {
         g[e] = ge;
         if (with_p) {
           p[e] = p[e] + h * ge;
-          double ps = minv[e] * p[e];
-          r[1] = r[1] + p[e] * ps;
+          if constexpr (!DENSE) {
+            double psv = minv[e] * p[e];
+            r[1] = r[1] + p[e] * psv;
+          }
         }
       }
       reduce(r);
@@ -347,21 +443,62 @@ struct DeviceBackend {
   __device__ __forceinline__ double leapfrog(double eps, int* flags) {
     const double h = eps / 2;
     double qbad = 0.0;
+    if constexpr (DENSE) {
+      double vel[EPL];
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) {
-      p[e] = p[e] + h * g[e];                 // pₘ = p + ϵ/2 * ∇ℓq        :277
-      const double vel = minv[e] * p[e];      // ∇kinetic_energy = M⁻¹ pₘ  :117
-      q[e] = q[e] + eps * vel;                // q′ = q + ϵ * (…)           :278
-      if (!dm_isfinite(q[e])) qbad = 1.0;
+      for (int e = 0; e < EPL; ++e) p[e] = p[e] + h * g[e];       // pₘ                        :277
+      matvec(p, vel);                                             // ∇kinetic_energy = M⁻¹ pₘ  :117
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        q[e] = q[e] + eps * vel[e];                               // q′                        :278
+        if (!dm_isfinite(q[e])) qbad = 1.0;
+      }
+      double ksum;
+      eval_model(true, h, qbad, &ksum, flags);                    // Q′, p′                    :279-280
+      matvec(p, ps);                                              // p♯′ = M⁻¹ p′ (K and turn statistics)
+      double r[1] = {kinetic_partial()};
+      reduce(r);
+      return hamiltonian_logdensity(lq, r[0]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        p[e] = p[e] + h * g[e];                 // pₘ = p + ϵ/2 * ∇ℓq        :277
+        const double vel = minv[e] * p[e];      // ∇kinetic_energy = M⁻¹ pₘ  :117
+        q[e] = q[e] + eps * vel;                // q′ = q + ϵ * (…)           :278
+        if (!dm_isfinite(q[e])) qbad = 1.0;
+      }
+      double ksum;
+      eval_model(true, h, qbad, &ksum, flags);  // Q′ = evaluate_ℓ; p′ = pₘ + ϵ/2 ∇ℓq′  :279-280
+      return hamiltonian_logdensity(lq, ksum);
     }
-    double ksum;
-    eval_model(true, h, qbad, &ksum, flags);  // Q′ = evaluate_ℓ; p′ = pₘ + ϵ/2 ∇ℓq′  :279-280
-    return hamiltonian_logdensity(lq, ksum);
   }
 
   // The six dot products of combine_turn_statistics (NUTS.jl:130-139) in build
   // order; leaves the combined ρ in rhoL.  Returns true when turning.
   __device__ __forceinline__ bool merge_check(int sEf, int sEl, int sEr, int sLf, bool L_leaf) {
+    if constexpr (DENSE) {
+      // p♯ of the four edge momenta come from the slots (stored next to p); ρ slots hold ρ only
+      const double* pEf = slot(sEf);
+      const double* pEl = slot(sEl);
+      const double* pEr = slot(sEr);
+      const double* pLf = L_leaf ? pEf : slot(sLf);
+      double d[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const double Ef = pEf[e * T], El = pEl[e * T], Er = pEr[e * T];
+        const double sEfv = pEf[vstride + e * T], sElv = pEl[vstride + e * T];
+        const double Lf = L_leaf ? p[e] : pLf[e * T];
+        const double sLfv = L_leaf ? ps[e] : pLf[vstride + e * T];
+        const double Lr = L_leaf ? p[e] : rhoL[e];
+        const double A = Er + Lf, Bv = El + Lr, R = Er + Lr;
+        d[0] = d[0] + sEfv * A;  d[1] = d[1] + sLfv * A;
+        d[2] = d[2] + sElv * Bv; d[3] = d[3] + ps[e] * Bv;
+        d[4] = d[4] + sEfv * R;  d[5] = d[5] + ps[e] * R;
+        rhoL[e] = R;
+      }
+      reduce(d);
+      return d[0] < 0 || d[1] < 0 || d[2] < 0 || d[3] < 0 || d[4] < 0 || d[5] < 0;
+    }
     const double* pEf = slot(sEf);
     const bool e_leaf = (sEl == sEf);
     if (e_leaf && L_leaf) {
@@ -417,29 +554,53 @@ struct DeviceBackend {
     return d[0] < 0 || d[1] < 0 || d[2] < 0 || d[3] < 0 || d[4] < 0 || d[5] < 0;
   }
 
-  // streaming window variance (Welford) — sample_M⁻¹(Diagonal, X), mcmc.jl:209
-  __device__ __forceinline__ void welford_reset() {
-    double* m = slot(n_slots - 1); double* s = slot(n_slots - 2);
+  // streaming window statistics — sample_M⁻¹, mcmc.jl:209 (Diagonal) / :211 (Symmetric)
+  __device__ __forceinline__ void metric_reset(int kind) {
+    double* m = slot(n_slots - 1); double* sv = slot(n_slots - 2);
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) { m[e * T] = 0.0; s[e * T] = 0.0; }
+    for (int e = 0; e < EPL; ++e) { m[e * T] = 0.0; sv[e * T] = 0.0; }
+    if (kind == DHMC_METRIC_SYMMETRIC) {
+      for (int j = 0; j < D; ++j) {
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) if (tid + e * T < D) covt[(size_t)j * D + tid + e * T] = 0.0;
+      }
+    }
   }
-  __device__ __forceinline__ void welford_push(int n) {
-    double* m = slot(n_slots - 1); double* s = slot(n_slots - 2);
+  __device__ __forceinline__ void metric_push(int kind, int n) {
+    double* m = slot(n_slots - 1); double* sv = slot(n_slots - 2);
     const double dn = (double)n;
+    double dl[EPL];
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
       const double mean = m[e * T];
       const double dlt = q[e] - mean;
       const double mean1 = mean + dlt / dn;
       m[e * T] = mean1;
-      s[e * T] = s[e * T] + dlt * (q[e] - mean1);
+      dl[e] = dlt;
+      if (kind == DHMC_METRIC_DIAGONAL) sv[e * T] = sv[e * T] + dlt * (q[e] - mean1);
+      else xs[tid + e * T] = q[e] - mean1;
+    }
+    if (kind == DHMC_METRIC_SYMMETRIC) {
+      // co-moments C[i][j] += δ_i (x_j − mean′_j), j ≤ i, stored transposed (coalesced over i)
+      group_sync();
+      double* col = covt + tid;
+      for (int j = 0; j < D; ++j, col += D) {
+        const double yj = xs[j];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          const int i = tid + e * T;
+          if (i < D && j <= i) col[e * T] = col[e * T] + dl[e] * yj;
+        }
+      }
+      group_sync();
     }
   }
-  __device__ __forceinline__ void welford_finish(int n) {
-    const double* s = slot(n_slots - 2);
+  __device__ __forceinline__ void metric_finish(int kind, int n) {
+    if (kind != DHMC_METRIC_DIAGONAL) return;   // Symmetric: finished by k_cov_finish + k_dense_factor
+    const double* sv = slot(n_slots - 2);
     const double dn1 = (double)(n - 1);
 #pragma unroll
-    for (int e = 0; e < EPL; ++e) minv[e] = valid(e) ? s[e * T] / dn1 : 1.0;
+    for (int e = 0; e < EPL; ++e) minv[e] = valid(e) ? sv[e * T] / dn1 : 1.0;
   }
 };
 

@@ -57,6 +57,8 @@ struct KArgs {
   int strict, randomize;
   double* out_phase;
   int chain_begin, chain_end;   // persistent kernels: chains [begin, end) of this launch
+  double *minv_dense, *wt, *covt;   // Symmetric metric: M⁻¹, Wᵀ, co-moments, each [B][D][D]
+  int xs_doubles;               // shared-memory staging vector (0 unless the dense arrays exist)
 };
 
 // Register budget: minimum resident CTAs per SM the compiler must allow for.
@@ -67,12 +69,14 @@ __host__ __device__ constexpr int min_ctas(int W, int EPL) {
   return W == 1 ? 16 : W == 2 ? 8 : W == 4 ? (EPL >= 8 ? DHMC_MINCTAS_W4E8 : 4) : 2;
 }
 
-template <int EPL, int FAM, int W>
-__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W>& b, const KArgs& a,
+template <int EPL, int FAM, int W, bool DN>
+__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN>& b, const KArgs& a,
                                               unsigned char* smem) {
   b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5;
   b.D = a.D;
-  const SmemLayout L = smem_layout(W, a.n_sm, b.stride);
+  const SmemLayout L = smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles);
+  b.xs = reinterpret_cast<double*>(smem + L.xs_off);
+  b.Mrow = nullptr; b.Wt = nullptr; b.covt = nullptr;
   b.red = reinterpret_cast<double*>(smem + L.red_off);
   b.red_buf = 0;
   b.rexp_cache = 0.0; b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;
@@ -90,8 +94,8 @@ __device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc, int be
   return s_misc[0];
 }
 
-template <int EPL, int FAM, int W>
-__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W>& b, const KArgs& a, long c,
+template <int EPL, int FAM, int W, bool DN>
+__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN>& b, const KArgs& a, long c,
                                            bool with_p) {
   b.chain = c;
   const size_t base = (size_t)c * a.D;
@@ -106,9 +110,16 @@ __device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W>& b, const 
     b.rhoL[e] = 0.0;
   }
   b.lq = a.lq[c];
+  const size_t dd = (size_t)a.D * a.D;
+  if (a.covt) b.covt = a.covt + (size_t)c * dd;
+  if constexpr (DN) {
+    b.Mrow = a.minv_dense + (size_t)c * dd;
+    b.Wt = a.wt + (size_t)c * dd;
+    if (with_p) b.matvec(b.p, b.ps);
+  }
 }
-template <int EPL, int FAM, int W>
-__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W>& b, double* dst,
+template <int EPL, int FAM, int W, bool DN>
+__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN>& b, double* dst,
                                           const double (&v)[EPL], size_t base, int D) {
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
@@ -118,9 +129,9 @@ __device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W>& b, d
 }
 
 // ------------------------------------------------------------------ k_nuts
-template <int EPL, int FAM, int W>
+template <int EPL, int FAM, int W, bool DN>
 struct DrawSink {
-  DeviceBackend<EPL, FAM, W>& b;
+  DeviceBackend<EPL, FAM, W, DN>& b;
   const KArgs& a;
   long c;
   __device__ __forceinline__ void operator()(int n, const dhmc_tree_stats& ts, double e) {
@@ -134,25 +145,25 @@ struct DrawSink {
   }
 };
 
-template <int EPL, int FAM, int W>
+template <int EPL, int FAM, int W, bool DN>
 __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_nuts(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W> b;
+  DeviceBackend<EPL, FAM, W, DN> b;
   setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride).misc_off);
+  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
   for (;;) {
     const int c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W, DN>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
-    DrawSink<EPL, FAM, W> sink{b, a, c};
+    DrawSink<EPL, FAM, W, DN> sink{b, a, c};
     const double eps_next = m.run(a.t0, a.N, a.eps[c], a.cfg, a.p_override,
                                   a.dir_override ? a.dir_override + c : nullptr, sink);
     const size_t base = (size_t)c * a.D;
     store_vec(b, a.q, b.q, base, a.D);
     store_vec(b, a.g, b.g, base, a.D);
-    if (a.cfg.metric != DHMC_METRIC_NOTHING) store_vec(b, a.minv, b.minv, base, a.D);
+    if (a.cfg.metric == DHMC_METRIC_DIAGONAL) store_vec(b, a.minv, b.minv, base, a.D);
     if (b.tid == 0) {
       a.lq[c] = b.lq;
       a.eps[c] = eps_next;
@@ -163,17 +174,17 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_nuts(const KArgs a
 }
 
 // ------------------------------------------------------------------ k_search
-template <int EPL, int FAM, int W>
+template <int EPL, int FAM, int W, bool DN>
 __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_search(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W> b;
+  DeviceBackend<EPL, FAM, W, DN> b;
   setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride).misc_off);
+  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
   for (;;) {
     const int c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W, DN>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
     const double eps = m.find_initial_stepsize(a.s_init, a.s_thresh, a.s_maxiter, a.p_override);
     if (b.tid == 0) {
@@ -185,10 +196,10 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_search(const KArgs
 
 // ------------------------------------------------------------------ k_leapfrog
 // Streaming leapfrog: reads q, p, ∇ℓ, M⁻¹ (32·D B), writes q′, p′, ∇ℓ′ (24·D B).
-template <int EPL, int FAM, int W>
+template <int EPL, int FAM, int W, bool DN>
 __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_leapfrog(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W> b;
+  DeviceBackend<EPL, FAM, W, DN> b;
   setup_backend(b, a, smem);
   for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
     load_chain(b, a, c, true);
@@ -242,10 +253,10 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_eval(const KArgs a
 }
 
 // ------------------------------------------------------------------ k_phase
-template <int EPL, int FAM, int W>
+template <int EPL, int FAM, int W, bool DN>
 __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_phase(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W> b;
+  DeviceBackend<EPL, FAM, W, DN> b;
   setup_backend(b, a, smem);
   for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
     load_chain(b, a, c, true);
@@ -253,6 +264,85 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_phase(const KArgs 
     if (b.tid == 0) a.out_phase[c] = H;
     if (W > 1) __syncthreads();
   }
+}
+
+// ------------------------------------------------------------------ Symmetric metric
+// Lower Cholesky factor of the row-major symmetric A, stored transposed:
+// Lt[k*D + i] = L[i][k].  One CTA; per output element the subtraction order is
+// k = 0..j-1, as in the oracle (cholesky_lower).  Returns false if not positive definite.
+__device__ bool chol_lower_t(const double* A, double* Lt, int D) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int j = 0; j < D; ++j) {
+    double s = A[(size_t)j * D + j];
+    for (int k = 0; k < j; ++k) { const double l = Lt[(size_t)k * D + j]; s = s - l * l; }
+    if (!(s > 0.0) || !dm_isfinite(s)) return false;      // uniform across the CTA
+    const double d = dm_sqrt(s);
+    __syncthreads();
+    if (tid == 0) Lt[(size_t)j * D + j] = d;
+    for (int i = j + 1 + tid; i < D; i += nt) {
+      double t = A[(size_t)i * D + j];
+      for (int k = 0; k < j; ++k) t = t - Lt[(size_t)k * D + i] * Lt[(size_t)k * D + j];
+      Lt[(size_t)j * D + i] = t / d;
+    }
+    __syncthreads();
+  }
+  return true;
+}
+// W = cholesky(inv(M⁻¹)).L — hamiltonian.jl:73, restated as in oracle dense_factor():
+// C = chol(M⁻¹), Ci = C⁻¹, M = CiᵀCi, W = chol(M); W is stored transposed in wt.
+__global__ void k_dense_factor(const double* minv_dense, double* wt, double* tmp, int* status, int D, int B) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const size_t dd = (size_t)D * D;
+  double* Ct = tmp + (size_t)blockIdx.x * 3 * dd;
+  double* Ci = Ct + dd;
+  double* M = Ci + dd;
+  for (int c = blockIdx.x; c < B; c += gridDim.x) {
+    const double* A = minv_dense + (size_t)c * dd;
+    bool ok = chol_lower_t(A, Ct, D);
+    if (ok) {
+      for (int j = tid; j < D; j += nt) {                 // Ci = C⁻¹, one column per thread
+        Ci[(size_t)j * D + j] = 1.0 / Ct[(size_t)j * D + j];
+        for (int i = j + 1; i < D; ++i) {
+          double sacc = 0.0;
+          for (int k = j; k < i; ++k) sacc = sacc - Ct[(size_t)k * D + i] * Ci[(size_t)k * D + j];
+          Ci[(size_t)i * D + j] = sacc / Ct[(size_t)i * D + i];
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < D; i += nt)                   // M = Ciᵀ Ci
+        for (int j = 0; j <= i; ++j) {
+          double sacc = 0.0;
+          for (int k = i; k < D; ++k) sacc = sacc + Ci[(size_t)k * D + i] * Ci[(size_t)k * D + j];
+          M[(size_t)i * D + j] = sacc; M[(size_t)j * D + i] = sacc;
+        }
+      __syncthreads();
+      ok = chol_lower_t(M, wt + (size_t)c * dd, D);
+    }
+    if (!ok && tid == 0) atomicOr(status + c, (int)DHMC_CHAIN_NOT_POSDEF);
+    __syncthreads();
+  }
+}
+// M⁻¹ = regularize_M⁻¹(Symmetric(cov(X; dims = 2)), λ) — mcmc.jl:211, :218-221, from the
+// streamed co-moments (transposed lower) of a window of n draws.
+__global__ void k_cov_finish(const double* covt, double* minv_dense, int n, double lambda, int D, int B) {
+  const size_t dd = (size_t)D * D;
+  const double dn1 = (double)(n - 1);
+  for (int c = blockIdx.x; c < B; c += gridDim.x) {
+    const double* ct = covt + (size_t)c * dd;
+    double* out = minv_dense + (size_t)c * dd;
+    for (int i = threadIdx.x; i < D; i += blockDim.x)
+      for (int j = 0; j <= i; ++j) {
+        const double sij = ct[(size_t)j * D + i] / dn1;
+        double v = (1 - lambda) * sij;
+        if (i == j) v = v + lambda * sij;
+        out[(size_t)i * D + j] = v; out[(size_t)j * D + i] = v;
+      }
+  }
+}
+__global__ void k_broadcast_mat(double* dst, const double* src, size_t dd, size_t B) {
+  const size_t n = dd * B;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i % dd];
 }
 
 // broadcast a D-vector (or scalar when D == 1) to all chains
@@ -290,6 +380,10 @@ struct dhmc_handle {
   double last_ms = 0;
   int64_t last_steps = 0;
   bool has_position = false, has_eps = false;
+  bool dense = false;               // κ is a Symmetric (dense) metric
+  double *minv_dense = nullptr, *wt = nullptr, *covt = nullptr, *dense_tmp = nullptr;
+  int reg_ctas[2] = {0, 0};         // occupancy of k_nuts (diag, dense)
+  size_t smem_sm = 0, smem_cta_max = 0;
   std::string err;
 };
 
@@ -339,16 +433,76 @@ static int dispatch(int W, int epl, int fam, F&& f) {
 }
 
 enum KernelId { K_NUTS, K_SEARCH, K_LEAPFROG, K_EVAL, K_PHASE };
+struct dhmc_handle;
 
+// dense (Symmetric metric) kernels are instantiated for the layouts of D <= 512
+constexpr bool dense_layout(int W, int EPL) { return W == 1 || (W == 2) || (W == 4 && EPL == 4); }
 template <int EPL, int FAM, int W>
-static const void* kernel_ptr(KernelId k) {
-  switch (k) {
-    case K_NUTS: return (const void*)k_nuts<EPL, FAM, W>;
-    case K_SEARCH: return (const void*)k_search<EPL, FAM, W>;
-    case K_LEAPFROG: return (const void*)k_leapfrog<EPL, FAM, W>;
-    case K_EVAL: return (const void*)k_eval<EPL, FAM, W>;
-    default: return (const void*)k_phase<EPL, FAM, W>;
+static const void* kernel_ptr(KernelId k, bool dense) {
+  if (dense) {
+    if constexpr (dense_layout(W, EPL)) {
+      switch (k) {
+        case K_NUTS: return (const void*)k_nuts<EPL, FAM, W, true>;
+        case K_SEARCH: return (const void*)k_search<EPL, FAM, W, true>;
+        case K_LEAPFROG: return (const void*)k_leapfrog<EPL, FAM, W, true>;
+        case K_PHASE: return (const void*)k_phase<EPL, FAM, W, true>;
+        default: break;
+      }
+    } else {
+      return nullptr;
+    }
   }
+  switch (k) {
+    case K_NUTS: return (const void*)k_nuts<EPL, FAM, W, false>;
+    case K_SEARCH: return (const void*)k_search<EPL, FAM, W, false>;
+    case K_LEAPFROG: return (const void*)k_leapfrog<EPL, FAM, W, false>;
+    case K_EVAL: return (const void*)k_eval<EPL, FAM, W>;
+    default: return (const void*)k_phase<EPL, FAM, W, false>;
+  }
+}
+
+// Plan the persistent kernels for the current metric kind: CTAs per SM (register
+// limited), how many slots fit in shared memory, and the global scratch arena.
+static int plan(dhmc_handle* h) {
+  const int T = h->T;
+  const size_t B = (size_t)h->cfg.n_chains;
+  const size_t slot_doubles = h->stride * (h->dense ? 2 : 1);
+  const size_t slot_bytes = sizeof(double) * slot_doubles;
+  const size_t xs = h->minv_dense ? h->stride : 0;
+  const SmemLayout L0 = smem_layout(h->W, 0, slot_doubles, xs);
+  h->smem_light = L0.total;
+  int& reg_ctas = h->reg_ctas[h->dense ? 1 : 0];
+  if (reg_ctas == 0) {
+    int rc = dispatch(h->W, h->EPL, h->cfg.family, [&](auto Wc, auto E, auto Fm) -> int {
+      constexpr int WW = decltype(Wc)::value;
+      constexpr int EP = decltype(E)::value;
+      constexpr int FA = decltype(Fm)::value;
+      const void* fn = kernel_ptr<EP, FA, WW>(K_NUTS, h->dense);
+      if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
+      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, fn, T, L0.total);
+      if (e != cudaSuccess) { h->err = std::string("occupancy query: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
+      return DHMC_OK;
+    });
+    if (rc != DHMC_OK) return rc;
+  }
+  if (reg_ctas < 1) { h->err = "kernel does not fit on an SM"; return DHMC_ECUDA; }
+  const int ctas = h->cfg.ctas_per_sm > 0 ? std::min(h->cfg.ctas_per_sm, reg_ctas) : reg_ctas;
+  // optionally leave part of the unified SM memory to L1
+  size_t l1_reserve = 0;
+  if (const char* ev = std::getenv("DHMC_L1_RESERVE_KB")) l1_reserve = (size_t)std::atol(ev) * 1024;
+  size_t per_cta = (h->smem_sm - std::min(l1_reserve, h->smem_sm / 2)) / ctas - 1024;   // 1 KB system reservation per CTA
+  if (per_cta > h->smem_cta_max) per_cta = h->smem_cta_max;
+  long n_sm = per_cta > L0.total ? (long)((per_cta - L0.total) / slot_bytes) : 0;
+  const int pool = h->n_slots - kWelfordSlots;   // the two highest slots stay in global memory
+  if (n_sm > pool) n_sm = pool;
+  h->n_sm = (int)n_sm;
+  h->smem_bytes = smem_layout(h->W, h->n_sm, slot_doubles, xs).total;
+  h->grid = (int)std::min<size_t>((size_t)ctas * h->sm_count, B);
+  h->light_grid = (int)std::min<size_t>((size_t)h->sm_count * 16, B);
+  h->scratch_per_cta = (size_t)(h->n_slots - h->n_sm) * slot_doubles;
+  cudaFree(h->scratch); h->scratch = nullptr;
+  CK(cudaMalloc(&h->scratch, sizeof(double) * h->scratch_per_cta * (size_t)h->grid));
+  return DHMC_OK;
 }
 
 static KArgs base_args(dhmc_handle* h) {
@@ -361,9 +515,11 @@ static KArgs base_args(dhmc_handle* h) {
   a.max_depth = h->cfg.max_depth; a.min_delta = h->cfg.min_delta;
   a.t0 = h->t;
   a.scratch = h->scratch; a.scratch_per_cta = h->scratch_per_cta;
-  a.n_sm = h->n_sm; a.n_slots = h->n_slots; a.stride = h->stride;
+  a.n_sm = h->n_sm; a.n_slots = h->n_slots; a.stride = h->stride * (h->dense ? 2 : 1);
   a.counter = h->counter; a.total_steps = h->total_steps;
   a.chain_begin = 0; a.chain_end = (int)h->cfg.n_chains;
+  a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr;
+  a.xs_doubles = h->minv_dense ? (int)((size_t)h->T * h->EPL) : 0;
   return a;
 }
 
@@ -381,7 +537,7 @@ static int read_timer(dhmc_handle* h) {
 static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_steps = true) {
   const bool heavy = (k == K_NUTS || k == K_SEARCH);
   if (!heavy) { a.n_sm = 0; }
-  const size_t smem = heavy ? h->smem_bytes : h->smem_light;
+  const size_t smem = heavy ? h->smem_bytes : smem_layout(h->W, 0, a.stride, (size_t)a.xs_doubles).total;
   int grid = heavy ? h->grid : h->light_grid;
   if (heavy) grid = std::max(1, std::min(grid, a.chain_end - a.chain_begin));
   if (heavy) {
@@ -393,7 +549,8 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_st
     constexpr int WW = decltype(Wc)::value;
     constexpr int EPL = decltype(E)::value;
     constexpr int FAM = decltype(Fm)::value;
-    const void* fn = kernel_ptr<EPL, FAM, WW>(k);
+    const void* fn = kernel_ptr<EPL, FAM, WW>(k, h->dense);
+    if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
     void* params[] = {(void*)&a};
@@ -456,6 +613,7 @@ int dhmc_destroy(dhmc_handle* h) {
   cudaFree(h->q); cudaFree(h->g); cudaFree(h->lq); cudaFree(h->p); cudaFree(h->minv); cudaFree(h->eps);
   cudaFree(h->mparams); cudaFree(h->status); cudaFree(h->scratch); cudaFree(h->counter);
   cudaFree(h->total_steps);
+  cudaFree(h->minv_dense); cudaFree(h->wt); cudaFree(h->covt); cudaFree(h->dense_tmp);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
@@ -523,38 +681,12 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   k_fill<<<1024, 256, 0, h->stream>>>(h->minv, 1.0, B * D);   // κ = GaussianKineticEnergy(D), mcmc.jl:130
   h->launches += 1;
 
-  // ---- plan the persistent kernels: CTAs per SM, on-chip slots, scratch ----
-  const size_t slot_bytes = sizeof(double) * h->stride;
-  const SmemLayout L0 = smem_layout(h->W, 0, h->stride);
-  h->smem_light = L0.total;
-  int reg_ctas = 0;
-  int rc = dispatch(T / 32, EPL, cfg->family, [&](auto Wc, auto E, auto Fm) -> int {
-    constexpr int WW = decltype(Wc)::value;
-    constexpr int EP = decltype(E)::value;
-    constexpr int FA = decltype(Fm)::value;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, k_nuts<EP, FA, WW>, T, L0.total);
-    if (e != cudaSuccess) { h->err = std::string("occupancy query: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
-    return DHMC_OK;
-  });
-  if (rc != DHMC_OK) return fail(rc);
-  if (reg_ctas < 1) { h->err = "kernel does not fit on an SM"; return fail(DHMC_ECUDA); }
-  int ctas = cfg->ctas_per_sm > 0 ? std::min(cfg->ctas_per_sm, reg_ctas) : reg_ctas;
-  const size_t smem_sm = (size_t)prop.sharedMemPerMultiprocessor;        // 228 KB
-  const size_t smem_cta_max = (size_t)prop.sharedMemPerBlockOptin;       // 227 KB
-  // leave part of the unified SM memory to L1 (register spills and the global-scratch slots go through it)
-  size_t l1_reserve = 0;
-  if (const char* ev = std::getenv("DHMC_L1_RESERVE_KB")) l1_reserve = (size_t)std::atol(ev) * 1024;
-  size_t per_cta = (smem_sm - std::min(l1_reserve, smem_sm / 2)) / ctas - 1024;   // 1 KB system reservation per CTA
-  if (per_cta > smem_cta_max) per_cta = smem_cta_max;
-  long n_sm = per_cta > L0.total ? (long)((per_cta - L0.total) / slot_bytes) : 0;
-  const int pool = h->n_slots - kWelfordSlots;   // the two highest slots stay in global memory
-  if (n_sm > pool) n_sm = pool;
-  h->n_sm = (int)n_sm;
-  h->smem_bytes = smem_layout(h->W, h->n_sm, h->stride).total;
-  h->grid = (int)std::min<size_t>((size_t)ctas * h->sm_count, B);
-  h->light_grid = (int)std::min<size_t>((size_t)h->sm_count * 16, B);
-  h->scratch_per_cta = (size_t)(h->n_slots - h->n_sm) * h->stride;
-  CKC(cudaMalloc(&h->scratch, sizeof(double) * h->scratch_per_cta * (size_t)h->grid));
+  h->smem_sm = (size_t)prop.sharedMemPerMultiprocessor;          // 228 KB
+  h->smem_cta_max = (size_t)prop.sharedMemPerBlockOptin;         // 227 KB
+  {
+    int rcp = plan(h);
+    if (rcp != DHMC_OK) return fail(rcp);
+  }
   CKC(cudaStreamSynchronize(h->stream));
 #undef CKC
   *out = h;
@@ -600,6 +732,61 @@ int dhmc_random_position(dhmc_handle* h) {
   return eval_position(h, true);
 }
 
+static int ensure_dense(dhmc_handle* h) {
+  if (h->minv_dense) return DHMC_OK;
+  if (h->cfg.dim > 512) { h->err = "dense (Symmetric) metric: dim <= 512 in this build"; return DHMC_EARG; }
+  const size_t B = (size_t)h->cfg.n_chains, dd = (size_t)h->cfg.dim * h->cfg.dim;
+  CK(cudaMalloc(&h->minv_dense, sizeof(double) * B * dd));
+  CK(cudaMalloc(&h->wt, sizeof(double) * B * dd));
+  CK(cudaMalloc(&h->covt, sizeof(double) * B * dd));
+  const int fgrid = (int)std::min<size_t>((size_t)h->sm_count * 4, B);
+  CK(cudaMalloc(&h->dense_tmp, sizeof(double) * 3 * dd * (size_t)fgrid));
+  CK(cudaMemsetAsync(h->wt, 0, sizeof(double) * B * dd, h->stream));
+  return plan(h);   // the shared-memory layout now carries the mat-vec staging vector
+}
+// κ = GaussianKineticEnergy(Symmetric M⁻¹): W = cholesky(inv(M⁻¹)).L on device, then switch
+// the handle to the dense kernels.
+static int factor_and_switch(dhmc_handle* h) {
+  const size_t B = (size_t)h->cfg.n_chains;
+  const int fgrid = (int)std::min<size_t>((size_t)h->sm_count * 4, B);
+  CK(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));
+  k_dense_factor<<<fgrid, 128, 0, h->stream>>>(h->minv_dense, h->wt, h->dense_tmp, h->status, (int)h->cfg.dim, (int)B);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  const bool was = h->dense;
+  h->dense = true;
+  if (!was) { int rc = plan(h); if (rc != DHMC_OK) return rc; }
+  return sync_and_check_status(h, DHMC_CHAIN_NOT_POSDEF, "GaussianKineticEnergy: M⁻¹ is not positive definite (PosDefException)");
+}
+
+int dhmc_set_metric_dense(dhmc_handle* h, const double* minv, int broadcast) {
+  if (!h || !minv) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = ensure_dense(h);
+  if (rc != DHMC_OK) return rc;
+  const size_t B = (size_t)h->cfg.n_chains, dd = (size_t)h->cfg.dim * h->cfg.dim;
+  if (broadcast) {
+    double* tmp = nullptr;
+    CK(cudaMalloc(&tmp, sizeof(double) * dd));
+    CK(cudaMemcpyAsync(tmp, minv, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream));
+    k_broadcast_mat<<<1024, 256, 0, h->stream>>>(h->minv_dense, tmp, dd, B);
+    h->launches += 1;
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(tmp);
+  } else {
+    CK(cudaMemcpyAsync(h->minv_dense, minv, sizeof(double) * B * dd, cudaMemcpyHostToDevice, h->stream));
+  }
+  return factor_and_switch(h);
+}
+int dhmc_get_metric_dense(dhmc_handle* h, double* minv) {
+  if (!h || !minv) return DHMC_EARG;
+  if (!h->dense) { h->err = "the current metric is diagonal"; return DHMC_EARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemcpy(minv, h->minv_dense, sizeof(double) * (size_t)h->cfg.n_chains * h->cfg.dim * h->cfg.dim, cudaMemcpyDeviceToHost));
+  return DHMC_OK;
+}
+int dhmc_metric_is_dense(dhmc_handle* h, int32_t* dense) { if (!h || !dense) return DHMC_EARG; *dense = h->dense ? 1 : 0; return DHMC_OK; }
+
 int dhmc_set_metric(dhmc_handle* h, const double* minv, int broadcast) {
   if (!h) return DHMC_EARG;
   CK(cudaSetDevice(h->cfg.device));
@@ -618,6 +805,7 @@ int dhmc_set_metric(dhmc_handle* h, const double* minv, int broadcast) {
   }
   h->launches += 1;
   CK(cudaStreamSynchronize(h->stream));
+  if (h->dense) { h->dense = false; int rc = plan(h); if (rc != DHMC_OK) return rc; }
   return DHMC_OK;
 }
 
@@ -728,7 +916,7 @@ static int ensure_stage(dhmc_handle* h, int i, size_t bytes) {
   h->stage_bytes[i] = bytes;
   return DHMC_OK;
 }
-static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, const double* p_over_host,
+static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda, const double* p_over_host,
                     const uint32_t* dir_over_host, double* posterior, dhmc_tree_stats* stats,
                     double* eps_used, double* logdens, bool outputs_on_device, bool advance_t) {
   if (!h->has_position || !h->has_eps) { h->err = "set position and step size (or run the initial search) first"; return DHMC_EARG; }
@@ -760,6 +948,7 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, const double*
   KArgs a = base_args(h);
   a.N = N; a.cfg = cfg; a.p_override = d_p; a.dir_override = d_dir;
   a.out_q = d_post; a.out_stats = d_stats; a.out_eps = d_eps; a.out_lq = d_ld;
+  if (cfg.metric == DHMC_METRIC_SYMMETRIC) a.covt = h->covt;
   const size_t out_bytes = posterior ? sizeof(double) * B * n * D : 0;
   const int nchunks = (!outputs_on_device && B >= 4096 && out_bytes >= ((size_t)32 << 20)) ? 8 : 1;
   for (int ci = 0; ci < nchunks; ++ci) {
@@ -788,14 +977,28 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, const double*
   cleanup();
   h->last_steps = (int64_t)steps;
   if (advance_t) h->t += (uint32_t)N;
-  return sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q | DHMC_CHAIN_BAD_ACCEPTANCE,
-                               "sampling: non-finite position or acceptance rate");
+  rc = sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q | DHMC_CHAIN_BAD_ACCEPTANCE,
+                             "sampling: non-finite position or acceptance rate");
+  if (rc != DHMC_OK) return rc;
+  if (cfg.metric == DHMC_METRIC_DIAGONAL && h->dense) {   // κ ← Diagonal: back to the diagonal kernels
+    h->dense = false;
+    rc = plan(h);
+    if (rc != DHMC_OK) return rc;
+  }
+  if (cfg.metric == DHMC_METRIC_SYMMETRIC) {
+    // κ = GaussianKineticEnergy(regularize_M⁻¹(sample_M⁻¹(Symmetric, X), λ)) — mcmc.jl:282
+    const int fgrid = (int)std::min<size_t>((size_t)h->sm_count * 4, (size_t)h->cfg.n_chains);
+    k_cov_finish<<<fgrid, 128, 0, h->stream>>>(h->covt, h->minv_dense, N, lambda, (int)h->cfg.dim, (int)h->cfg.n_chains);
+    h->launches += 1;
+    rc = factor_and_switch(h);
+  }
+  return rc;
 }
 
 int dhmc_sample_tree(dhmc_handle* h, const double* p, const uint32_t* directions, dhmc_tree_stats* stats) {
   if (!h) return DHMC_EARG;
   AdaptConfig cfg{};
-  return run_nuts(h, 1, cfg, p, directions, nullptr, stats, nullptr, nullptr, false, true);
+  return run_nuts(h, 1, cfg, 0.0, p, directions, nullptr, stats, nullptr, nullptr, false, true);
 }
 
 int dhmc_warmup_stage(dhmc_handle* h, int32_t N, int32_t metric, const dhmc_dual_averaging* da,
@@ -805,7 +1008,7 @@ int dhmc_warmup_stage(dhmc_handle* h, int32_t N, int32_t metric, const dhmc_dual
   // TuningNUTS @argchecks — mcmc.jl:191-192
   if (!(N >= 20)) { h->err = "N ≥ 20"; return DHMC_EARG; }
   if (!(lambda >= 0)) { h->err = "λ ≥ 0"; return DHMC_EARG; }
-  if (metric != DHMC_METRIC_NOTHING && metric != DHMC_METRIC_DIAGONAL) { h->err = "metric: Nothing or Diagonal in this build"; return DHMC_EARG; }
+  if (metric != DHMC_METRIC_NOTHING && metric != DHMC_METRIC_DIAGONAL && metric != DHMC_METRIC_SYMMETRIC) { h->err = "metric: Nothing, Diagonal or Symmetric"; return DHMC_EARG; }
   AdaptConfig cfg{};
   cfg.metric = metric;
   if (da) {
@@ -815,20 +1018,21 @@ int dhmc_warmup_stage(dhmc_handle* h, int32_t N, int32_t metric, const dhmc_dual
     }
     cfg.adapt = 1; cfg.delta = da->delta; cfg.gamma = da->gamma; cfg.kappa = da->kappa; cfg.t0 = da->t0;
   }
-  return run_nuts(h, N, cfg, nullptr, nullptr, posterior, stats, eps_used, logdens, false, true);
+  if (metric == DHMC_METRIC_SYMMETRIC) { int rcd = ensure_dense(h); if (rcd != DHMC_OK) return rcd; }
+  return run_nuts(h, N, cfg, lambda, nullptr, nullptr, posterior, stats, eps_used, logdens, false, true);
 }
 
 int dhmc_mcmc(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats, double* logdens) {
   if (!h || N < 0) return DHMC_EARG;
   if (N == 0) return DHMC_OK;
   AdaptConfig cfg{};
-  return run_nuts(h, N, cfg, nullptr, nullptr, posterior, stats, nullptr, logdens, false, true);
+  return run_nuts(h, N, cfg, 0.0, nullptr, nullptr, posterior, stats, nullptr, logdens, false, true);
 }
 int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats, double* logdens) {
   if (!h || N < 0) return DHMC_EARG;
   if (N == 0) return DHMC_OK;
   AdaptConfig cfg{};
-  return run_nuts(h, N, cfg, nullptr, nullptr, posterior, stats, nullptr, logdens, true, true);
+  return run_nuts(h, N, cfg, 0.0, nullptr, nullptr, posterior, stats, nullptr, logdens, true, true);
 }
 
 int dhmc_last_total_steps(dhmc_handle* h, int64_t* steps) { if (!h || !steps) return DHMC_EARG; *steps = h->last_steps; return DHMC_OK; }

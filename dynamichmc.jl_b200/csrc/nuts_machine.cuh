@@ -336,7 +336,7 @@ struct NutsMachine {
   DHMC_M double run(uint32_t t0, int N, double eps, const AdaptConfig& cfg,
                      const double* p_override, const uint32_t* dir_override, Sink& sink) {
     DA A = da_init(eps > 0 ? eps : 1.0);
-    if (cfg.metric != DHMC_METRIC_NOTHING) b.welford_reset();
+    if (cfg.metric != DHMC_METRIC_NOTHING) b.metric_reset(cfg.metric);
     long total_steps = 0;
     for (int n = 0; n < N; ++n) {
       const double e = cfg.adapt ? dm_exp(A.logeps) : eps;   // current_ϵ :163
@@ -349,9 +349,9 @@ struct NutsMachine {
         if (a >= 0 && a <= 1) da_adapt(A, cfg, a);           // @argcheck 0 ≤ a ≤ 1
         else status |= DHMC_CHAIN_BAD_ACCEPTANCE;
       }
-      if (cfg.metric != DHMC_METRIC_NOTHING) b.welford_push(n + 1);
+      if (cfg.metric != DHMC_METRIC_NOTHING) b.metric_push(cfg.metric, n + 1);
     }
-    if (cfg.metric != DHMC_METRIC_NOTHING) b.welford_finish(N);   // sample_M⁻¹, mcmc.jl:209
+    if (cfg.metric != DHMC_METRIC_NOTHING) b.metric_finish(cfg.metric, N);   // sample_M⁻¹, mcmc.jl:209-211
     steps_out = total_steps;
     return cfg.adapt ? dm_exp(A.logepsbar) : eps;                // final_ϵ :170
   }

@@ -43,11 +43,12 @@ enum {
   DHMC_CHAIN_BAD_INITIAL = 1,   /* evaluate_ℓ(strict) failed, hamiltonian.jl:212-215 */
   DHMC_CHAIN_SEARCH_FAILED = 2, /* find_initial_stepsize, stepsize.jl:58 / :78 */
   DHMC_CHAIN_NONFINITE_Q = 4,   /* evaluate_ℓ: non-finite position, hamiltonian.jl:203 */
-  DHMC_CHAIN_BAD_ACCEPTANCE = 8 /* adapt_stepsize @argcheck 0 ≤ a ≤ 1, stepsize.jl:148 */
+  DHMC_CHAIN_BAD_ACCEPTANCE = 8, /* adapt_stepsize @argcheck 0 ≤ a ≤ 1, stepsize.jl:148 */
+  DHMC_CHAIN_NOT_POSDEF = 16     /* cholesky(inv(M⁻¹)) failed, hamiltonian.jl:73 (PosDefException) */
 };
 
 /* log-density family ids: see include/dhmc_models.h */
-enum { DHMC_METRIC_NOTHING = 0, DHMC_METRIC_DIAGONAL = 1 };
+enum { DHMC_METRIC_NOTHING = 0, DHMC_METRIC_DIAGONAL = 1, DHMC_METRIC_SYMMETRIC = 2 };
 
 typedef struct dhmc_handle dhmc_handle;
 
@@ -101,6 +102,12 @@ int dhmc_random_position(dhmc_handle* h);
 /* κ = GaussianKineticEnergy(Diagonal(minv)) (hamiltonian.jl:80); minv [D,B],
  * or [D] broadcast to all chains when broadcast != 0; NULL = identity (:87). */
 int dhmc_set_metric(dhmc_handle* h, const double* minv, int broadcast);
+/* κ = GaussianKineticEnergy(Symmetric M⁻¹) (hamiltonian.jl:73): minv is [D,D,B], or
+ * [D,D] for all chains when broadcast != 0.  W = cholesky(inv(M⁻¹)).L is computed on the
+ * device; a matrix that is not positive definite sets DHMC_CHAIN_NOT_POSDEF. */
+int dhmc_set_metric_dense(dhmc_handle* h, const double* minv, int broadcast);
+int dhmc_get_metric_dense(dhmc_handle* h, double* minv /* [D,D,B] */);
+int dhmc_metric_is_dense(dhmc_handle* h, int32_t* dense);
 /* ϵ per chain [B], or one value for all chains when broadcast != 0. */
 int dhmc_set_stepsize(dhmc_handle* h, const double* eps, int broadcast);
 /* Momentum of the phase point used by dhmc_leapfrog / dhmc_phase_logdensity. */
@@ -131,8 +138,8 @@ int dhmc_sample_tree(dhmc_handle* h, const double* p, const uint32_t* directions
 int dhmc_find_initial_stepsize(dhmc_handle* h, double initial_eps, double log_threshold,
                                int32_t maxiter_crossing);
 /* warmup(::TuningNUTS{M}) — mcmc.jl:258-286.  da == NULL: FixedStepsize
- * (stepsize.jl:181-189).  metric: DHMC_METRIC_NOTHING | _DIAGONAL.  lambda is
- * accepted for interface parity; it is the identity for Diagonal (mcmc.jl:223).
+ * (stepsize.jl:181-189).  metric: DHMC_METRIC_NOTHING | _DIAGONAL | _SYMMETRIC.  lambda is
+ * the shrinkage of regularize_M⁻¹ (mcmc.jl:218-221); identity for Diagonal (:223).
  * Outputs may be NULL: posterior [D,N,B], stats/eps_used/logdens [N,B]. */
 int dhmc_warmup_stage(dhmc_handle* h, int32_t N, int32_t metric, const dhmc_dual_averaging* da,
                       double lambda, double* posterior, dhmc_tree_stats* stats,

@@ -123,15 +123,90 @@ struct Model {
 };
 
 // ------------------------------------------------------------- Hamiltonian
-// GaussianKineticEnergy with Diagonal M⁻¹ — src/hamiltonian.jl:56-87.
+// Deterministic dense linear algebra used by the Symmetric metric.  The reference
+// calls LAPACK/BLAS (`cholesky(inv(M⁻¹)).L`, `Symmetric * v`), whose summation order
+// is unspecified; these restate the same mathematics with a fixed sequential
+// order per output element (what each GPU thread does for its own elements).
+inline bool cholesky_lower(const vec& A, int D, vec& L) {   // A = L Lᵀ, row-major
+  L.assign((size_t)D * D, 0.0);
+  for (int j = 0; j < D; ++j) {
+    double s = A[(size_t)j * D + j];
+    for (int k = 0; k < j; ++k) s = s - L[(size_t)j * D + k] * L[(size_t)j * D + k];
+    if (!(s > 0.0) || !dm_isfinite(s)) return false;          // PosDefException
+    const double d = dm_sqrt(s);
+    L[(size_t)j * D + j] = d;
+    for (int i = j + 1; i < D; ++i) {
+      double t = A[(size_t)i * D + j];
+      for (int k = 0; k < j; ++k) t = t - L[(size_t)i * D + k] * L[(size_t)j * D + k];
+      L[(size_t)i * D + j] = t / d;
+    }
+  }
+  return true;
+}
+// W = cholesky(inv(M⁻¹)).L — src/hamiltonian.jl:73: C = chol(M⁻¹); Cinv = C⁻¹; M = CinvᵀCinv; W = chol(M)
+inline bool dense_factor(const vec& Minv, int D, vec& W) {
+  vec C;
+  if (!cholesky_lower(Minv, D, C)) return false;
+  vec Ci((size_t)D * D, 0.0);
+  for (int j = 0; j < D; ++j) {
+    Ci[(size_t)j * D + j] = 1.0 / C[(size_t)j * D + j];
+    for (int i = j + 1; i < D; ++i) {
+      double s = 0.0;
+      for (int k = j; k < i; ++k) s = s - C[(size_t)i * D + k] * Ci[(size_t)k * D + j];
+      Ci[(size_t)i * D + j] = s / C[(size_t)i * D + i];
+    }
+  }
+  vec M((size_t)D * D, 0.0);
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double s = 0.0;
+      for (int k = i; k < D; ++k) s = s + Ci[(size_t)k * D + i] * Ci[(size_t)k * D + j];
+      M[(size_t)i * D + j] = s; M[(size_t)j * D + i] = s;
+    }
+  return cholesky_lower(M, D, W);
+}
+
+// GaussianKineticEnergy — src/hamiltonian.jl:56-87: Diagonal M⁻¹ (:80, :87) or dense
+// Symmetric M⁻¹ (:73).
 struct KineticEnergy {
-  vec minv;  // diag(M⁻¹)
-  vec w;     // W = Diagonal(.√inv.(diag(M⁻¹)))  (hamiltonian.jl:80)
-  explicit KineticEnergy(const vec& m) : minv(m), w(m.size()) {
+  bool dense = false;
+  int D = 0;
+  vec minv;  // diag(M⁻¹) [D]   or M⁻¹ [D*D] row-major (symmetric)
+  vec w;     // W = Diagonal(.√inv.(diag(M⁻¹))) [D]   or lower-triangular W [D*D], W Wᵀ = M
+  explicit KineticEnergy(const vec& m) : D((int)m.size()), minv(m), w(m.size()) {
     for (size_t i = 0; i < m.size(); ++i) w[i] = dm_sqrt(1.0 / m[i]);
   }
   KineticEnergy(int N, double m = 1.0) : KineticEnergy(vec(N, m)) {}  // :87
-  int size() const { return (int)minv.size(); }                      // :96
+  static KineticEnergy Dense(const vec& M, int D_) {                 // :73
+    KineticEnergy k(1);
+    k.dense = true; k.D = D_; k.minv = M;
+    if ((int)M.size() != D_ * D_) throw ArgumentError("checksquare(M⁻¹)");
+    if (!dense_factor(M, D_, k.w)) throw DynamicHMCError("PosDefException: M⁻¹ is not positive definite");
+    return k;
+  }
+  int size() const { return D; }                                     // :96
+  // M⁻¹ * p
+  vec apply_minv(const vec& p) const {
+    vec r(D);
+    if (!dense) { for (int i = 0; i < D; ++i) r[i] = minv[i] * p[i]; return r; }
+    for (int i = 0; i < D; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < D; ++j) acc = acc + minv[(size_t)i * D + j] * p[j];
+      r[i] = acc;
+    }
+    return r;
+  }
+  // W * z
+  vec apply_w(const vec& z) const {
+    vec r(D);
+    if (!dense) { for (int i = 0; i < D; ++i) r[i] = w[i] * z[i]; return r; }
+    for (int i = 0; i < D; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j <= i; ++j) acc = acc + w[(size_t)i * D + j] * z[j];
+      r[i] = acc;
+    }
+    return r;
+  }
 };
 
 // EvaluatedLogDensity — src/hamiltonian.jl:165-186
@@ -174,18 +249,13 @@ struct Hamiltonian {  // src/hamiltonian.jl:130-150
 
 // kinetic_energy — src/hamiltonian.jl:103: dot(p, M⁻¹ * p) / 2
 inline double kinetic_energy(const Hamiltonian& H, const vec& p) {
-  const vec& m = H.k.minv;
-  double s = canon_sum(H.T(), (int)p.size(), [&](int i) {
-    double ps = m[i] * p[i];
-    return p[i] * ps;
-  });
+  const vec ps = H.k.apply_minv(p);
+  double s = canon_sum(H.T(), (int)p.size(), [&](int i) { return p[i] * ps[i]; });
   return s / 2.0;
 }
 // calculate_p♯ — src/hamiltonian.jl:110
 inline vec calculate_psharp(const Hamiltonian& H, const vec& p) {
-  vec r(p.size());
-  for (size_t i = 0; i < p.size(); ++i) r[i] = H.k.minv[i] * p[i];
-  return r;
+  return H.k.apply_minv(p);
 }
 // logdensity(H, z) — src/hamiltonian.jl:251-256
 inline double logdensity(const Hamiltonian& H, const PhasePoint& z) {
@@ -202,10 +272,8 @@ inline PhasePoint leapfrog(const Hamiltonian& H, const PhasePoint& z, double eps
   const double h = eps / 2;
   vec pm(D), q1(D), p1(D);
   for (int i = 0; i < D; ++i) pm[i] = z.p[i] + h * z.Q.g[i];      // :277
-  for (int i = 0; i < D; ++i) {
-    double vel = H.k.minv[i] * pm[i];                             // :117 → :110
-    q1[i] = z.Q.q[i] + eps * vel;                                 // :278
-  }
+  const vec vel = H.k.apply_minv(pm);                             // :117 → :110
+  for (int i = 0; i < D; ++i) q1[i] = z.Q.q[i] + eps * vel[i];    // :278
   EvaluatedLogDensity Q1 = evaluate_l(H.l, q1);                   // :279
   for (int i = 0; i < D; ++i) p1[i] = pm[i] + h * Q1.g[i];        // :280
   return {Q1, p1};
@@ -226,9 +294,9 @@ struct Rng {
 // rand_p — src/hamiltonian.jl:124:  κ.W * randn(rng, D)
 inline vec rand_p(const dm_rng_key& key, uint32_t stream, uint32_t t, const KineticEnergy& k) {
   int D = k.size();
-  vec p(D);
-  for (int i = 0; i < D; ++i) p[i] = k.w[i] * dm_normal_elem(key, stream, t, (uint32_t)i);
-  return p;
+  vec z(D);
+  for (int i = 0; i < D; ++i) z[i] = dm_normal_elem(key, stream, t, (uint32_t)i);
+  return k.apply_w(z);
 }
 // random_position — src/mcmc.jl:108: rand(rng, N) .* 4 .- 2
 inline vec random_position(const dm_rng_key& key, int D) {
@@ -627,8 +695,51 @@ struct Welford {
   }
 };
 
+// sample_M⁻¹(Symmetric, X) = Symmetric(cov(X; dims = 2)) — mcmc.jl:211 (two-pass)
+inline vec sample_cov_twopass(const std::vector<vec>& X) {
+  size_t n = X.size(), D = X[0].size();
+  vec mean(D), C(D * D);
+  for (size_t i = 0; i < D; ++i) { double s = 0; for (size_t k = 0; k < n; ++k) s += X[k][i]; mean[i] = s / (double)n; }
+  for (size_t i = 0; i < D; ++i)
+    for (size_t j = 0; j <= i; ++j) {
+      double ss = 0;
+      for (size_t k = 0; k < n; ++k) ss += (X[k][i] - mean[i]) * (X[k][j] - mean[j]);
+      C[i * D + j] = C[j * D + i] = ss / (double)(n - 1);
+    }
+  return C;
+}
+// streaming co-moments (what the device accumulates): lower triangle, mirrored
+struct WelfordCov {
+  int64_t n = 0; int D; vec mean, c;
+  explicit WelfordCov(int D_) : D(D_), mean(D_, 0.0), c((size_t)D_ * D_, 0.0) {}
+  void push(const vec& x) {
+    n += 1;
+    vec d(D);
+    for (int i = 0; i < D; ++i) { d[i] = x[i] - mean[i]; mean[i] = mean[i] + d[i] / (double)n; }
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j <= i; ++j) c[(size_t)i * D + j] = c[(size_t)i * D + j] + d[i] * (x[j] - mean[j]);
+  }
+  vec covariance() const {
+    vec C((size_t)D * D);
+    for (int i = 0; i < D; ++i)
+      for (int j = 0; j <= i; ++j) C[(size_t)i * D + j] = C[(size_t)j * D + i] = c[(size_t)i * D + j] / (double)(n - 1);
+    return C;
+  }
+};
+// regularize_M⁻¹(Σ::Symmetric, λ) = (1 - λ) * Σ + λ * Diagonal(diag(Σ)) — mcmc.jl:218-221
+inline vec regularize_dense(const vec& S, int D, double lambda) {
+  vec R((size_t)D * D);
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      double v = (1 - lambda) * S[(size_t)i * D + j];
+      if (i == j) v = v + lambda * S[(size_t)i * D + i];
+      R[(size_t)i * D + j] = v;
+    }
+  return R;
+}
+
 enum StageKind { STAGE_NOTHING = 0, STAGE_STEPSIZE_SEARCH = 1, STAGE_TUNING = 2 };
-enum MetricKind { METRIC_NOTHING = 0, METRIC_DIAGONAL = 1 };
+enum MetricKind { METRIC_NOTHING = 0, METRIC_DIAGONAL = 1, METRIC_SYMMETRIC = 2 };
 struct Stage {
   int kind = STAGE_TUNING; int N = 0; int metric = METRIC_NOTHING; bool dual_averaging = true;
   double lambda = 0;  // regularisation; identity for Diagonal (mcmc.jl:223)
@@ -682,6 +793,7 @@ inline ChainOutput warmup_tuning(Sampler& S, const Stage& stage, WarmupState& st
   double fixed_eps = st.eps;
   if (stage.dual_averaging) da = initial_adaptation_state(stage.da, st.eps);
   Welford wf(S.l.D);
+  WelfordCov wc(stage.metric == METRIC_SYMMETRIC ? S.l.D : 1);
   for (int i = 0; i < stage.N; ++i) {
     double eps = stage.dual_averaging ? current_eps(da) : fixed_eps;
     out.eps_used.push_back(eps);
@@ -690,12 +802,16 @@ inline ChainOutput warmup_tuning(Sampler& S, const Stage& stage, WarmupState& st
     S.t += 1;
     st.Q = Q;
     out.posterior.push_back(Q.q); out.logdensities.push_back(Q.lq); out.stats.push_back(stats);
-    if (stage.metric != METRIC_NOTHING && S.welford) wf.push(Q.q);
+    if (stage.metric == METRIC_DIAGONAL && S.welford) wf.push(Q.q);
+    if (stage.metric == METRIC_SYMMETRIC && S.welford) wc.push(Q.q);
     if (stage.dual_averaging) da = adapt_stepsize(stage.da, da, stats.acceptance_rate);
   }
-  if (stage.metric != METRIC_NOTHING) {
+  if (stage.metric == METRIC_DIAGONAL) {
     vec minv = S.welford ? wf.variance() : sample_minv_twopass(out.posterior);
     st.k = KineticEnergy(minv);  // regularize_M⁻¹(::Diagonal) is the identity — mcmc.jl:223
+  } else if (stage.metric == METRIC_SYMMETRIC) {
+    vec C = S.welford ? wc.covariance() : sample_cov_twopass(out.posterior);
+    st.k = KineticEnergy::Dense(regularize_dense(C, S.l.D, stage.lambda), S.l.D);   // mcmc.jl:282
   }
   st.eps = stage.dual_averaging ? final_eps(da) : fixed_eps;
   return out;
@@ -718,7 +834,9 @@ inline ChainOutput mcmc(Sampler& S, int N, WarmupState& st) {
 // initialize_warmup_state — mcmc.jl:129-132 (strict evaluation)
 inline WarmupState initialize_warmup_state(const Sampler& S, const vec* q, const vec* minv, const double* eps) {
   vec q0 = q ? *q : random_position(S.key, S.l.D);
-  KineticEnergy k = minv ? KineticEnergy(*minv) : KineticEnergy(S.l.D);
+  KineticEnergy k = !minv ? KineticEnergy(S.l.D)
+                    : ((int)minv->size() == S.l.D * S.l.D && S.l.D > 1 ? KineticEnergy::Dense(*minv, S.l.D)
+                                                                      : KineticEnergy(*minv));
   return WarmupState{evaluate_l(S.l, q0, true), k, eps ? *eps : 0.0, eps != nullptr};
 }
 

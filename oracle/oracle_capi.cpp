@@ -13,6 +13,11 @@ using namespace orc;
 
 namespace {
 thread_local std::string g_err;
+thread_local int g_dense = 0;   // when set, `minv` pointers are D x D row-major (Symmetric metric)
+KineticEnergy make_k(const double* minv, int D) {
+  if (g_dense) return KineticEnergy::Dense(vec(minv, minv + (size_t)D * D), D);
+  return KineticEnergy(vec(minv, minv + (size_t)D));
+}
 Model make_model(int family, int D, const double* params, int nparams, int T, int always_div) {
   Model m; m.family = family; m.D = D; m.T = T; m.always_divergent = always_div != 0;
   if (params && nparams > 0) m.params.assign(params, params + nparams);
@@ -33,6 +38,18 @@ int guarded(F f) {
 extern "C" {
 
 const char* orc_last_error() { return g_err.c_str(); }
+void orc_set_dense(int flag) { g_dense = flag; }
+// W = cholesky(inv(M⁻¹)).L; returns 0 ok, 2 not positive definite
+int orc_dense_factor(int D, const double* minv, double* W) {
+  vec w;
+  if (!dense_factor(vec(minv, minv + (size_t)D * D), D, w)) return 2;
+  std::memcpy(W, w.data(), sizeof(double) * (size_t)D * D);
+  return 0;
+}
+void orc_rand_p(uint64_t seed, uint64_t chain, uint32_t stream, uint32_t t, int D, const double* minv, double* out) {
+  vec p = rand_p(dm_make_key(seed, chain), stream, t, make_k(minv, D));
+  std::memcpy(out, p.data(), sizeof(double) * D);
+}
 
 // ------------------------------------------------------------------- math
 void orc_math(int fn, int n, const double* x, const double* y, double* out) {
@@ -136,13 +153,13 @@ double orc_logdensity_and_gradient(int family, int D, const double* params, int 
 }
 double orc_kinetic_energy(int D, int T, const double* minv, const double* p) {
   Model m = make_model(0, D, nullptr, 0, T, 0);
-  Hamiltonian H(KineticEnergy(vec(minv, minv + D)), m);
+  Hamiltonian H(make_k(minv, D), m);
   return kinetic_energy(H, vec(p, p + D));
 }
 // logdensity(H, z) with explicit lq (tests the −Inf fallbacks, test_hamiltonian.jl:196-200)
 double orc_phase_logdensity(int D, int T, const double* minv, double lq, const double* p) {
   Model m = make_model(0, D, nullptr, 0, T, 0);
-  Hamiltonian H(KineticEnergy(vec(minv, minv + D)), m);
+  Hamiltonian H(make_k(minv, D), m);
   PhasePoint z{{vec(D, 0.0), lq, vec(D, 0.0)}, vec(p, p + D)};
   return logdensity(H, z);
 }
@@ -159,7 +176,7 @@ int orc_leapfrog(int family, int D, const double* params, int T, const double* m
                  double* p, double* g, double* lq, double eps, int n_steps) {
   return guarded([&] {
     Model m = make_model(family, D, params, nparams_of(family, D), T, 0);
-    Hamiltonian H(KineticEnergy(vec(minv, minv + D)), m);
+    Hamiltonian H(make_k(minv, D), m);
     PhasePoint z{evaluate_l(m, vec(q, q + D)), vec(p, p + D)};
     for (int s = 0; s < n_steps; ++s) z = leapfrog(H, z, eps);
     std::memcpy(q, z.Q.q.data(), sizeof(double) * D);
@@ -209,7 +226,7 @@ int orc_sample_tree(int family, int D, const double* params, int T, const double
                     int accept_cap, int* n_accept) {
   return guarded([&] {
     Model m = make_model(family, D, params, nparams_of(family, D), T, always_divergent);
-    Hamiltonian H(KineticEnergy(vec(minv, minv + D)), m);
+    Hamiltonian H(make_k(minv, D), m);
     NUTS alg{max_depth, min_delta}; alg.check();
     auto Q = evaluate_l(m, vec(q, q + D), true);
     Rng rng{dm_make_key(seed, chain), t, 0};
@@ -241,7 +258,7 @@ int orc_find_initial_stepsize(int family, int D, const double* params, int T, co
                               double log_threshold, int maxiter, double* eps_out) {
   return guarded([&] {
     Model m = make_model(family, D, params, nparams_of(family, D), T, 0);
-    Hamiltonian H(KineticEnergy(vec(minv, minv + D)), m);
+    Hamiltonian H(make_k(minv, D), m);
     PhasePoint z{evaluate_l(m, vec(q, q + D), true), vec(p, p + D)};
     InitialStepsizeSearch par{initial_eps, log_threshold, maxiter}; par.check();
     *eps_out = find_initial_stepsize(par, local_log_acceptance_ratio(H, z));
@@ -250,7 +267,7 @@ int orc_find_initial_stepsize(int family, int D, const double* params, int T, co
 double orc_local_log_acceptance_ratio(int family, int D, const double* params, int T,
                                       const double* minv, const double* q, const double* p, double eps) {
   Model m = make_model(family, D, params, nparams_of(family, D), T, 0);
-  Hamiltonian H(KineticEnergy(vec(minv, minv + D)), m);
+  Hamiltonian H(make_k(minv, D), m);
   PhasePoint z{evaluate_l(m, vec(q, q + D), true), vec(p, p + D)};
   return local_log_acceptance_ratio(H, z)(eps);
 }
@@ -297,14 +314,15 @@ int orc_mcmc_with_warmup(int family, int D, const double* params, int T, int max
     Sampler S; S.l = make_model(family, D, params, nparams_of(family, D), T, 0);
     S.alg = NUTS{max_depth, min_delta}; S.key = dm_make_key(seed, chain); S.welford = welford != 0;
     auto stages = make_stages(n_stages, kind, stN, metric, da_on, da4, search3);
-    vec qv, mv; if (q0) qv.assign(q0, q0 + D); if (minv0) mv.assign(minv0, minv0 + D);
+    vec qv, mv; if (q0) qv.assign(q0, q0 + D);
+    if (minv0) mv.assign(minv0, minv0 + (g_dense ? (size_t)D * D : (size_t)D));
     auto r = mcmc_with_warmup(S, N, stages, q0 ? &qv : nullptr, minv0 ? &mv : nullptr, eps0);
     for (int i = 0; i < N; ++i) {
       if (posterior) std::memcpy(posterior + (size_t)i * D, r.inference.posterior[i].data(), sizeof(double) * D);
       if (stats) stats[i] = r.inference.stats[i];
       if (logdens) logdens[i] = r.inference.logdensities[i];
     }
-    if (minv_out) std::memcpy(minv_out, r.final_state.k.minv.data(), sizeof(double) * D);
+    if (minv_out) std::memcpy(minv_out, r.final_state.k.minv.data(), sizeof(double) * r.final_state.k.minv.size());
     if (eps_out) *eps_out = r.final_state.eps;
     if (state_q_out) std::memcpy(state_q_out, r.final_state.Q.q.data(), sizeof(double) * D);
     size_t off = 0;

@@ -15,7 +15,7 @@ _LIB = None
 
 FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL = 0, 1, 2
 STAGE_NOTHING, STAGE_SEARCH, STAGE_TUNING = 0, 1, 2
-METRIC_NOTHING, METRIC_DIAGONAL = 0, 1
+METRIC_NOTHING, METRIC_DIAGONAL, METRIC_SYMMETRIC = 0, 1, 2
 
 tree_stats_dtype = np.dtype(
     [("pi", "<f8"), ("depth", "<i8"), ("left", "<i8"), ("right", "<i8"),
@@ -80,6 +80,44 @@ def _d(a):
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _metric:
+    """Pass `minv` ([D] diagonal or [D, D] Symmetric) and flip the library's dense mode."""
+
+    def __init__(self, minv, D):
+        if minv is None:
+            minv = np.ones(D)
+        self.a = _d(minv)
+        self.dense = self.a.ndim == 2
+        if self.dense:
+            assert self.a.shape == (D, D)
+
+    def __enter__(self):
+        lib().orc_set_dense(C.c_int(int(self.dense)))
+        return self.a
+
+    def __exit__(self, *exc):
+        lib().orc_set_dense(C.c_int(0))
+
+
+def dense_factor(minv):
+    minv = _d(minv)
+    D = minv.shape[0]
+    W = np.empty((D, D))
+    st = lib().orc_dense_factor(C.c_int(D), _p(minv), _p(W))
+    if st != 0:
+        raise OracleError(st, "PosDefException")
+    return W
+
+
+def rand_p(seed, chain, stream, t, minv):
+    D = np.asarray(minv).shape[0]
+    out = np.empty(D)
+    with _metric(minv, D) as m:
+        lib().orc_rand_p(C.c_uint64(seed), C.c_uint64(chain), C.c_uint32(stream), C.c_uint32(t),
+                         C.c_int(D), _p(m), _p(out))
+    return out
 
 
 def _params(family, D, params):
@@ -203,24 +241,26 @@ def evaluate_l(family, q, params=None, T=32, strict=False):
 
 
 def kinetic_energy(minv, p, T=32):
-    minv, p = _d(minv), _d(p)
-    return lib().orc_kinetic_energy(C.c_int(p.size), C.c_int(T), _p(minv), _p(p))
+    p = _d(p)
+    with _metric(minv, p.size) as m:
+        return lib().orc_kinetic_energy(C.c_int(p.size), C.c_int(T), _p(m), _p(p))
 
 
 def phase_logdensity(minv, lq, p, T=32):
-    minv, p = _d(minv), _d(p)
-    return lib().orc_phase_logdensity(C.c_int(p.size), C.c_int(T), _p(minv), C.c_double(lq), _p(p))
+    p = _d(p)
+    with _metric(minv, p.size) as m:
+        return lib().orc_phase_logdensity(C.c_int(p.size), C.c_int(T), _p(m), C.c_double(lq), _p(p))
 
 
 def leapfrog(family, q, p, eps, minv=None, params=None, T=32, n_steps=1):
     q, p = _d(q).copy(), _d(p).copy()
     D = q.size
-    minv = np.ones(D) if minv is None else _d(minv)
     g = np.empty(D)
     lq = C.c_double()
     pr = _params(family, D, params)
-    _check(lib().orc_leapfrog(C.c_int(family), C.c_int(D), _p(pr), C.c_int(T), _p(minv), _p(q),
-                              _p(p), _p(g), C.byref(lq), C.c_double(eps), C.c_int(n_steps)))
+    with _metric(minv, D) as m:
+        _check(lib().orc_leapfrog(C.c_int(family), C.c_int(D), _p(pr), C.c_int(T), _p(m), _p(q),
+                                  _p(p), _p(g), C.byref(lq), C.c_double(eps), C.c_int(n_steps)))
     return q, p, g, lq.value
 
 
@@ -251,7 +291,6 @@ def sample_tree(family, q, eps, seed, chain, t, minv=None, params=None, T=32, ma
                 min_delta=-1000.0, p=None, directions=None, always_divergent=False):
     q = _d(q)
     D = q.size
-    minv = np.ones(D) if minv is None else _d(minv)
     pr = _params(family, D, params)
     q1, g1 = np.empty(D), np.empty(D)
     lq1 = C.c_double()
@@ -260,11 +299,12 @@ def sample_tree(family, q, eps, seed, chain, t, minv=None, params=None, T=32, ma
     ntrace = C.c_int()
     pp = None if p is None else _d(p)
     dd = None if directions is None else np.array([directions], dtype=np.uint32)
-    _check(lib().orc_sample_tree(
-        C.c_int(family), C.c_int(D), _p(pr), C.c_int(T), _p(minv), C.c_int(max_depth),
-        C.c_double(min_delta), C.c_int(int(always_divergent)), C.c_uint64(seed), C.c_uint64(chain),
-        C.c_uint32(t), _p(q), C.c_double(eps), _p(pp), _p(dd), _p(q1), C.byref(lq1), _p(g1),
-        _p(stats), _p(trace), C.c_int(trace.size), C.byref(ntrace)))
+    with _metric(minv, D) as m:
+        _check(lib().orc_sample_tree(
+            C.c_int(family), C.c_int(D), _p(pr), C.c_int(T), _p(m), C.c_int(max_depth),
+            C.c_double(min_delta), C.c_int(int(always_divergent)), C.c_uint64(seed), C.c_uint64(chain),
+            C.c_uint32(t), _p(q), C.c_double(eps), _p(pp), _p(dd), _p(q1), C.byref(lq1), _p(g1),
+            _p(stats), _p(trace), C.c_int(trace.size), C.byref(ntrace)))
     return dict(q=q1, lq=lq1.value, g=g1, stats=stats[0], accept_trace=trace[:ntrace.value].copy())
 
 
@@ -287,23 +327,23 @@ def find_initial_stepsize(family, q, p, minv=None, params=None, T=32, initial_ep
                           log_threshold=np.log(0.8), maxiter=400):
     q, p = _d(q), _d(p)
     D = q.size
-    minv = np.ones(D) if minv is None else _d(minv)
     pr = _params(family, D, params)
     eps = C.c_double()
-    _check(lib().orc_find_initial_stepsize(C.c_int(family), C.c_int(D), _p(pr), C.c_int(T),
-                                           _p(minv), _p(q), _p(p), C.c_double(initial_eps),
-                                           C.c_double(log_threshold), C.c_int(maxiter),
-                                           C.byref(eps)))
+    with _metric(minv, D) as m:
+        _check(lib().orc_find_initial_stepsize(C.c_int(family), C.c_int(D), _p(pr), C.c_int(T),
+                                               _p(m), _p(q), _p(p), C.c_double(initial_eps),
+                                               C.c_double(log_threshold), C.c_int(maxiter),
+                                               C.byref(eps)))
     return eps.value
 
 
 def local_log_acceptance_ratio(family, q, p, eps, minv=None, params=None, T=32):
     q, p = _d(q), _d(p)
     D = q.size
-    minv = np.ones(D) if minv is None else _d(minv)
     pr = _params(family, D, params)
-    return lib().orc_local_log_acceptance_ratio(C.c_int(family), C.c_int(D), _p(pr), C.c_int(T),
-                                                _p(minv), _p(q), _p(p), C.c_double(eps))
+    with _metric(minv, D) as m:
+        return lib().orc_local_log_acceptance_ratio(C.c_int(family), C.c_int(D), _p(pr), C.c_int(T),
+                                                    _p(m), _p(q), _p(p), C.c_double(eps))
 
 
 def da_init(eps):
@@ -321,7 +361,7 @@ def da_adapt(state, a, delta=0.8, gamma=0.05, kappa=0.75, t0=10):
 
 # ------------------------------------------------------------------ mcmc
 def default_warmup_stages(init_steps=75, middle_steps=25, doubling_stages=5, terminating_steps=50,
-                          search=True, dual_averaging=True):
+                          search=True, dual_averaging=True, M=METRIC_DIAGONAL):
     """(kind, N, metric, dual_averaging) tuples mirroring mcmc.jl:415-425."""
     st = []
     if search:
@@ -329,7 +369,7 @@ def default_warmup_stages(init_steps=75, middle_steps=25, doubling_stages=5, ter
     if dual_averaging:
         st.append((STAGE_TUNING, init_steps, METRIC_NOTHING, 1))
     for i in range(doubling_stages):
-        st.append((STAGE_TUNING, middle_steps * 2 ** i, METRIC_DIAGONAL, int(dual_averaging)))
+        st.append((STAGE_TUNING, middle_steps * 2 ** i, M, int(dual_averaging)))
     if dual_averaging:
         st.append((STAGE_TUNING, terminating_steps, METRIC_NOTHING, 1))
     return st
@@ -351,7 +391,15 @@ def mcmc_with_warmup(family, D, N, seed, chain, stages=None, params=None, T=32, 
     post = np.empty((N, D))
     stats = np.zeros(N, dtype=tree_stats_dtype)
     logd = np.empty(N)
-    minv = np.empty(D)
+    m0 = None if minv0 is None else _d(minv0)
+    dense_in = m0 is not None and m0.ndim == 2
+    dense_out = dense_in or any(s[0] == STAGE_TUNING and s[2] == METRIC_SYMMETRIC for s in stages)
+    for s_ in stages:
+        if s_[0] == STAGE_TUNING and s_[2] == METRIC_SYMMETRIC:
+            dense_out = True
+        elif s_[0] == STAGE_TUNING and s_[2] == METRIC_DIAGONAL:
+            dense_out = False
+    minv = np.empty(D * D if (dense_out or dense_in) else D)
     eps = C.c_double()
     nw = int(sum(s[1] for s in stages if s[0] == STAGE_TUNING))
     post_w = np.empty((nw, D)) if keep_warmup else None
@@ -360,14 +408,21 @@ def mcmc_with_warmup(family, D, N, seed, chain, stages=None, params=None, T=32, 
     qf = np.empty(D)
     da4, s3 = _d(da), _d(search)
     q0a = None if q0 is None else _d(q0)
-    m0a = None if minv0 is None else _d(minv0)
+    m0a = m0
     e0 = None if eps0 is None else C.byref(C.c_double(eps0))
-    _check(lib().orc_mcmc_with_warmup(
+    lib().orc_set_dense(C.c_int(int(dense_in)))
+    try:
+        _mcmc_call = lib().orc_mcmc_with_warmup
+    finally:
+        pass
+    _check(_mcmc_call(
         C.c_int(family), C.c_int(D), _p(pr), C.c_int(T), C.c_int(max_depth), C.c_double(min_delta),
         C.c_uint64(seed), C.c_uint64(chain), C.c_int(N), C.c_int(ns), _p(kind), _p(stN),
         _p(metric), _p(da_on), _p(da4), _p(s3), _p(q0a), _p(m0a), e0, C.c_int(int(welford)),
         _p(post), _p(stats), _p(logd), _p(minv), C.byref(eps), _p(post_w), _p(stats_w), _p(eps_w),
         _p(qf)))
+    lib().orc_set_dense(C.c_int(0))
+    minv = minv.reshape(D, D) if dense_out else minv[:D]
     out = dict(posterior_matrix=post, tree_statistics=stats, logdensities=logd, minv=minv,
                eps=eps.value, q_final=qf)
     if keep_warmup:

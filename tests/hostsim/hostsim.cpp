@@ -145,15 +145,15 @@ struct HostBackend {
            d6 = dot(p, Rnew);
     return d1 < 0 || d2 < 0 || d3 < 0 || d4 < 0 || d5 < 0 || d6 < 0;
   }
-  void welford_reset() { std::fill(wmean.begin(), wmean.end(), 0.0); std::fill(wm2.begin(), wm2.end(), 0.0); }
-  void welford_push(int n) {
+  void metric_reset(int) { std::fill(wmean.begin(), wmean.end(), 0.0); std::fill(wm2.begin(), wm2.end(), 0.0); }
+  void metric_push(int, int n) {
     for (int i = 0; i < D; ++i) {
       double d = q[i] - wmean[i];
       wmean[i] = wmean[i] + d / (double)n;
       wm2[i] = wm2[i] + d * (q[i] - wmean[i]);
     }
   }
-  void welford_finish(int n) { for (int i = 0; i < D; ++i) minv[i] = wm2[i] / (double)(n - 1); }
+  void metric_finish(int, int n) { for (int i = 0; i < D; ++i) minv[i] = wm2[i] / (double)(n - 1); }
 };
 
 struct Sink {

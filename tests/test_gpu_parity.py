@@ -268,3 +268,90 @@ def test_chunked_host_output_pipeline(pkg):
         assert np.array_equal(a["posterior_matrix"][off:off + n], b["posterior_matrix"])
         assert np.array_equal(a["tree_statistics"][off:off + n], b["tree_statistics"])
         assert np.array_equal(a["logdensities"][off:off + n], b["logdensities"])
+
+
+# --------------------------------------------------------------- Symmetric (dense) metric
+def _spd(rng, D):
+    A = rng.normal(size=(D, D))
+    return A @ A.T / D + np.diag(rng.uniform(0.5, 2.0, D))
+
+
+@pytest.mark.parametrize("D", [3, 10, 40, 100, 256])
+def test_dense_metric_leapfrog_and_tree_match_oracle(pkg, po, D):
+    """GaussianKineticEnergy(Symmetric M⁻¹) (hamiltonian.jl:73): W = cholesky(inv(M⁻¹)).L on
+    device, p♯ = M⁻¹p mat-vec, rand_p = W·randn — against the oracle, bit for bit."""
+    rng = np.random.default_rng(500 + D)
+    K = 6
+    ℓ = pkg.DiagNormal(rng.normal(size=D), rng.uniform(0.3, 3, D))
+    eng = _engine(pkg, ℓ, K, seed=21)
+    T, _ = eng.layout()
+    Minv = np.stack([_spd(rng, D) for _ in range(K)])
+    q, p = rng.normal(size=(K, D)), rng.normal(size=(K, D))
+    eps = rng.uniform(0.02, 0.2, K)
+    eng.set_metric_dense(Minv)
+    assert eng.metric_is_dense() and np.array_equal(eng.get_metric_dense(), Minv)
+    eng.set_position(q); eng.set_momentum(p); eng.set_stepsize(eps)
+    H = eng.phase_logdensity()
+    lq0 = [po.logdensity_and_gradient(1, q[k], ℓ.params(), T)[0] for k in range(K)]
+    for k in range(K):
+        assert H[k] == po.phase_logdensity(Minv[k], lq0[k], p[k], T)
+    eng.leapfrog(3, 1)
+    st = eng.get_state(("q", "p", "grad", "lq"))
+    for k in range(K):
+        qo, p_o, go, lqo = po.leapfrog(1, q[k], p[k], eps[k], minv=Minv[k], params=ℓ.params(), T=T, n_steps=3)
+        np.testing.assert_allclose(st["q"][k], qo, rtol=RTOL, atol=0)
+        assert np.array_equal(st["q"][k], qo) and np.array_equal(st["p"][k], p_o) and st["lq"][k] == lqo
+    eng.set_position(q)
+    for t in range(2):
+        stats = eng.sample_tree()
+        new = eng.get_state(("q",))["q"]
+        for k in range(K):
+            o = po.sample_tree(1, q[k], eps[k], 21, k, t, minv=Minv[k], params=ℓ.params(), T=T)
+            for f in INT_FIELDS:
+                assert o["stats"][f] == stats[k][f], (f, k, t)
+            assert o["stats"]["acceptance_rate"] == stats[k]["acceptance_rate"]
+            assert np.array_equal(new[k], o["q"])
+        q = new
+    # switching back to a diagonal metric works
+    eng.set_metric(np.ones(D))
+    assert not eng.metric_is_dense()
+    eng.sample_tree()
+    eng.close()
+
+
+def test_dense_metric_not_positive_definite(pkg):
+    D, K = 4, 3
+    eng = _engine(pkg, pkg.StandardNormal(D), K)
+    M = np.stack([np.eye(D)] * K)
+    M[1] = -np.eye(D)
+    with pytest.raises(pkg.DynamicHMCError) as e:          # PosDefException in the reference
+        eng.set_metric_dense(M)
+    st = e.value.debug_information["chain_status"]
+    assert st[1] & 16 and st[0] == 0 and st[2] == 0
+    eng.close()
+
+
+@pytest.mark.parametrize("D", [8, 50])
+def test_full_warmup_symmetric_matches_oracle(pkg, po, D):
+    """default_warmup_stages(; M = Symmetric) (mcmc.jl:415-425): covariance window, shrinkage,
+    dense factorisation — vs the oracle with streaming co-moments."""
+    rng = np.random.default_rng(77)
+    ℓ = pkg.DiagNormal(rng.normal(size=D), np.logspace(-1, 1, D))
+    K, N, seed = 10, 20, 99
+    stages = pkg.default_warmup_stages(M=pkg.Symmetric, init_steps=30, middle_steps=25, doubling_stages=2,
+                                       terminating_steps=20)
+    r = pkg.mcmc_keep_warmup(seed, ℓ, N, chains=K, warmup_stages=stages)
+    T, _ = r["engine"].layout()
+    res = r["inference"]
+    ostages = po.default_warmup_stages(init_steps=30, middle_steps=25, doubling_stages=2, terminating_steps=20,
+                                       M=po.METRIC_SYMMETRIC)
+    for k in range(0, K, 3):
+        o = po.mcmc_with_warmup(1, D, N, seed, k, stages=ostages, params=ℓ.params(), T=T, welford=True,
+                                keep_warmup=True)
+        w = np.concatenate([s["results"]["tree_statistics"][k] for s in r["warmup"] if s["results"]])
+        for f in INT_FIELDS:
+            assert np.array_equal(w[f], o["warmup_stats"][f]), f
+        assert res[k]["κ"].dense and np.array_equal(res[k]["κ"].minv, o["minv"])
+        assert res[k]["ϵ"] == o["eps"]
+        assert np.array_equal(res[k]["posterior_matrix"].T, o["posterior_matrix"])
+    r["engine"].close()
