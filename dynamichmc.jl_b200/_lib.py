@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DHMC_B200_LIB", os.path.join(_HERE, "csrc", "libdhmc_b200.so"))
 
 DHMC_OK, DHMC_EARG, DHMC_ENUMERIC, DHMC_ECUDA, DHMC_ENOMEM = 0, 1, 2, 3, 4
-FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL = 0, 1, 2
+FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL, FAMILY_LOGISTIC = 0, 1, 2, 3
 METRIC_NOTHING, METRIC_DIAGONAL, METRIC_SYMMETRIC = 0, 1, 2
 
 tree_stats_dtype = np.dtype(

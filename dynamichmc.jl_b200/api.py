@@ -107,6 +107,39 @@ class Funnel(DeviceLogDensity):
         return -v * v / 18 - 0.5 * ev * S - 0.5 * (self.D - 1) * v, g
 
 
+@dataclass
+class LogisticRegression(DeviceLogDensity):
+    """ℓ(β) = Σ[yᵢ xᵢᵀβ − log1pexp(xᵢᵀβ)] − ½‖β‖²  (SURVEY.md §8d C4); X is [N, p], y ∈ {0,1}ᴺ."""
+    X: np.ndarray
+    y: np.ndarray
+    family = L.FAMILY_LOGISTIC
+
+    def __post_init__(self):
+        self.X = np.ascontiguousarray(self.X, float)
+        self.y = np.ascontiguousarray(self.y, float)
+        _argcheck(self.X.ndim == 2 and self.y.shape == (self.X.shape[0],), "X: [N, p], y: [N]")
+        self.D = self.X.shape[1]
+
+    def params(self):
+        return np.concatenate([[float(self.X.shape[0])], self.X.ravel(), self.y])
+
+    def logdensity_and_gradient(self, q):
+        q = np.asarray(q, float)
+        eta = self.X @ q
+        ll = self.y * eta - np.logaddexp(0.0, eta)
+        r = self.y - 1.0 / (1.0 + np.exp(-eta))
+        return float(ll.sum() - 0.5 * q @ q), self.X.T @ r - q
+
+    @staticmethod
+    def synthetic(N=10000, p=256, seed=7):
+        """The C4 data set: Xᵢⱼ ~ N(0,1)/√p, β* ~ N(0,I), yᵢ ~ Bernoulli(σ(xᵢᵀβ*))."""
+        rng = np.random.default_rng(seed)
+        X = rng.normal(size=(N, p)) / np.sqrt(p)
+        beta = rng.normal(size=p)
+        y = (rng.uniform(size=N) < 1.0 / (1.0 + np.exp(-(X @ beta)))).astype(float)
+        return LogisticRegression(X, y), beta
+
+
 # ------------------------------------------------------------------ algorithm structs
 @dataclass
 class NUTS:

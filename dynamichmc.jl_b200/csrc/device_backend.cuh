@@ -75,6 +75,8 @@ struct DeviceBackend {
   // dense metric: this chain's M⁻¹ (symmetric, [D][D]), Wᵀ (column-major lower W), co-moment
   // accumulator (transposed lower) and the shared-memory staging vector
   const double* Mrow; const double* Wt; double* covt; double* xs;
+  // logistic regression: X [N][D], Xᵀ [D][N], y [N], per-CTA residual scratch [N]
+  const double* lX; const double* lXt; const double* ly; double* lr; int lN;
   // memory
   double* red; int red_buf;
   Entry* ctl;
@@ -365,7 +367,72 @@ struct DeviceBackend {
   // bit2: ℓq was replaced by −Inf (what `strict` turns into an error, :212-215).
   __device__ __forceinline__ void eval_model(bool with_p, double h, double qbad_in, double* ksum,
                                              int* flags) {
-    if (FAM == DHMC_FAMILY_FUNNEL) {
+    if (FAM == DHMC_FAMILY_LOGISTIC) {
+      // η = Xβ: β is staged in shared memory, thread t handles rows n = t, t+T, …
+      // (Xᵀ read coalesced over n); residuals go to the per-CTA scratch, then every
+      // thread accumulates its own gradient elements over n = 0..N-1 (X read coalesced over j).
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) xs[tid + e * T] = q[e];
+      group_sync();
+      double r[5] = {0.0, 0.0, qbad_in, 0.0, 0.0};   // Σ ll, Σ β², bad q, bad ∇ℓ, Σ p·p♯
+      for (int n0 = tid; n0 < lN; n0 += 4 * T) {     // four rows per pass for ILP
+        double eta[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* col = lXt + n0;
+        for (int j = 0; j < D; ++j, col += lN) {
+          const double bj = xs[j];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (n0 + u * T < lN) eta[u] = eta[u] + __ldg(col + u * T) * bj;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = n0 + u * T;
+          if (n < lN) {
+            const double yn = __ldg(ly + n);
+            r[0] = r[0] + dhmc_logit_ll(yn, eta[u]);
+            lr[n] = dhmc_logit_resid(yn, eta[u]);
+          }
+        }
+      }
+      group_sync();
+      double acc[EPL];
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) acc[e] = 0.0;
+      const double* row = lX + tid;
+      for (int n = 0; n < lN; ++n, row += D) {
+        const double rn = lr[n];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e)
+          if (tid + e * T < D) acc[e] = acc[e] + __ldg(row + e * T) * rn;
+      }
+      group_sync();
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        double ge = 0.0;
+        if (i < D) {
+          ge = dhmc_logit_grad(acc[e], q[e]);
+          if (!dm_isfinite(ge)) r[3] = 1.0;
+        }
+        r[1] = r[1] + q[e] * q[e];
+        g[e] = ge;
+        if (with_p) {
+          p[e] = p[e] + h * ge;
+          if constexpr (!DENSE) {
+            double psv = minv[e] * p[e];
+            r[4] = r[4] + p[e] * psv;
+          }
+        }
+      }
+      reduce(r);
+      double l = dhmc_logit_lq(r[0], r[1]);
+      if (!((dm_isfinite(l) && r[3] == 0.0) || l == -dm_inf())) *flags |= 4;
+      l = sanitise(l, r[3] != 0.0);
+      if (r[2] != 0.0) { *flags |= 1; l = -dm_inf(); }
+      if (r[3] != 0.0) *flags |= 2;
+      lq = l;
+      *ksum = r[4];
+    } else if (FAM == DHMC_FAMILY_FUNNEL) {
       double r1[3] = {0.0, 0.0, qbad_in};
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {

@@ -59,6 +59,9 @@ struct KArgs {
   int chain_begin, chain_end;   // persistent kernels: chains [begin, end) of this launch
   double *minv_dense, *wt, *covt;   // Symmetric metric: M⁻¹, Wᵀ, co-moments, each [B][D][D]
   int xs_doubles;               // shared-memory staging vector (0 unless the dense arrays exist)
+  const double *lX, *lXt, *ly;  // logistic regression data
+  double* lr;                   // per-CTA residual scratch [grid][lN]
+  int lN;
 };
 
 // Register budget: minimum resident CTAs per SM the compiler must allow for.
@@ -77,6 +80,8 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN>& b,
   const SmemLayout L = smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles);
   b.xs = reinterpret_cast<double*>(smem + L.xs_off);
   b.Mrow = nullptr; b.Wt = nullptr; b.covt = nullptr;
+  b.lX = a.lX; b.lXt = a.lXt; b.ly = a.ly; b.lN = a.lN;
+  b.lr = a.lr ? a.lr + (size_t)blockIdx.x * a.lN : nullptr;
   b.red = reinterpret_cast<double*>(smem + L.red_off);
   b.red_buf = 0;
   b.rexp_cache = 0.0; b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;
@@ -345,6 +350,13 @@ __global__ void k_broadcast_mat(double* dst, const double* src, size_t dd, size_
     dst[i] = src[i % dd];
 }
 
+__global__ void k_transpose(const double* X, double* Xt, size_t N, size_t D) {   // Xt[j][n] = X[n][j]
+  const size_t tot = N * D;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t j = i / N, n = i % N;
+    Xt[i] = X[n * D + j];
+  }
+}
 // broadcast a D-vector (or scalar when D == 1) to all chains
 __global__ void k_broadcast(double* dst, const double* src, size_t D, size_t B) {
   const size_t n = D * B;
@@ -382,6 +394,8 @@ struct dhmc_handle {
   bool has_position = false, has_eps = false;
   bool dense = false;               // κ is a Symmetric (dense) metric
   double *minv_dense = nullptr, *wt = nullptr, *covt = nullptr, *dense_tmp = nullptr;
+  double *lX = nullptr, *lXt = nullptr, *ly = nullptr, *lr = nullptr;   // logistic regression
+  int lN = 0;
   int reg_ctas[2] = {0, 0};         // occupancy of k_nuts (diag, dense)
   size_t smem_sm = 0, smem_cta_max = 0;
   std::string err;
@@ -406,6 +420,7 @@ static int dispatch_f(int fam, F&& f) {
     case DHMC_FAMILY_STD_NORMAL: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_STD_NORMAL>{});
     case DHMC_FAMILY_DIAG_NORMAL: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_DIAG_NORMAL>{});
     case DHMC_FAMILY_FUNNEL: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_FUNNEL>{});
+    case DHMC_FAMILY_LOGISTIC: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_LOGISTIC>{});
   }
   return DHMC_EARG;
 }
@@ -468,7 +483,7 @@ static int plan(dhmc_handle* h) {
   const size_t B = (size_t)h->cfg.n_chains;
   const size_t slot_doubles = h->stride * (h->dense ? 2 : 1);
   const size_t slot_bytes = sizeof(double) * slot_doubles;
-  const size_t xs = h->minv_dense ? h->stride : 0;
+  const size_t xs = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? h->stride : 0;
   const SmemLayout L0 = smem_layout(h->W, 0, slot_doubles, xs);
   h->smem_light = L0.total;
   int& reg_ctas = h->reg_ctas[h->dense ? 1 : 0];
@@ -502,6 +517,10 @@ static int plan(dhmc_handle* h) {
   h->scratch_per_cta = (size_t)(h->n_slots - h->n_sm) * slot_doubles;
   cudaFree(h->scratch); h->scratch = nullptr;
   CK(cudaMalloc(&h->scratch, sizeof(double) * h->scratch_per_cta * (size_t)h->grid));
+  if (h->lN) {   // residual scratch of the logistic family follows the grid
+    cudaFree(h->lr); h->lr = nullptr;
+    CK(cudaMalloc(&h->lr, sizeof(double) * (size_t)h->lN * (size_t)std::max(h->grid, h->light_grid)));
+  }
   return DHMC_OK;
 }
 
@@ -519,7 +538,8 @@ static KArgs base_args(dhmc_handle* h) {
   a.counter = h->counter; a.total_steps = h->total_steps;
   a.chain_begin = 0; a.chain_end = (int)h->cfg.n_chains;
   a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr;
-  a.xs_doubles = h->minv_dense ? (int)((size_t)h->T * h->EPL) : 0;
+  a.xs_doubles = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? (int)((size_t)h->T * h->EPL) : 0;
+  a.lX = h->lX; a.lXt = h->lXt; a.ly = h->ly; a.lr = h->lr; a.lN = h->lN;
   return a;
 }
 
@@ -614,6 +634,7 @@ int dhmc_destroy(dhmc_handle* h) {
   cudaFree(h->mparams); cudaFree(h->status); cudaFree(h->scratch); cudaFree(h->counter);
   cudaFree(h->total_steps);
   cudaFree(h->minv_dense); cudaFree(h->wt); cudaFree(h->covt); cudaFree(h->dense_tmp);
+  cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
@@ -703,7 +724,27 @@ int dhmc_get_layout(dhmc_handle* h, int32_t* T, int32_t* epl) {
 int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n) {
   if (!h) return DHMC_EARG;
   CK(cudaSetDevice(h->cfg.device));
-  const size_t want = h->cfg.family == DHMC_FAMILY_DIAG_NORMAL ? 2 * (size_t)h->cfg.dim : 0;
+  const size_t D = (size_t)h->cfg.dim;
+  if (h->cfg.family == DHMC_FAMILY_LOGISTIC) {
+    // params = [N, X row-major (N×D), y (N)]
+    if (!params || n < 1) { h->err = "dhmc_set_problem: logistic regression needs [N, X, y]"; return DHMC_EARG; }
+    const size_t N = (size_t)params[0];
+    if (N < 1 || n != 1 + N * D + N) { h->err = "dhmc_set_problem: expected 1 + N*D + N values"; return DHMC_EARG; }
+    cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr);
+    h->lX = h->lXt = h->ly = h->lr = nullptr;
+    CK(cudaMalloc(&h->lX, sizeof(double) * N * D));
+    CK(cudaMalloc(&h->lXt, sizeof(double) * N * D));
+    CK(cudaMalloc(&h->ly, sizeof(double) * N));
+    CK(cudaMalloc(&h->lr, sizeof(double) * N * (size_t)std::max(h->grid, h->light_grid)));
+    CK(cudaMemcpyAsync(h->lX, params + 1, sizeof(double) * N * D, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->ly, params + 1 + N * D, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
+    k_transpose<<<1024, 256, 0, h->stream>>>(h->lX, h->lXt, N, D);
+    h->launches += 1;
+    h->lN = (int)N;
+    CK(cudaStreamSynchronize(h->stream));
+    return DHMC_OK;
+  }
+  const size_t want = h->cfg.family == DHMC_FAMILY_DIAG_NORMAL ? 2 * D : 0;
   if (n != want || (want && !params)) { h->err = "dhmc_set_problem: wrong parameter count for this family"; return DHMC_EARG; }
   if (want) CK(cudaMemcpyAsync(h->mparams, params, sizeof(double) * want, cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));

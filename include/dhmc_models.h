@@ -12,6 +12,11 @@
  *               params = [mu(D), prec(D)]
  *   FUNNEL      Neal's funnel, theta = (v, x_1..x_{D-1}):
  *               l = -v^2/18 - 1/2 e^{-v} sum x_i^2 - (D-1)/2 v
+ *   LOGISTIC    logistic regression with a N(0, I) prior, X [N x p], y in {0,1}:
+ *               eta = X beta;  l = sum_n [y_n eta_n - log1pexp(eta_n)] - 1/2 |beta|^2
+ *               grad = X' (y - sigma(eta)) - beta
+ *               params = [N, X row-major (N*p), y (N)];  eta_n and (X' r)_j are sequential sums
+ *               over j resp. n, the two scalar sums use the canonical reduction.
  */
 #ifndef DHMC_MODELS_H
 #define DHMC_MODELS_H
@@ -21,7 +26,8 @@ enum {
   DHMC_FAMILY_STD_NORMAL = 0,
   DHMC_FAMILY_DIAG_NORMAL = 1,
   DHMC_FAMILY_FUNNEL = 2,
-  DHMC_FAMILY_COUNT = 3
+  DHMC_FAMILY_LOGISTIC = 3,
+  DHMC_FAMILY_COUNT = 4
 };
 
 /* --- STD_NORMAL: term of the sum and gradient element */
@@ -52,5 +58,12 @@ DHMC_HD double dhmc_funnel_grad(int i, double x, double v, double ev, double S,
   if (i == 0) return ((-v) / 9.0 + (0.5 * ev) * S) - 0.5 * (double)(D - 1);
   return -(ev * x);
 }
+
+/* --- LOGISTIC */
+DHMC_HD double dhmc_logit_sigma(double eta) { return 1.0 / (1.0 + dm_exp(-eta)); }
+DHMC_HD double dhmc_logit_ll(double y, double eta) { return y * eta - dm_log1pexp(eta); }
+DHMC_HD double dhmc_logit_resid(double y, double eta) { return y - dhmc_logit_sigma(eta); }
+DHMC_HD double dhmc_logit_lq(double sum_ll, double sum_b2) { return sum_ll - 0.5 * sum_b2; }
+DHMC_HD double dhmc_logit_grad(double xtr, double beta) { return xtr - beta; }
 
 #endif

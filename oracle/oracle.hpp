@@ -117,6 +117,27 @@ struct Model {
         for (int i = 0; i < D; ++i) g[i] = dhmc_funnel_grad(i, q[i], v, ev, S, D);
         return dhmc_funnel_lq(v, ev, S, D);
       }
+      case DHMC_FAMILY_LOGISTIC: {
+        // params = [N, X row-major (N×D), y (N)]
+        const int N = (int)params[0];
+        const double* X = params.data() + 1;
+        const double* y = X + (size_t)N * D;
+        vec r(N), ll(N);
+        for (int n = 0; n < N; ++n) {
+          double eta = 0.0;
+          for (int j = 0; j < D; ++j) eta = eta + X[(size_t)n * D + j] * q[j];
+          ll[n] = dhmc_logit_ll(y[n], eta);
+          r[n] = dhmc_logit_resid(y[n], eta);
+        }
+        double sll = canon_sum(T, N, [&](int n) { return ll[n]; });
+        double sb = canon_sum(T, D, [&](int i) { return q[i] * q[i]; });
+        for (int j = 0; j < D; ++j) {
+          double acc = 0.0;
+          for (int n = 0; n < N; ++n) acc = acc + X[(size_t)n * D + j] * r[n];
+          g[j] = dhmc_logit_grad(acc, q[j]);
+        }
+        return dhmc_logit_lq(sll, sb);
+      }
     }
     throw ArgumentError("unknown family");
   }

@@ -23,7 +23,9 @@ Model make_model(int family, int D, const double* params, int nparams, int T, in
   if (params && nparams > 0) m.params.assign(params, params + nparams);
   return m;
 }
+thread_local int g_logistic_n = 0;   // N of the logistic-regression family (set by orc_set_logistic_n)
 int nparams_of(int family, int D) {
+  if (family == DHMC_FAMILY_LOGISTIC) return 1 + g_logistic_n * D + g_logistic_n;
   return family == DHMC_FAMILY_DIAG_NORMAL ? 2 * D : 0;
 }
 template <class F>
@@ -39,6 +41,7 @@ extern "C" {
 
 const char* orc_last_error() { return g_err.c_str(); }
 void orc_set_dense(int flag) { g_dense = flag; }
+void orc_set_logistic_n(int n) { g_logistic_n = n; }
 // W = cholesky(inv(M⁻¹)).L; returns 0 ok, 2 not positive definite
 int orc_dense_factor(int D, const double* minv, double* W) {
   vec w;

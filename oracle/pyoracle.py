@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL = 0, 1, 2
+FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL, FAMILY_LOGISTIC = 0, 1, 2, 3
 STAGE_NOTHING, STAGE_SEARCH, STAGE_TUNING = 0, 1, 2
 METRIC_NOTHING, METRIC_DIAGONAL, METRIC_SYMMETRIC = 0, 1, 2
 
@@ -120,10 +120,22 @@ def rand_p(seed, chain, stream, t, minv):
     return out
 
 
+def logistic_params(X, y):
+    """params vector of the LOGISTIC family: [N, X row-major, y]"""
+    X, y = _d(X), _d(y)
+    return np.concatenate([[float(X.shape[0])], X.ravel(), y])
+
+
 def _params(family, D, params):
     if family == FAMILY_DIAG_NORMAL:
         params = _d(params)
         assert params.size == 2 * D
+        return params
+    if family == FAMILY_LOGISTIC:
+        params = _d(params)
+        N = int(params[0])
+        assert params.size == 1 + N * D + N
+        lib().orc_set_logistic_n(C.c_int(N))
         return params
     return np.zeros(1)
 

@@ -104,6 +104,25 @@ struct HostBackend {
         l = dhmc_diag_lq(s);
         break;
       }
+      case DHMC_FAMILY_LOGISTIC: {
+        const int N = (int)params[0];
+        const double* X = params + 1; const double* y = X + (size_t)N * D;
+        vec r(N), ll(N);
+        for (int n = 0; n < N; ++n) {
+          double eta = 0.0;
+          for (int j = 0; j < D; ++j) eta = eta + X[(size_t)n * D + j] * q[j];
+          ll[n] = dhmc_logit_ll(y[n], eta); r[n] = dhmc_logit_resid(y[n], eta);
+        }
+        double sll = canon_sum(T, N, [&](int n) { return ll[n]; });
+        double sb = canon_sum(T, D, [&](int i) { return q[i] * q[i]; });
+        for (int j = 0; j < D; ++j) {
+          double acc = 0.0;
+          for (int n = 0; n < N; ++n) acc = acc + X[(size_t)n * D + j] * r[n];
+          g[j] = dhmc_logit_grad(acc, q[j]);
+        }
+        l = dhmc_logit_lq(sll, sb);
+        break;
+      }
       default: {
         double v = q[0], ev = dm_exp(-v);
         double S = canon_sum(T, D, [&](int i) { return dhmc_funnel_term(i, q[i]); });

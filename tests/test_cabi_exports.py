@@ -62,7 +62,8 @@ def test_device_models_match_oracle_models(pkg, po):
     q = rng.normal(size=10)
     for ℓ, fam, params in ((pkg.StandardNormal(10), 0, None),
                            (pkg.DiagNormal(rng.normal(size=10), rng.uniform(0.5, 2, 10)), 1, "p"),
-                           (pkg.Funnel(10), 2, None)):
+                           (pkg.Funnel(10), 2, None),
+                           (pkg.LogisticRegression(rng.normal(size=(30, 10)), (rng.uniform(size=30) < 0.5) * 1.0), 3, "p")):
         pr = ℓ.params() if params else None
         lq, g = po.logdensity_and_gradient(fam, q, pr)
         lq2, g2 = ℓ.logdensity_and_gradient(q)

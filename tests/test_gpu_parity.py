@@ -355,3 +355,61 @@ def test_full_warmup_symmetric_matches_oracle(pkg, po, D):
         assert res[k]["ϵ"] == o["eps"]
         assert np.array_equal(res[k]["posterior_matrix"].T, o["posterior_matrix"])
     r["engine"].close()
+
+
+# --------------------------------------------------------------- logistic regression family
+@pytest.mark.parametrize("N,p", [(50, 3), (333, 40), (1000, 100), (2000, 256)])
+def test_logistic_regression_matches_oracle(pkg, po, N, p):
+    rng = np.random.default_rng(N + p)
+    X = rng.normal(size=(N, p)) / np.sqrt(p)
+    y = (rng.uniform(size=N) < 1 / (1 + np.exp(-X @ rng.normal(size=p)))).astype(float)
+    ℓ = pkg.LogisticRegression(X, y)
+    K = 5
+    eng = _engine(pkg, ℓ, K, seed=8)
+    T, _ = eng.layout()
+    params = po.logistic_params(X, y)
+    q = rng.normal(size=(K, p)) * 0.3
+    pm = rng.normal(size=(K, p))
+    eps = rng.uniform(0.01, 0.08, K)
+    eng.set_position(q); eng.set_momentum(pm); eng.set_stepsize(eps)
+    st = eng.get_state(("lq", "grad"))
+    for k in range(K):
+        lq, g = po.logdensity_and_gradient(po.FAMILY_LOGISTIC, q[k], params, T)
+        assert st["lq"][k] == lq and np.array_equal(st["grad"][k], g)
+    eng.leapfrog(2, 1)
+    st = eng.get_state(("q", "p", "lq"))
+    for k in range(K):
+        qo, p_o, go, lqo = po.leapfrog(po.FAMILY_LOGISTIC, q[k], pm[k], eps[k], params=params, T=T, n_steps=2)
+        np.testing.assert_allclose(st["q"][k], qo, rtol=RTOL, atol=0)
+        assert np.array_equal(st["q"][k], qo) and np.array_equal(st["p"][k], p_o) and st["lq"][k] == lqo
+    eng.set_position(q)
+    stats = eng.sample_tree()
+    new = eng.get_state(("q",))["q"]
+    for k in range(K):
+        o = po.sample_tree(po.FAMILY_LOGISTIC, q[k], eps[k], 8, k, 0, params=params, T=T)
+        for f in INT_FIELDS:
+            assert o["stats"][f] == stats[k][f]
+        assert np.array_equal(new[k], o["q"])
+    eng.close()
+
+
+def test_logistic_dense_warmup_matches_oracle(pkg, po):
+    """C4 in miniature: logistic regression, default_warmup_stages(; M = Symmetric)."""
+    ℓ, _ = pkg.LogisticRegression.synthetic(N=400, p=12, seed=7)
+    K, N, seed = 6, 15, 5
+    stages = pkg.default_warmup_stages(M=pkg.Symmetric, init_steps=25, middle_steps=25, doubling_stages=2,
+                                       terminating_steps=20)
+    r = pkg.mcmc_keep_warmup(seed, ℓ, N, chains=K, warmup_stages=stages)
+    T, _ = r["engine"].layout()
+    params = po.logistic_params(ℓ.X, ℓ.y)
+    ostages = po.default_warmup_stages(init_steps=25, middle_steps=25, doubling_stages=2, terminating_steps=20,
+                                       M=po.METRIC_SYMMETRIC)
+    for k in (0, 3, 5):
+        o = po.mcmc_with_warmup(po.FAMILY_LOGISTIC, 12, N, seed, k, stages=ostages, params=params, T=T,
+                                welford=True)
+        res = r["inference"][k]
+        assert res["κ"].dense and np.array_equal(res["κ"].minv, o["minv"]) and res["ϵ"] == o["eps"]
+        assert np.array_equal(res["posterior_matrix"].T, o["posterior_matrix"])
+        for f in INT_FIELDS:
+            assert np.array_equal(res["tree_statistics"][f], o["tree_statistics"][f])
+    r["engine"].close()

@@ -235,3 +235,21 @@ def test_error_for_nonfinite_initial_density(po):  # :93-98
     with pytest.raises(po.OracleError) as e:
         po.find_initial_stepsize(po.FAMILY_STD_NORMAL, np.zeros(2), np.full(2, np.nan))
     assert e.value.status == 2
+
+
+def test_logistic_regression_model(po):
+    """LOGISTIC family: ℓ and ∇ℓ against numpy, and finite differences."""
+    rng = np.random.default_rng(12)
+    N, p = 300, 7
+    X = rng.normal(size=(N, p)) / np.sqrt(p)
+    y = (rng.uniform(size=N) < 0.5).astype(float)
+    beta = rng.normal(size=p)
+    params = po.logistic_params(X, y)
+    lq, g = po.logdensity_and_gradient(po.FAMILY_LOGISTIC, beta, params)
+    eta = X @ beta
+    ref = np.sum(y * eta - np.logaddexp(0, eta)) - 0.5 * beta @ beta
+    gref = X.T @ (y - 1 / (1 + np.exp(-eta))) - beta
+    assert lq == pytest.approx(ref, rel=1e-13) and np.allclose(g, gref, rtol=1e-12, atol=1e-13)
+    r = po.mcmc_with_warmup(po.FAMILY_LOGISTIC, p, 300, seed=3, chain=0, params=params)
+    assert r["tree_statistics"]["acceptance_rate"].mean() > 0.6
+    assert np.all(np.abs(r["posterior_matrix"].mean(0)) < 3.0)

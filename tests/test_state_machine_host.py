@@ -23,10 +23,15 @@ def _same_stats(a, b):
 def _problem(rng, family, D):
     if family == 1:
         return np.concatenate([rng.normal(size=D), rng.uniform(0.2, 5.0, D)])
+    if family == 3:
+        N = int(rng.integers(20, 80))
+        X = rng.normal(size=(N, D)) / np.sqrt(D)
+        y = (rng.uniform(size=N) < 0.5).astype(float)
+        return np.concatenate([[float(N)], X.ravel(), y])
     return None
 
 
-@pytest.mark.parametrize("family", [0, 1, 2])
+@pytest.mark.parametrize("family", [0, 1, 2, 3])
 def test_single_transitions_match_oracle(po, family):
     rng = np.random.default_rng(100 + family)
     seen_depths, seen_div, seen_turn_sub, seen_max = set(), 0, 0, 0
