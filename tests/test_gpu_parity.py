@@ -413,3 +413,71 @@ def test_logistic_dense_warmup_matches_oracle(pkg, po):
         for f in INT_FIELDS:
             assert np.array_equal(res["tree_statistics"][f], o["tree_statistics"][f])
     r["engine"].close()
+
+
+# --------------------------------------------------------------- full-size properties (BASELINE configs[1])
+def test_full_size_properties_c2(pkg):
+    """65 536 chains × D=1000 (config C2): size-independent properties the domain offers —
+    leapfrog reversibility, energy error of the integrator, tree-statistics invariants,
+    and agreement of a shard with the full run."""
+    D, K = 1000, 65536
+    ℓ = pkg.StandardNormal(D)
+    eng = _engine(pkg, ℓ, K, seed=2026)
+    eng.random_position()
+    q0 = eng.get_state(("q",))["q"]
+    rng = np.random.default_rng(0)
+    p0 = rng.normal(size=(K, D))
+    eng.set_momentum(p0)
+    eng.set_stepsize(0.05)
+    H0 = eng.phase_logdensity()
+    eng.leapfrog(8, 1)
+    H1 = eng.phase_logdensity()
+    assert np.max(np.abs(H1 - H0)) < 0.5                      # test_hamiltonian.jl:118-141
+    eng.leapfrog(8, -1)
+    st = eng.get_state(("q", "p"))
+    assert np.max(np.abs(st["q"] - q0)) < 1e-9 and np.max(np.abs(st["p"] - p0)) < 1e-9   # :143-177
+    eng.set_stepsize(0.28)
+    out = eng.mcmc(1)
+    ts = out["tree_statistics"][:, 0]
+    assert np.all(ts["depth"] >= 0) and np.all(ts["depth"] <= 10)
+    assert np.all(ts["steps"] >= 1) and np.all(ts["steps"] <= 2 ** (ts["depth"] + 1) - 1)
+    assert np.all(ts["steps"] >= 2 ** ts["depth"] - 1)
+    assert np.all((ts["acceptance_rate"] >= 0) & (ts["acceptance_rate"] <= 1))
+    maxd = (ts["left"] == 1) & (ts["right"] == 0)
+    assert np.all(ts["depth"][maxd] == 10)
+    assert eng.last_total_steps() == int(ts["steps"].sum())
+    assert np.all(np.isfinite(out["logdensities"])) and np.all(eng.chain_status() == 0)
+    lq = -0.5 * np.einsum("kd,kd->k", out["posterior_matrix"][:, 0], out["posterior_matrix"][:, 0])
+    np.testing.assert_allclose(out["logdensities"][:, 0], lq, rtol=1e-12)
+    eng.close()
+    # a 64-chain shard at offset 40 000 reproduces those chains bit for bit
+    sh = pkg.Engine(ℓ, chains=64, seed=2026, chain_offset=40000)
+    sh.random_position(); sh.set_momentum(p0[40000:40064]); sh.set_stepsize(0.05)
+    sh.leapfrog(8, 1); sh.leapfrog(8, -1)
+    sh.set_stepsize(0.28)
+    b = sh.mcmc(1)
+    sh.close()
+    assert np.array_equal(b["posterior_matrix"], out["posterior_matrix"][40000:40064])
+    assert np.array_equal(b["tree_statistics"], out["tree_statistics"][40000:40064])
+
+
+def test_checkpoint_and_resume(pkg):
+    """mcmc_keep_warmup / mcmc_steps surface (mcmc.jl:335-351, :521-532): (Q, κ, ϵ, RNG counter)
+    is a complete checkpoint — a fresh handle restored from it continues the same chains."""
+    D, K = 30, 50
+    ℓ = pkg.DiagNormal(np.zeros(D), np.linspace(0.5, 4, D))
+    a = _engine(pkg, ℓ, K, seed=5)
+    a.random_position(); a.find_initial_stepsize()
+    a.warmup_stage(pkg.TuningNUTS(40, pkg.DualAveraging(), pkg.Diagonal))
+    ck = a.get_state(("q", "minv", "eps"))
+    t = a.transition_count
+    ref = a.mcmc(6)
+    a.close()
+    b = _engine(pkg, ℓ, K, seed=5)
+    b.set_metric(ck["minv"]); b.set_position(ck["q"]); b.set_stepsize(ck["eps"])
+    b.transition_count = t
+    first = b.mcmc(2)
+    second = b.mcmc(4)
+    b.close()
+    got = np.concatenate([first["posterior_matrix"], second["posterior_matrix"]], axis=1)
+    assert np.array_equal(got, ref["posterior_matrix"])
