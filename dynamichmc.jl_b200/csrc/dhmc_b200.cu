@@ -103,6 +103,7 @@ template <int EPL, int FAM, int W, bool DN>
 __device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN>& b, const KArgs& a, long c,
                                            bool with_p) {
   b.chain = c;
+  b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;   // the randexp batch belongs to one chain
   const size_t base = (size_t)c * a.D;
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {

@@ -481,3 +481,21 @@ def test_checkpoint_and_resume(pkg):
     b.close()
     got = np.concatenate([first["posterior_matrix"], second["posterior_matrix"]], axis=1)
     assert np.array_equal(got, ref["posterior_matrix"])
+
+
+def test_many_chains_per_cta_single_transition(pkg, po):
+    """Regression: with more chains than resident CTAs and N = 1, every chain must use its own
+    randexp stream (the 32-wide batch is per chain)."""
+    D, K = 16, 20000
+    eng = _engine(pkg, pkg.StandardNormal(D), K, seed=4)
+    T, _ = eng.layout()
+    eng.random_position(); eng.set_stepsize(0.3)
+    q0 = eng.get_state(("q",))["q"]
+    stats = eng.sample_tree()
+    q1 = eng.get_state(("q",))["q"]
+    for k in list(range(0, K, 997)) + [K - 1]:
+        o = po.sample_tree(0, q0[k], 0.3, 4, k, 0, T=T)
+        for f in INT_FIELDS:
+            assert o["stats"][f] == stats[k][f]
+        assert o["stats"]["pi"] == stats[k]["pi"] and np.array_equal(q1[k], o["q"])
+    eng.close()
