@@ -232,9 +232,9 @@ def main():
         lib, h = eng._lib, eng._h
 
         def step_e2e():
-            eng._ck(lib.dhmc_set_position(h, C.c_void_p(q_host.data_ptr())))
-            eng._ck(lib.dhmc_mcmc(h, C.c_int32(n), C.c_void_p(post_host.data_ptr()),
-                                  C.c_void_p(stats_host.data_ptr()), C.c_void_p(logd_host.data_ptr())))
+            eng._ck(lib.dhmc_mcmc_from(h, C.c_void_p(q_host.data_ptr()), C.c_int32(n),
+                                       C.c_void_p(post_host.data_ptr()), C.c_void_p(stats_host.data_ptr()),
+                                       C.c_void_p(logd_host.data_ptr())))
             return eng.last_total_steps()
 
         for _ in range(max(1, args.warmup - 1)):

@@ -423,6 +423,21 @@ class Engine:
         self._ck(self._lib.dhmc_mcmc(self._h, C.c_int32(N), L.ptr(post), L.ptr(stats), L.ptr(ld)))
         return dict(posterior_matrix=post, tree_statistics=stats, logdensities=ld)
 
+    def mcmc_from(self, q, N, out=None):
+        """mcmc starting from host positions q ([K, D]); upload, evaluate_ℓ, sampling and
+        download are pipelined by chain chunks.  `out` may hold preallocated (pinned) arrays."""
+        K, D = self.K, self.D
+        q = self._kd(q, "q")
+        out = out or {}
+        post = out.get("posterior_matrix", None)
+        post = np.empty((K, N, D)) if post is None else post
+        stats = out.get("tree_statistics", None)
+        stats = np.zeros((K, N), dtype=L.tree_stats_dtype) if stats is None else stats
+        ld = out.get("logdensities", None)
+        ld = np.empty((K, N)) if ld is None else ld
+        self._ck(self._lib.dhmc_mcmc_from(self._h, L.ptr(q), C.c_int32(N), L.ptr(post), L.ptr(stats), L.ptr(ld)))
+        return dict(posterior_matrix=post, tree_statistics=stats, logdensities=ld)
+
     def mcmc_dev(self, N, posterior_ptr=0, stats_ptr=0, logdens_ptr=0):
         """Device-pointer variant: draws stay in HBM (e.g. torch tensors' data_ptr())."""
         self._ck(self._lib.dhmc_mcmc_dev(self._h, C.c_int32(N), C.c_void_p(posterior_ptr or None),

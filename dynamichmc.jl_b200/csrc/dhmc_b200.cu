@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_leapfrog(const KAr
   extern __shared__ __align__(16) unsigned char smem[];
   DeviceBackend<EPL, FAM, W, DN> b;
   setup_backend(b, a, smem);
-  for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
+  for (long c = a.chain_begin + blockIdx.x; c < a.chain_end; c += gridDim.x) {
     load_chain(b, a, c, true);
     const double eps = a.lf_sign >= 0 ? a.eps[c] : -a.eps[c];
     int flags = 0;
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_eval(const KArgs a
   extern __shared__ __align__(16) unsigned char smem[];
   DeviceBackend<EPL, FAM, W> b;
   setup_backend(b, a, smem);
-  for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
+  for (long c = a.chain_begin + blockIdx.x; c < a.chain_end; c += gridDim.x) {
     load_chain(b, a, c, false);
     double qbad = 0.0;
     if (a.randomize) {
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_phase(const KArgs 
   extern __shared__ __align__(16) unsigned char smem[];
   DeviceBackend<EPL, FAM, W, DN> b;
   setup_backend(b, a, smem);
-  for (long c = blockIdx.x; c < a.B; c += gridDim.x) {
+  for (long c = a.chain_begin + blockIdx.x; c < a.chain_end; c += gridDim.x) {
     load_chain(b, a, c, true);
     const double H = b.phase_logdensity();
     if (b.tid == 0) a.out_phase[c] = H;
@@ -377,7 +377,8 @@ struct dhmc_handle {
   int n_slots = 0, n_sm = 0, grid = 0, sm_count = 0, light_grid = 0;
   size_t smem_bytes = 0, smem_light = 0;
   size_t scratch_per_cta = 0;
-  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr, h2d_stream = nullptr;
+  cudaEvent_t h2d_ev[16] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t chunk_ev[16] = {};
   void* stage[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only device staging for host outputs
@@ -641,6 +642,8 @@ int dhmc_destroy(dhmc_handle* h) {
   for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
   for (auto& b : h->stage) cudaFree(b);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (auto& e : h->h2d_ev) if (e) cudaEventDestroy(e);
+  if (h->h2d_stream) cudaStreamDestroy(h->h2d_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return DHMC_OK;
@@ -679,6 +682,8 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
+  for (auto& e : h->h2d_ev) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   for (auto& e : h->chunk_ev) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
@@ -960,8 +965,9 @@ static int ensure_stage(dhmc_handle* h, int i, size_t bytes) {
 }
 static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda, const double* p_over_host,
                     const uint32_t* dir_over_host, double* posterior, dhmc_tree_stats* stats,
-                    double* eps_used, double* logdens, bool outputs_on_device, bool advance_t) {
-  if (!h->has_position || !h->has_eps) { h->err = "set position and step size (or run the initial search) first"; return DHMC_EARG; }
+                    double* eps_used, double* logdens, bool outputs_on_device, bool advance_t,
+                    const double* q_host = nullptr) {
+  if ((!h->has_position && !q_host) || !h->has_eps) { h->err = "set position and step size (or run the initial search) first"; return DHMC_EARG; }
   CK(cudaSetDevice(h->cfg.device));
   const size_t B = (size_t)h->cfg.n_chains, D = (size_t)h->cfg.dim, n = (size_t)N;
   double *d_post = nullptr, *d_eps = nullptr, *d_ld = nullptr, *d_p = nullptr;
@@ -993,9 +999,25 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   if (cfg.metric == DHMC_METRIC_SYMMETRIC) a.covt = h->covt;
   const size_t out_bytes = posterior ? sizeof(double) * B * n * D : 0;
   const int nchunks = (!outputs_on_device && B >= 4096 && out_bytes >= ((size_t)32 << 20)) ? 8 : 1;
+  if (q_host) CKR(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));
   for (int ci = 0; ci < nchunks; ++ci) {
     const size_t c0 = B * ci / nchunks, c1 = B * (ci + 1) / nchunks, nc = c1 - c0;
     a.chain_begin = (int)c0; a.chain_end = (int)c1;
+    if (q_host) {
+      // positions of this chunk: H2D on its own stream, then evaluate_ℓ(strict) on the compute
+      // stream — overlaps with the previous chunk's sampling and D2H
+      if (ci == 0) {   // uploads start after everything already queued on the compute stream
+        CKR(cudaEventRecord(h->h2d_ev[15], h->stream));
+        CKR(cudaStreamWaitEvent(h->h2d_stream, h->h2d_ev[15], 0));
+      }
+      CKR(cudaMemcpyAsync(h->q + c0 * D, q_host + c0 * D, sizeof(double) * nc * D, cudaMemcpyHostToDevice, h->h2d_stream));
+      CKR(cudaEventRecord(h->h2d_ev[ci], h->h2d_stream));
+      CKR(cudaStreamWaitEvent(h->stream, h->h2d_ev[ci], 0));
+      KArgs ea = a;
+      ea.strict = 1; ea.randomize = 0;
+      rc = launch(h, K_EVAL, ea, 0);
+      if (rc != DHMC_OK) { cleanup(); return rc; }
+    }
     const int timing = nchunks == 1 ? 1 : (ci == 0 ? 2 : (ci == nchunks - 1 ? 3 : 4));
     rc = launch(h, K_NUTS, a, timing == 1 ? 2 : timing, ci == 0);
     if (rc != DHMC_OK) { cleanup(); return rc; }
@@ -1019,8 +1041,10 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   cleanup();
   h->last_steps = (int64_t)steps;
   if (advance_t) h->t += (uint32_t)N;
-  rc = sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q | DHMC_CHAIN_BAD_ACCEPTANCE,
-                             "sampling: non-finite position or acceptance rate");
+  if (q_host) h->has_position = true;
+  rc = sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q | DHMC_CHAIN_BAD_ACCEPTANCE | (q_host ? DHMC_CHAIN_BAD_INITIAL : 0),
+                             q_host ? "invalid initial position, or non-finite position / acceptance rate while sampling"
+                                    : "sampling: non-finite position or acceptance rate");
   if (rc != DHMC_OK) return rc;
   if (cfg.metric == DHMC_METRIC_DIAGONAL && h->dense) {   // κ ← Diagonal: back to the diagonal kernels
     h->dense = false;
@@ -1069,6 +1093,12 @@ int dhmc_mcmc(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* sta
   if (N == 0) return DHMC_OK;
   AdaptConfig cfg{};
   return run_nuts(h, N, cfg, 0.0, nullptr, nullptr, posterior, stats, nullptr, logdens, false, true);
+}
+int dhmc_mcmc_from(dhmc_handle* h, const double* q, int32_t N, double* posterior, dhmc_tree_stats* stats,
+                   double* logdens) {
+  if (!h || !q || N < 1) return DHMC_EARG;
+  AdaptConfig cfg{};
+  return run_nuts(h, N, cfg, 0.0, nullptr, nullptr, posterior, stats, nullptr, logdens, false, true, q);
 }
 int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats, double* logdens) {
   if (!h || N < 0) return DHMC_EARG;

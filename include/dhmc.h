@@ -147,6 +147,11 @@ int dhmc_warmup_stage(dhmc_handle* h, int32_t N, int32_t metric, const dhmc_dual
 /* mcmc — mcmc.jl:366-381: N transitions at the adapted (κ, ϵ). */
 int dhmc_mcmc(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats,
               double* logdens);
+/* mcmc from host positions: WarmupState.Q given by the caller (q: [D,B], evaluated strictly
+ * like dhmc_set_position) with the current (κ, ϵ) — mcmc_steps / mcmc_next_step,
+ * mcmc.jl:335-351.  Upload, evaluation, sampling and download are pipelined by chain chunks. */
+int dhmc_mcmc_from(dhmc_handle* h, const double* q, int32_t N, double* posterior,
+                   dhmc_tree_stats* stats, double* logdens);
 /* Same with DEVICE output pointers (draws stay in HBM for an NCCL all-gather). */
 int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats,
                   double* logdens);

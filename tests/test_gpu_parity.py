@@ -499,3 +499,25 @@ def test_many_chains_per_cta_single_transition(pkg, po):
             assert o["stats"][f] == stats[k][f]
         assert o["stats"]["pi"] == stats[k]["pi"] and np.array_equal(q1[k], o["q"])
     eng.close()
+
+
+def test_mcmc_from_host_positions(pkg):
+    """dhmc_mcmc_from = set_position + mcmc, pipelined; same results, strict initial check."""
+    D, K, N = 64, 8192, 8
+    ℓ = pkg.StandardNormal(D)
+    rng = np.random.default_rng(1)
+    q = rng.normal(size=(K, D))
+    a = _engine(pkg, ℓ, K, seed=6)
+    a.set_position(q); a.set_stepsize(0.4)
+    ra = a.mcmc(N)
+    a.close()
+    b = _engine(pkg, ℓ, K, seed=6)
+    b.set_stepsize(0.4)
+    rb = b.mcmc_from(q, N)
+    assert np.array_equal(ra["posterior_matrix"], rb["posterior_matrix"])
+    assert np.array_equal(ra["tree_statistics"], rb["tree_statistics"])
+    q[77, 3] = np.inf
+    with pytest.raises(pkg.DynamicHMCError) as e:
+        b.mcmc_from(q, 1)
+    assert e.value.debug_information["chain_status"][77] & 1
+    b.close()
