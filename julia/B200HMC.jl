@@ -124,17 +124,21 @@ function mcmc_with_warmup(seed::Integer, ℓ::DeviceLogDensity, N::Integer; chai
      for k in 1:chains]
 end
 
+# GaussianKineticEnergy(Symmetric M⁻¹) — src/hamiltonian.jl:73 (W is computed on the device)
+set_metric_dense!(h::Handle, M⁻¹::AbstractMatrix) =
+    _ck(h, ccall((:dhmc_set_metric_dense, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint), h.ptr, Matrix{Float64}(M⁻¹), 1))
+
 warmup!(h::Handle, ::Nothing) = nothing                          # src/mcmc.jl:99-101
 warmup!(h::Handle, s::InitialStepsizeSearch) =                   # src/mcmc.jl:134-148
     _ck(h, ccall((:dhmc_find_initial_stepsize, LIB), Cint, (Ptr{Cvoid}, Float64, Float64, Int32),
                  h.ptr, s.initial_ϵ, s.log_threshold, s.maxiter_crossing))
 function warmup!(h::Handle, t::TuningNUTS{M}) where {M}          # src/mcmc.jl:258-286
-    M === Nothing || M <: Diagonal || throw(ArgumentError("Symmetric metric: not built yet"))
+    metric = M === Nothing ? 0 : M <: Diagonal ? 1 : 2            # DHMC_METRIC_NOTHING/_DIAGONAL/_SYMMETRIC
     a = t.stepsize_adaptation
     da = a isa DualAveraging ? Ref(DualAveragingC(a.δ, a.γ, a.κ, a.t₀, 0)) : C_NULL
     _ck(h, ccall((:dhmc_warmup_stage, LIB), Cint,
                  (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
-                 h.ptr, t.N, M === Nothing ? 0 : 1, da, t.λ, C_NULL, C_NULL, C_NULL, C_NULL))
+                 h.ptr, t.N, metric, da, t.λ, C_NULL, C_NULL, C_NULL, C_NULL))
 end
 
 end # module

@@ -521,3 +521,71 @@ def test_mcmc_from_host_positions(pkg):
         b.mcmc_from(q, 1)
     assert e.value.debug_information["chain_status"][77] & 1
     b.close()
+
+
+# --------------------------------------------------------------- reference integration tests (test/test_mcmc.jl)
+def _rhat(x):
+    """split-R̂ per parameter; x: [draw, chain, param] (stack_posterior_matrices layout)."""
+    n = x.shape[0] // 2
+    y = np.concatenate([x[:n], x[n:2 * n]], axis=1)
+    W = y.var(0, ddof=1).mean(0)
+    B = n * y.mean(0).var(0, ddof=1)
+    return np.sqrt(((n - 1) / n * W + B / n) / W)
+
+
+def test_mcmc_with_warmup_normal_moments(pkg):
+    """test_mcmc.jl:18-26 with the full default warm-up, 64 chains at once."""
+    D, N, K = 5, 2000, 64
+    ℓ = pkg.DiagNormal(np.ones(D), np.ones(D))
+    res = pkg.mcmc_with_warmup(123, ℓ, N, chains=K)
+    Z = pkg.pool_posterior_matrices(res)                      # [param, draw ⊗ chain]
+    assert Z.shape == (D, N * K)
+    assert np.max(np.abs(Z.mean(1) - 1)) < 0.04 and np.max(np.abs(Z.std(1, ddof=1) - 1)) < 0.04
+    S = pkg.stack_posterior_matrices(res)                     # [draw, chain, param], test_mcmc.jl:74-80
+    assert S.shape == (N, K, D)
+    assert np.all(_rhat(S) < 1.02)                            # sample-correctness_utilities.jl:107-110
+    for k in (0, K - 1):
+        r = res[k]
+        assert r["posterior_matrix"].shape == (D, N)
+        assert r["tree_statistics"]["acceptance_rate"].mean() >= 0.7
+        assert 0.5 <= r["ϵ"] <= 2
+        lq = np.array([ℓ.logdensity_and_gradient(q)[0] for q in r["posterior_matrix"].T[:20]])
+        np.testing.assert_allclose(r["logdensities"][:20], lq, rtol=1e-12)
+    accs = np.mean([res[k]["tree_statistics"]["acceptance_rate"].mean() for k in range(K)])
+    assert accs >= 0.8
+
+
+def test_fixed_stepsize_and_skipped_search(pkg):
+    """test_mcmc.jl:28-48"""
+    D, N, K = 5, 1000, 32
+    ℓ = pkg.DiagNormal(np.ones(D), np.ones(D))
+    res = pkg.mcmc_with_warmup(5, ℓ, N, chains=K, initialization={"ϵ": 1.0},
+                               warmup_stages=pkg.fixed_stepsize_warmup_stages())
+    assert all(res[k]["ϵ"] == 1.0 for k in range(K))
+    Z = pkg.pool_posterior_matrices(res)
+    assert np.max(np.abs(Z.mean(1) - 1)) < 0.05
+    res = pkg.mcmc_with_warmup(6, ℓ, N, chains=K, initialization=dict(ϵ=1.0),
+                               warmup_stages=pkg.default_warmup_stages(stepsize_search=None))
+    assert all(0.5 <= res[k]["ϵ"] <= 2 for k in range(K))
+    with pytest.raises(pkg.ArgumentError):              # search refuses a user-supplied ϵ, mcmc.jl:137
+        pkg.mcmc_with_warmup(6, ℓ, 10, chains=4, initialization={"ϵ": 1.0})
+
+
+def test_200_dim_never_reaches_max_depth(pkg):
+    """test_mcmc.jl:60-72: N(0, I₂₀₀), max_depth 12, 20 chains × 1000 draws."""
+    res = pkg.mcmc_with_warmup(11, pkg.StandardNormal(200), 1000, chains=20, algorithm=pkg.NUTS(max_depth=12))
+    for k in range(20):
+        ts = res[k]["tree_statistics"]
+        assert not np.any((ts["left"] == 1) & (ts["right"] == 0)) and ts["depth"].max() < 12
+
+
+def test_funnel_sample_correctness(pkg):
+    """sample-correctness_tests.jl:112-118 (funnel): R̂ and marginal of v across many chains.
+    The raw funnel's neck makes v mix slowly for NUTS with 1000 draws (the reference tests a
+    mixed/transformed funnel with 10 000 draws), hence the looser bound on v."""
+    res = pkg.mcmc_with_warmup(3, pkg.Funnel(5), 1000, chains=256)
+    S = pkg.stack_posterior_matrices(res)
+    rh = _rhat(S)
+    assert rh[0] < 1.3 and np.all(rh[1:] < 1.05)
+    v = S[:, :, 0]
+    assert abs(v.mean()) < 0.35 and 2.2 < v.std() < 3.3          # v ~ N(0, 3)
