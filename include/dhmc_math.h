@@ -187,15 +187,67 @@ DHMC_HD double dm_log1p(double x) {
 /* x^y for x > 0 (DualAveraging: m^(-kappa), src/stepsize.jl:154) */
 DHMC_HD double dm_pow(double x, double y) { return dm_exp(y * dm_log(x)); }
 
+/* softplus(-d) = log(1 + exp(-d)) for d >= 0 — the only transcendental on the tree's
+ * per-merge critical path (logaddexp of log weights / acceptance sums).  Table driven, no
+ * division: exp(-d) = 2^k * T[j] * exp(r) with |r| <= ln2/128, then log(u), u = 1 + t in
+ * (1,2), = logc[i] + log1p(u*invc[i] - 1) over 128 intervals, plus the rounding error of u.
+ * Absolute error ~1e-16 (it is always ADDED to max(a,b)); deterministic like the rest. */
+#include "dhmc_tables.h"
+static const double dm_h_exp2[64] = DM_TAB_EXP2_INIT;
+static const double dm_h_invc[128] = DM_TAB_INVC_INIT;
+static const double dm_h_logc[128] = DM_TAB_LOGC_INIT;
+#if defined(__CUDACC__)
+static __constant__ double dm_d_exp2[64] = DM_TAB_EXP2_INIT;
+static __constant__ double dm_d_invc[128] = DM_TAB_INVC_INIT;
+static __constant__ double dm_d_logc[128] = DM_TAB_LOGC_INIT;
+#endif
+#if defined(__CUDA_ARCH__)
+#define DM_TAB(name, i) dm_d_##name[i]
+#else
+#define DM_TAB(name, i) dm_h_##name[i]
+#endif
+DHMC_HDH double dm_softplus_neg(double d) {
+  if (d != d) return d;
+  if (d == 0.0) return DM_LN2;
+  if (d > 745.2) return 0.0;
+  const double x = -d;
+  const double kd = dm_floor(x * DM_64_INVLN2 + 0.5);
+  const int n = (int)kd;
+  double r = dm_fma(kd, -DM_LN2_64_HI, x);        /* kd * HI is exact */
+  r = dm_fma(kd, -DM_LN2_64_LO, r);               /* |r| <= ln2/128 */
+  const int j = n & 63, k = n >> 6;               /* n = 64 k + j, 0 <= j < 64 */
+  double p = 1.0 / 120.0;
+  p = dm_fma(p, r, 1.0 / 24.0);
+  p = dm_fma(p, r, 1.0 / 6.0);
+  p = dm_fma(p, r, 0.5);
+  p = dm_fma(p * r, r, r);                        /* expm1(r) */
+  const double tj = DM_TAB(exp2, j);
+  const double y = dm_fma(tj, p, tj);             /* 2^(j/64) e^r */
+  const int k1 = k / 2, k2 = k - k1;
+  const double t = (y * dm_pow2i(k1)) * dm_pow2i(k2);   /* exp(-d) */
+  if (d > 36.7368005696771) return t;             /* 1 + t == 1: log1p(t) = t */
+  const double u = 1.0 + t;
+  if (u >= 2.0) return DM_LN2;
+  const int i = (int)((dm_bits(u) >> 45) & 127u);
+  const double ic = DM_TAB(invc, i);
+  const double rr = dm_fma(u, ic, -1.0);          /* |rr| <~ 2^-8 */
+  double q = -1.0 / 6.0;
+  q = dm_fma(q, rr, 1.0 / 5.0);
+  q = dm_fma(q, rr, -1.0 / 4.0);
+  q = dm_fma(q, rr, 1.0 / 3.0);
+  q = dm_fma(q, rr, -0.5);
+  q = dm_fma(q * rr, rr, rr);                     /* log1p(rr) */
+  const double c = t - (u - 1.0);                 /* rounding error of u, exact */
+  return DM_TAB(logc, i) + dm_fma(c, ic, q);
+}
+
 /* log(exp(a)+exp(b)), LogExpFunctions.logaddexp semantics
  * (call sites src/trees.jl:145, src/NUTS.jl:70): equal arguments (incl. both
  * -Inf) give a + log(2); otherwise max + log1pexp(-|a-b|). */
 DHMC_HD double dm_logaddexp(double a, double b) {
   double d = (a == b) ? 0.0 : dm_fabs(a - b);
   double mx = dm_max_nan(a, b);
-  double t = -d;
-  double l = (t < -36.7368005696771) ? dm_exp(t) : dm_log1p(dm_exp(t));
-  return mx + l;
+  return mx + dm_softplus_neg(d);
 }
 
 /* log(1+exp(x)) (logistic-regression likelihood) */

@@ -66,6 +66,7 @@ void orc_math(int fn, int n, const double* x, const double* y, double* out) {
       case 5: out[i] = dm_log1pexp(x[i]); break;
       case 6: { double s, c; dm_sincos2pi(x[i], &s, &c); out[i] = s; break; }
       case 7: { double s, c; dm_sincos2pi(x[i], &s, &c); out[i] = c; break; }
+      case 8: out[i] = dm_softplus_neg(x[i]); break;
       default: out[i] = dm_nan();
     }
   }

@@ -142,7 +142,7 @@ def _params(family, D, params):
 
 # ---------------------------------------------------------------- math
 _FN = {"exp": 0, "log": 1, "log1p": 2, "logaddexp": 3, "pow": 4, "log1pexp": 5,
-       "sin2pi": 6, "cos2pi": 7}
+       "sin2pi": 6, "cos2pi": 7, "softplus_neg": 8}
 
 
 def math(fn, x, y=None):

@@ -30,6 +30,19 @@ def test_exp_log_accuracy(po):
     assert _max_ulp(po.math("cos2pi", u), [mp.cos(2 * mp.pi * mp.mpf(float(v))) for v in u]) < 3
 
 
+def test_softplus_table_accuracy(po):
+    """dm_softplus_neg(d) = log(1 + exp(-d)): table-driven, absolute error ~1e-16 (it is always
+    added to max(a, b) inside logaddexp)."""
+    mp.mp.prec = 200
+    rng = np.random.default_rng(5)
+    d = np.concatenate([rng.uniform(0, 40, 6000), np.exp(rng.uniform(-40, 3, 2000)),
+                        [0.0, 36.7368005696771, 36.74, 50.0, 700.0, 745.0, 746.0]])
+    got = po.math("softplus_neg", d)
+    ref = np.array([float(mp.log1p(mp.exp(-mp.mpf(float(v))))) for v in d])
+    assert np.max(np.abs(got - ref)) < 2.3e-16
+    assert po.math("softplus_neg", [np.inf])[0] == 0.0 and np.isnan(po.math("softplus_neg", [np.nan])[0])
+
+
 def test_special_values(po):
     inf, nan = np.inf, np.nan
     e = po.math("exp", [-inf, inf, 710.0, -746.0, 0.0])
