@@ -32,6 +32,7 @@ struct SmemLayout {
   int red_off;    // doubles: [2][kMaxWarps][kRedWidth]
   int ctl_off;    // bytes from base: Entry[W][kMaxLevels+1]
   int misc_off;   // bytes: int[4]
+  int top_off;    // bytes: TopState[W] (transition-level scalars, one copy per warp)
   int xs_off;     // bytes: staging vector for the dense mat-vec (dense metric only)
   int slots_off;  // bytes
   size_t total;   // bytes
@@ -47,6 +48,8 @@ __host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride
   off = (off + 15) & ~(size_t)15;
   L.misc_off = (int)off;
   off += 16;
+  L.top_off = (int)off;
+  off += ((sizeof(TopState) + 15) & ~(size_t)15) * (size_t)W;
   L.xs_off = (int)off;
   off += sizeof(double) * xs;
   L.slots_off = (int)off;
@@ -80,6 +83,7 @@ struct DeviceBackend {
   // memory
   double* red; int red_buf;
   Entry* ctl;
+  TopState* tops;
   double* sm_slots; double* gl_slots; int n_sm;
   const double* mparams;
   int n_slots;
@@ -169,6 +173,8 @@ struct DeviceBackend {
   }
 
   // ---- interface used by NutsMachine ----
+  __device__ __forceinline__ TopState& top() const { return *tops; }
+  __device__ __forceinline__ void top_sync() const { __syncwarp(); }
   __device__ __forceinline__ uint64_t reserved_mask() const {
     return (1ull << (n_slots - 1)) | (1ull << (n_slots - 2));   // Welford mean / M2
   }

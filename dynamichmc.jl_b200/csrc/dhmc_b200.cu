@@ -86,6 +86,7 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN>& b,
   b.red_buf = 0;
   b.rexp_cache = 0.0; b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;
   b.ctl = reinterpret_cast<Entry*>(smem + L.ctl_off) + b.warp * (kMaxLevels + 1);
+  b.tops = reinterpret_cast<TopState*>(smem + L.top_off + b.warp * ((sizeof(TopState) + 15) & ~(size_t)15));
   b.sm_slots = reinterpret_cast<double*>(smem + L.slots_off);
   b.gl_slots = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
   b.n_sm = a.n_sm; b.n_slots = a.n_slots;
@@ -998,7 +999,9 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   a.out_q = d_post; a.out_stats = d_stats; a.out_eps = d_eps; a.out_lq = d_ld;
   if (cfg.metric == DHMC_METRIC_SYMMETRIC) a.covt = h->covt;
   const size_t out_bytes = posterior ? sizeof(double) * B * n * D : 0;
-  const int nchunks = (!outputs_on_device && B >= 4096 && out_bytes >= ((size_t)32 << 20)) ? 8 : 1;
+  // chunks must stay many waves long, or the ragged tail of every chunk idles the SMs
+  int nchunks = (!outputs_on_device && B >= 4096 && out_bytes >= ((size_t)32 << 20)) ? 8 : 1;
+  while (nchunks > 1 && B / (size_t)nchunks < (size_t)16 * (size_t)h->grid) nchunks /= 2;
   if (q_host) CKR(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));
   for (int ci = 0; ci < nchunks; ++ci) {
     const size_t c0 = B * ci / nchunks, c1 = B * (ci + 1) / nchunks, nc = c1 - c0;

@@ -76,6 +76,19 @@ struct AdaptConfig {
   int metric;          // DHMC_METRIC_*
 };
 
+// Transition-level scalars (touched once per doubling or per transition, not per leaf).
+// The GPU backend keeps them in shared memory (one copy per warp, every lane writes the same
+// values) so that the per-leaf state stays in registers: left to the compiler they are spilled to
+// local memory, i.e. to L2 latency, because shared memory takes almost all of the L1 carve-out.
+struct TopState {
+  double other_lq, zt_lq, zt_H, omega_top, v_log, eps;
+  double da_mu, da_Hbar, da_logeps, da_logepsbar;
+  long v_steps, term_l, term_r, da_m, total_steps;
+  int i_near, i_far, depth, regs_fwd;
+  uint32_t flags, dirs;
+  int s_oq, s_og, s_zq, s_zg, s_op, s_near, s_rhot;
+};
+
 template <class B>
 struct NutsMachine {
   B& b;
@@ -131,41 +144,51 @@ struct NutsMachine {
     n_exp = 0;
     // p = rand_p(rng, κ) first, directions second — NUTS.jl:233
     b.draw_momentum(key, t, p_override);
-    const uint32_t dirs = dir_override ? *dir_override : dm_rand_directions(key, t);
-    uint32_t flags = dirs;
+    TopState& S = b.top();
+    S.dirs = dir_override ? *dir_override : dm_rand_directions(key, t);
+    S.flags = S.dirs;
+    S.eps = eps;
+    uint32_t& flags = S.flags;
     const double pi0 = b.phase_logdensity();  // logdensity(H, z), NUTS.jl:236
 
     // ---- initial leaf (trees.jl:285, NUTS.jl:148-159 with is_initial) ----
     freemask = (n_slots >= 64 ? ~0ull : ((1ull << n_slots) - 1ull)) & ~b.reserved_mask();
-    const int s_oq = alloc_hi(), s_og = alloc_hi();   // other edge q, ∇ℓ (rarely touched)
-    int s_zq = alloc_hi(), s_zg = alloc_hi();         // proposal ζ of the whole tree
-    const int s_op = alloc_lo();                      // other edge p  (= far-edge momentum)
-    const int s_near = alloc_lo();                    // momentum of the near edge before the subtree
-    const int s_rhot = alloc_lo();                    // ρ of the whole tree
+    S.s_oq = alloc_hi(); S.s_og = alloc_hi();         // other edge q, ∇ℓ (rarely touched)
+    S.s_zq = alloc_hi(); S.s_zg = alloc_hi();         // proposal ζ of the whole tree
+    S.s_op = alloc_lo();                              // other edge p  (= far-edge momentum)
+    S.s_near = alloc_lo();                            // momentum of the near edge before the subtree
+    S.s_rhot = alloc_lo();                            // ρ of the whole tree
+    const int& s_oq = S.s_oq; const int& s_og = S.s_og; int& s_zq = S.s_zq; int& s_zg = S.s_zg;
+    const int& s_op = S.s_op; const int& s_near = S.s_near; const int& s_rhot = S.s_rhot;
     b.st_q(s_oq); b.st_g(s_og); b.st_p(s_op);
     b.st_q(s_zq); b.st_g(s_zg);
     b.st_p(s_rhot);
-    double other_lq = b.cur_lq();
-    double zt_lq = b.cur_lq(), zt_H = pi0;
-    double omega_top = 0.0;                           // Δ = 0 for the initial leaf
-    double v_log = -dm_inf(); long v_steps = 0;       // leaf_acceptance_statistic(Δ, true)
-    int i_near = 0, i_far = 0;
-    bool regs_fwd = true;
-    int depth = 0;
-    long term_l = 1, term_r = 0;                      // REACHED_MAX_DEPTH
+    double& other_lq = S.other_lq; double& zt_lq = S.zt_lq; double& zt_H = S.zt_H;
+    double& omega_top = S.omega_top; double& v_log = S.v_log; long& v_steps = S.v_steps;
+    int& i_near = S.i_near; int& i_far = S.i_far; int& regs_fwd = S.regs_fwd; int& depth = S.depth;
+    long& term_l = S.term_l; long& term_r = S.term_r;
+    other_lq = b.cur_lq();
+    zt_lq = b.cur_lq(); zt_H = pi0;
+    omega_top = 0.0;                                  // Δ = 0 for the initial leaf
+    v_log = -dm_inf(); v_steps = 0;                   // leaf_acceptance_statistic(Δ, true)
+    i_near = 0; i_far = 0;
+    regs_fwd = 1;
+    depth = 0;
+    term_l = 1; term_r = 0;                           // REACHED_MAX_DEPTH
+    b.top_sync();
 
     while (depth < max_depth) {
       const bool fwd = (flags & 1u) != 0;             // next_direction, trees.jl:31-34
       flags >>= 1;
-      if (depth > 0 && fwd != regs_fwd) {
+      if (depth > 0 && fwd != (regs_fwd != 0)) {
         // continue from the other edge: exchange it with the register-resident point
         double tmp = b.cur_lq(); b.set_cur_lq(other_lq); other_lq = tmp;
         b.swap_cur(s_oq, s_op, s_og);
         int ti = i_near; i_near = i_far; i_far = ti;
       }
-      regs_fwd = fwd;
+      regs_fwd = fwd ? 1 : 0;
       b.st_p(s_near);
-      const double eps_s = fwd ? eps : -eps;          // move, NUTS.jl:28-31
+      const double eps_s = fwd ? S.eps : -S.eps;      // move, NUTS.jl:28-31
 
       // ---------------- adjacent_tree(depth) flattened ----------------
       const unsigned nleaves = 1u << depth;
@@ -308,7 +331,7 @@ struct NutsMachine {
     ts->left = term_l; ts->right = term_r;
     ts->acceptance_rate = dm_min_nan(dm_exp(v_log) / (double)v_steps, 1.0);  // NUTS.jl:87
     ts->steps = v_steps;
-    ts->directions = dirs;
+    ts->directions = S.dirs;
     ts->pad = 0;
     // new position ζ.Q
     b.ld_q(s_zq); b.ld_g(s_zg); b.set_cur_lq(zt_lq);
@@ -335,25 +358,34 @@ struct NutsMachine {
   template <class Sink>
   DHMC_M double run(uint32_t t0, int N, double eps, const AdaptConfig& cfg,
                      const double* p_override, const uint32_t* dir_override, Sink& sink) {
-    DA A = da_init(eps > 0 ? eps : 1.0);
+    TopState& S = b.top();
+    {
+      DA A0 = da_init(eps > 0 ? eps : 1.0);
+      S.da_mu = A0.mu; S.da_m = A0.m; S.da_Hbar = A0.Hbar; S.da_logeps = A0.logeps; S.da_logepsbar = A0.logepsbar;
+    }
     if (cfg.metric != DHMC_METRIC_NOTHING) b.metric_reset(cfg.metric);
-    long total_steps = 0;
+    S.total_steps = 0;
     for (int n = 0; n < N; ++n) {
-      const double e = cfg.adapt ? dm_exp(A.logeps) : eps;   // current_ϵ :163
+      const double e = cfg.adapt ? dm_exp(S.da_logeps) : eps;   // current_ϵ :163
       dhmc_tree_stats ts;
       transition(t0 + (uint32_t)n, e, p_override, dir_override, &ts);
-      total_steps += ts.steps;
+      S.total_steps += ts.steps;
       sink(n, ts, e);
       if (cfg.adapt) {
         const double a = ts.acceptance_rate;
-        if (a >= 0 && a <= 1) da_adapt(A, cfg, a);           // @argcheck 0 ≤ a ≤ 1
-        else status |= DHMC_CHAIN_BAD_ACCEPTANCE;
+        if (a >= 0 && a <= 1) {                                // @argcheck 0 ≤ a ≤ 1
+          DA A{S.da_mu, S.da_m, S.da_Hbar, S.da_logeps, S.da_logepsbar};
+          da_adapt(A, cfg, a);
+          S.da_m = A.m; S.da_Hbar = A.Hbar; S.da_logeps = A.logeps; S.da_logepsbar = A.logepsbar;
+        } else {
+          status |= DHMC_CHAIN_BAD_ACCEPTANCE;
+        }
       }
       if (cfg.metric != DHMC_METRIC_NOTHING) b.metric_push(cfg.metric, n + 1);
     }
     if (cfg.metric != DHMC_METRIC_NOTHING) b.metric_finish(cfg.metric, N);   // sample_M⁻¹, mcmc.jl:209-211
-    steps_out = total_steps;
-    return cfg.adapt ? dm_exp(A.logepsbar) : eps;                // final_ϵ :170
+    steps_out = S.total_steps;
+    return cfg.adapt ? dm_exp(S.da_logepsbar) : eps;             // final_ϵ :170
   }
   long steps_out = 0;
 

@@ -47,6 +47,9 @@ struct HostBackend {
       : D(D_), T(T_), family(fam), params(pr), q(D_), p(D_), g(D_), minv(D_, 1.0), rhoL(D_),
         Rnew(D_), slots(nslots, vec(D_)), wmean(D_), wm2(D_) {}
 
+  TopState top_;
+  TopState& top() { return top_; }
+  void top_sync() {}
   uint64_t reserved_mask() const { return 0; }
   double cur_lq() const { return lq; }
   void set_cur_lq(double v) { lq = v; }
