@@ -437,8 +437,17 @@ def test_full_size_properties_c2(pkg):
     st = eng.get_state(("q", "p"))
     assert np.max(np.abs(st["q"] - q0)) < 1e-9 and np.max(np.abs(st["p"] - p0)) < 1e-9   # :143-177
     eng.set_stepsize(0.28)
+    q_before = st["q"]
     out = eng.mcmc(1)
     ts = out["tree_statistics"][:, 0]
+    # the chunk-pipelined upload path (dhmc_mcmc_from) gives the same transition
+    eng2 = _engine(pkg, ℓ, K, seed=2026)
+    eng2.set_stepsize(0.28)
+    out2 = eng2.mcmc_from(q_before, 1)
+    eng2.close()
+    assert np.array_equal(out2["posterior_matrix"], out["posterior_matrix"])
+    assert np.array_equal(out2["tree_statistics"], out["tree_statistics"])
+    del out2
     assert np.all(ts["depth"] >= 0) and np.all(ts["depth"] <= 10)
     assert np.all(ts["steps"] >= 1) and np.all(ts["steps"] <= 2 ** (ts["depth"] + 1) - 1)
     assert np.all(ts["steps"] >= 2 ** ts["depth"] - 1)
