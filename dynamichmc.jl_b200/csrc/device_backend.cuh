@@ -33,6 +33,7 @@ struct SmemLayout {
   int ctl_off;    // bytes from base: Entry[W][kMaxLevels+1]
   int misc_off;   // bytes: int[4]
   int top_off;    // bytes: TopState[W] (transition-level scalars, one copy per warp)
+  int tab_off;    // bytes: double*[64] base address of every slot (shared or global)
   int xs_off;     // bytes: staging vector for the dense mat-vec (dense metric only)
   int slots_off;  // bytes
   size_t total;   // bytes
@@ -50,6 +51,8 @@ __host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride
   off += 16;
   L.top_off = (int)off;
   off += ((sizeof(TopState) + 15) & ~(size_t)15) * (size_t)W;
+  L.tab_off = (int)off;
+  off += sizeof(double*) * 64;
   L.xs_off = (int)off;
   off += sizeof(double) * xs;
   L.slots_off = (int)off;
@@ -89,9 +92,15 @@ struct DeviceBackend {
   int n_slots;
 
   __device__ __forceinline__ bool valid(int e) const { return tid + e * T < D; }
-  __device__ __forceinline__ double* slot(int s) const {
-    return (s < n_sm ? sm_slots + (size_t)s * stride : gl_slots + (size_t)(s - n_sm) * stride) + tid;
+  // slot base addresses are tabulated once per CTA in shared memory: one LDS.64 instead of a
+  // 64-bit select + multiply-add at every access
+  double** slot_tab;
+  __device__ __forceinline__ void build_slot_table() {
+    for (int s = tid; s < 64; s += T)
+      slot_tab[s] = s < n_sm ? sm_slots + (size_t)s * stride : gl_slots + (size_t)(s - n_sm) * stride;
+    if (W > 1) __syncthreads(); else __syncwarp();
   }
+  __device__ __forceinline__ double* slot(int s) const { return slot_tab[s] + tid; }
 
   // ---- scalar all-reduce of N <= 8 values in the canonical order.
   // Intra-warp: shuffle reduce-scatter with xor offsets 16, 8, 4, 2, 1 — at each

@@ -90,6 +90,8 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN>& b,
   b.sm_slots = reinterpret_cast<double*>(smem + L.slots_off);
   b.gl_slots = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
   b.n_sm = a.n_sm; b.n_slots = a.n_slots;
+  b.slot_tab = reinterpret_cast<double**>(smem + L.tab_off);
+  b.build_slot_table();
   b.mparams = a.mparams;
 }
 
