@@ -911,6 +911,7 @@ int dhmc_leapfrog(dhmc_handle* h, int32_t n_steps, int32_t sign) {
   if (!h || n_steps < 0) return DHMC_EARG;
   if (!h->has_position || !h->has_eps) { h->err = "dhmc_leapfrog: set position and step size first"; return DHMC_EARG; }
   CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)h->cfg.n_chains, h->stream));   // status words describe the current call
   KArgs a = base_args(h);
   a.lf_steps = n_steps; a.lf_sign = sign;
   int rc = launch(h, K_LEAPFROG, a, 1);
@@ -945,6 +946,7 @@ int dhmc_find_initial_stepsize(dhmc_handle* h, double initial_eps, double log_th
   if (!h->has_position) { h->err = "set the position first"; return DHMC_EARG; }
   if (h->has_eps) { h->err = "stepsize ϵ manually specified, won't perform initial search"; return DHMC_EARG; }  // mcmc.jl:137
   CK(cudaSetDevice(h->cfg.device));
+  CK(cudaMemsetAsync(h->status, 0, sizeof(int) * (size_t)h->cfg.n_chains, h->stream));   // status words describe the current call
   KArgs a = base_args(h);
   a.s_init = initial_eps; a.s_thresh = log_threshold; a.s_maxiter = maxiter;
   int rc = launch(h, K_SEARCH, a, 1);
@@ -1004,7 +1006,7 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   // chunks must stay many waves long, or the ragged tail of every chunk idles the SMs
   int nchunks = (!outputs_on_device && B >= 4096 && out_bytes >= ((size_t)32 << 20)) ? 8 : 1;
   while (nchunks > 1 && B / (size_t)nchunks < (size_t)16 * (size_t)h->grid) nchunks /= 2;
-  if (q_host) CKR(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));
+  CKR(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));   // status words describe the current call
   for (int ci = 0; ci < nchunks; ++ci) {
     const size_t c0 = B * ci / nchunks, c1 = B * (ci + 1) / nchunks, nc = c1 - c0;
     a.chain_begin = (int)c0; a.chain_end = (int)c1;

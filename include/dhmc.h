@@ -112,9 +112,11 @@ int dhmc_metric_is_dense(dhmc_handle* h, int32_t* dense);
 int dhmc_set_stepsize(dhmc_handle* h, const double* eps, int broadcast);
 /* Momentum of the phase point used by dhmc_leapfrog / dhmc_phase_logdensity. */
 int dhmc_set_momentum(dhmc_handle* h, const double* p);
-/* Any output pointer may be NULL.  q, grad, minv, p: [D,B]; lq, eps: [B]. */
+/* Any output pointer may be NULL.  q, grad, minv, p: [D,B]; lq, eps: [B].  minv is the
+ * DIAGONAL metric; with a Symmetric metric use dhmc_get_metric_dense. */
 int dhmc_get_state(dhmc_handle* h, double* q, double* lq, double* grad, double* minv,
                    double* eps, double* p);
+/* Status words of the most recent state-changing call (they are reset when a call starts). */
 int dhmc_chain_status(dhmc_handle* h, int32_t* status /* [B] */);
 /* Number of transitions already drawn per chain (RNG counter); get/set make the
  * (q, κ, ϵ, counter) tuple a checkpoint (mcmc_keep_warmup/mcmc_steps, §8f). */
