@@ -2,7 +2,7 @@
 DynamicHMC.jl sampler API.  The numeric path is libdhmc_b200.so (hand-written
 sm_100a CUDA, csrc/); this package is the thin host mirror of the reference's
 interface over its C ABI.  There is no CPU fallback."""
-from . import _lib, parallel
+from . import _lib, diagnostics, parallel
 from .api import (ArgumentError, DiagNormal, Diagonal, DualAveraging, DynamicHMCError, Engine,
                   FixedStepsize, Funnel, GaussianKineticEnergy, InitialStepsizeSearch, LogisticRegression, NUTS,
                   Results, StandardNormal, Symmetric, TuningNUTS, default_warmup_stages,

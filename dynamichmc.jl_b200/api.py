@@ -443,6 +443,19 @@ class Engine:
         self._ck(self._lib.dhmc_mcmc_dev(self._h, C.c_int32(N), C.c_void_p(posterior_ptr or None),
                                          C.c_void_p(stats_ptr or None), C.c_void_p(logdens_ptr or None)))
 
+    def tree_summary_dev(self, stats_ptr, N, ebfmi=True):
+        """Diagnostics reduced on the GPU from a DEVICE statistics buffer [K, N] (dhmc_mcmc_dev)."""
+        depth = np.zeros(33, dtype=np.int64)
+        term = np.zeros(3, dtype=np.int64)
+        acc, steps = C.c_double(), C.c_int64()
+        eb = np.empty(self.K) if ebfmi else None
+        self._ck(self._lib.dhmc_tree_summary_dev(self._h, C.c_void_p(stats_ptr), C.c_int32(N), L.ptr(depth), L.ptr(term),
+                                                 C.byref(acc), C.byref(steps), L.ptr(eb)))
+        nz = np.nonzero(depth)[0]
+        return dict(N=self.K * N, a_mean=acc.value / (self.K * N), steps=steps.value,
+                    termination_counts=dict(max_depth=int(term[0]), divergence=int(term[1]), turning=int(term[2])),
+                    depth_counts=depth[: nz[-1] + 1].tolist() if nz.size else [], EBFMI=eb)
+
     # -- measurement hooks
     def last_total_steps(self):
         v = C.c_int64()

@@ -361,6 +361,40 @@ __global__ void k_transpose(const double* X, double* Xt, size_t N, size_t D) {  
     Xt[i] = X[n * D + j];
   }
 }
+// Device-side reduction of tree statistics (Diagnostics.summarize_tree_statistics /
+// EBFMI, diagnostics.jl:29-32, 65-106): one warp per chain over its N records.
+__global__ void k_tree_summary(const dhmc_tree_stats* stats, int N, int B, unsigned long long* depth_counts /*[33]*/,
+                               unsigned long long* term_counts /*[3]: max_depth, divergence, turning*/,
+                               double* acc_sum, unsigned long long* step_sum, double* ebfmi /*[B] or null*/) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int c = warp; c < B; c += nwarps) {
+    const dhmc_tree_stats* s = stats + (size_t)c * N;
+    double a = 0.0, sp = 0.0, sd2 = 0.0;
+    unsigned long long st = 0;
+    for (int n = lane; n < N; n += 32) {
+      const dhmc_tree_stats r = s[n];
+      a += r.acceptance_rate; st += (unsigned long long)r.steps; sp += r.pi;
+      if (n + 1 < N) { const double d = s[n + 1].pi - r.pi; sd2 += d * d; }
+      atomicAdd(depth_counts + (r.depth < 32 ? r.depth : 32), 1ull);
+      const int k = (r.left == 1 && r.right == 0) ? 0 : (r.left == r.right ? 1 : 2);
+      atomicAdd(term_counts + k, 1ull);
+    }
+    for (int o = 16; o; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o); sp += __shfl_xor_sync(0xffffffffu, sp, o);
+      sd2 += __shfl_xor_sync(0xffffffffu, sd2, o); st += __shfl_xor_sync(0xffffffffu, st, o);
+    }
+    const double mean = sp / N;
+    double ss = 0.0;
+    for (int n = lane; n < N; n += 32) { const double d = s[n].pi - mean; ss += d * d; }
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) {
+      atomicAdd(acc_sum, a); atomicAdd(step_sum, st);
+      if (ebfmi) ebfmi[c] = (N > 1) ? (sd2 / (N - 1)) / (ss / (N - 1)) : dm_nan();
+    }
+  }
+}
+
 // broadcast a D-vector (or scalar when D == 1) to all chains
 __global__ void k_broadcast(double* dst, const double* src, size_t D, size_t B) {
   const size_t n = D * B;
@@ -1112,6 +1146,34 @@ int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats*
   if (N == 0) return DHMC_OK;
   AdaptConfig cfg{};
   return run_nuts(h, N, cfg, 0.0, nullptr, nullptr, posterior, stats, nullptr, logdens, true, true);
+}
+
+int dhmc_tree_summary_dev(dhmc_handle* h, const dhmc_tree_stats* stats_dev, int32_t N, int64_t* depth_counts,
+                          int64_t* termination_counts, double* acceptance_sum, int64_t* steps_sum, double* ebfmi) {
+  if (!h || !stats_dev || N < 1) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  const int B = (int)h->cfg.n_chains;
+  unsigned long long* d_cnt = nullptr;   // [33 depth][3 term][1 steps]
+  double* d_f = nullptr;                 // [1 acc][B ebfmi]
+  CK(cudaMalloc(&d_cnt, sizeof(unsigned long long) * 37));
+  CK(cudaMalloc(&d_f, sizeof(double) * (1 + (size_t)B)));
+  CK(cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long) * 37, h->stream));
+  CK(cudaMemsetAsync(d_f, 0, sizeof(double), h->stream));
+  k_tree_summary<<<h->sm_count * 8, 256, 0, h->stream>>>(stats_dev, N, B, d_cnt, d_cnt + 33, d_f, d_cnt + 36, ebfmi ? d_f + 1 : nullptr);
+  h->launches += 1;
+  unsigned long long cnt[37];
+  double acc = 0;
+  cudaError_t e = cudaMemcpyAsync(cnt, d_cnt, sizeof cnt, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&acc, d_f, sizeof acc, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && ebfmi) e = cudaMemcpyAsync(ebfmi, d_f + 1, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_cnt); cudaFree(d_f);
+  if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return DHMC_ECUDA; }
+  if (depth_counts) for (int i = 0; i < 33; ++i) depth_counts[i] = (int64_t)cnt[i];
+  if (termination_counts) for (int i = 0; i < 3; ++i) termination_counts[i] = (int64_t)cnt[33 + i];
+  if (steps_sum) *steps_sum = (int64_t)cnt[36];
+  if (acceptance_sum) *acceptance_sum = acc;
+  return DHMC_OK;
 }
 
 int dhmc_last_total_steps(dhmc_handle* h, int64_t* steps) { if (!h || !steps) return DHMC_EARG; *steps = h->last_steps; return DHMC_OK; }

@@ -158,6 +158,15 @@ int dhmc_mcmc_from(dhmc_handle* h, const double* q, int32_t N, double* posterior
 int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats,
                   double* logdens);
 
+/* ---- diagnostics on device-resident statistics (§8f) ------------------------ */
+/* Diagnostics.summarize_tree_statistics / EBFMI (diagnostics.jl:29-32, 65-106) reduced on the
+ * GPU over stats_dev [N,B] (DEVICE pointer, e.g. the buffer given to dhmc_mcmc_dev): pooled
+ * depth counts [33], termination counts [max_depth, divergence, turning], Σ acceptance rate,
+ * Σ steps (host outputs, may be NULL) and the per-chain EBFMI [B] (host, may be NULL). */
+int dhmc_tree_summary_dev(dhmc_handle* h, const dhmc_tree_stats* stats_dev, int32_t N,
+                          int64_t* depth_counts, int64_t* termination_counts,
+                          double* acceptance_sum, int64_t* steps_sum, double* ebfmi);
+
 /* ---- measurement hooks ------------------------------------------------- */
 /* Σ tree_statistics.steps over all chains and draws of the last sampling call. */
 int dhmc_last_total_steps(dhmc_handle* h, int64_t* steps);

@@ -600,3 +600,25 @@ def test_funnel_sample_correctness(pkg):
     # v ~ N(0, 3) exactly, but NUTS under-explores the neck of the raw funnel: the known upward bias
     # of E[v] (≈ +1 at this chain length, identical in the oracle) — check the biased range.
     assert -0.5 < v.mean() < 1.8 and 2.0 < v.std() < 3.4, (v.mean(), v.std())
+
+
+def test_diagnostics_host_and_device(pkg):
+    """Diagnostics.EBFMI / summarize_tree_statistics (diagnostics.jl): numpy mirror on returned
+    statistics vs the device-side reduction over a device-resident statistics buffer."""
+    import torch
+    D, K, N = 20, 300, 64
+    eng = _engine(pkg, pkg.Funnel(D), K, seed=17)
+    eng.random_position(); eng.set_stepsize(0.2)
+    stats_dev = torch.empty((K, N, 56), dtype=torch.uint8, device="cuda")
+    eng.mcmc_dev(N, 0, stats_dev.data_ptr(), 0)
+    dev = eng.tree_summary_dev(stats_dev.data_ptr(), N)
+    host = np.frombuffer(stats_dev.cpu().numpy().tobytes(), dtype=pkg._lib.tree_stats_dtype).reshape(K, N)
+    eng.close()
+    summ = pkg.diagnostics.summarize_tree_statistics(host)
+    assert dev["N"] == summ.N == K * N
+    assert dev["a_mean"] == pytest.approx(summ.a_mean, rel=1e-12)
+    assert dev["termination_counts"] == summ.termination_counts and dev["depth_counts"] == summ.depth_counts
+    assert dev["steps"] == int(host["steps"].sum())
+    eb = np.array([pkg.diagnostics.EBFMI(host[k]) for k in range(K)])
+    np.testing.assert_allclose(dev["EBFMI"], eb, rtol=1e-10)
+    assert len(summ.a_quantiles) == 5 and sum(summ.termination_counts.values()) == K * N
