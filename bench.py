@@ -156,7 +156,12 @@ def main():
     assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("DHMC_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner there at any debug level
+        if "DHMC_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["DHMC_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pkg = entry.load_package()
     D, K, n = args.dim, args.chains, args.draws_per_step

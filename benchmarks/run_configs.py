@@ -79,6 +79,8 @@ def c5(scale):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
+        os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     D, Kg, N = 1000, int(65536 * scale), 4
     sigma2 = 10.0 ** (4 * np.arange(D) / (D - 1))
