@@ -7,6 +7,7 @@
 // This is a TEST HARNESS: it is not linked into libdhmc_b200.so and the product
 // has no CPU fallback.
 #include <cstring>
+#include <set>
 #include <vector>
 
 #include "../../dynamichmc.jl_b200/csrc/nuts_machine.cuh"
@@ -190,7 +191,81 @@ struct Sink {
 
 }  // namespace
 
+// ---- DummyTrajectory backend (reference test/test_trees.jl:28-103) for the flattened machine:
+// positions are integers, a "vector" is the position it belongs to, a tree is turning when all
+// of its leaves are in the `turning` set, a leaf is divergent when it is in `divergent`.
+struct DummyBackend {
+  std::set<long> turning, divergent;
+  long z = 0, z0 = 0;
+  std::vector<long> slots;
+  std::vector<long> visited;
+  Entry entries[kMaxLevels + 2];
+  TopState top_;
+  static double l(long zz) { return -((double)(zz - 3) * (double)(zz - 3)) * 0.1; }   // testℓ, :106
+  explicit DummyBackend(int nslots) : slots(nslots, 0) {}
+  TopState& top() { return top_; }
+  void top_sync() {}
+  uint64_t reserved_mask() const { return 0; }
+  double cur_lq() const { return 0.0; }
+  void set_cur_lq(double) {}
+  void st_q(int s) { slots[s] = z; }
+  void st_p(int s) { slots[s] = z; }
+  void st_g(int s) { slots[s] = z; }
+  void st_rho(int) {}
+  void ld_q(int s) { z = slots[s]; }
+  void ld_p(int s) { z = slots[s]; }
+  void ld_g(int) {}
+  void swap_cur(int sq, int sp, int sg) { long t = slots[sq]; slots[sq] = z; slots[sp] = z; slots[sg] = z; z = t; }
+  void rho_from_p() {}
+  void rho_commit() {}
+  void put_entry(int j, const Entry& e) { entries[j] = e; }
+  Entry get_entry(int j) const { return entries[j]; }
+  void logaddexp2(double a0, double b0, double a1, double b1, double* r0, double* r1) {
+    *r0 = dm_logaddexp(a0, b0); *r1 = dm_logaddexp(a1, b1);
+  }
+  double randexp(dm_rng_key key, uint32_t t, uint32_t j) { return dm_randexp(key, t, j); }
+  void draw_momentum(dm_rng_key, uint32_t, const double*) {}
+  void draw_search_momentum(dm_rng_key, const double*) {}
+  double phase_logdensity() const { return l(z0); }
+  double leapfrog(double eps, int*) {                       // move: z ± 1, leaf: Δ = ℓ(z)
+    z += eps > 0 ? 1 : -1;
+    visited.push_back(z);
+    return divergent.count(z) ? -dm_inf() : l(z);
+  }
+  bool all_turning(long a, long b) const {
+    if (a > b) std::swap(a, b);
+    for (long k = a; k <= b; ++k) if (!turning.count(k)) return false;
+    return true;
+  }
+  bool merge_check(int sEf, int sEl, int, int sLf, bool L_leaf) {
+    const long lf = L_leaf ? z : slots[sLf];
+    return all_turning(slots[sEf], slots[sEl]) && all_turning(lf, z);
+  }
+  void metric_reset(int) {}
+  void metric_push(int, int) {}
+  void metric_finish(int, int) {}
+};
+
 extern "C" {
+
+// The product's flattened tree on the reference's DummyTrajectory: visited order, depth,
+// termination and steps for a given direction word.
+int hs_dummy_sample_trajectory(long z0, int max_depth, uint32_t flags, const long* turning, int nt,
+                               const long* divergent, int nd, long* visited, int* n_visited, int* depth,
+                               long* left, long* right, long* steps) {
+  const int ns = slots_needed(max_depth);
+  DummyBackend b(ns);
+  for (int i = 0; i < nt; ++i) b.turning.insert(turning[i]);
+  for (int i = 0; i < nd; ++i) b.divergent.insert(divergent[i]);
+  b.z = b.z0 = z0;
+  NutsMachine<DummyBackend> m(b, dm_make_key(1, 1), max_depth, -1000.0, ns);
+  dhmc_tree_stats ts;
+  m.transition(0, 1.0, nullptr, &flags, &ts);
+  *n_visited = (int)b.visited.size();
+  for (size_t i = 0; i < b.visited.size() && i < 4096; ++i) visited[i] = b.visited[i];
+  *depth = (int)ts.depth; *left = ts.left; *right = ts.right; *steps = ts.steps;
+  return 0;
+}
 
 int hs_slots_needed(int max_depth) { return slots_needed(max_depth); }
 

@@ -70,3 +70,17 @@ def find_initial_stepsize(family, q, seed, chain, minv=None, params=None, T=32, 
                                             C.c_double(log_threshold), C.c_int(maxiter),
                                             C.byref(eps))
     return eps.value, status
+
+
+def dummy_sample_trajectory(z, max_depth, flags, turning=(), divergent=()):
+    """The flattened machine on the reference's DummyTrajectory (test/test_trees.jl:28-103)."""
+    t = np.ascontiguousarray(list(turning), dtype=np.int64)
+    d = np.ascontiguousarray(list(divergent), dtype=np.int64)
+    vis = np.zeros(4096, dtype=np.int64)
+    nv, depth = C.c_int(), C.c_int()
+    left, right, steps = C.c_long(), C.c_long(), C.c_long()
+    lib().hs_dummy_sample_trajectory(C.c_long(z), C.c_int(max_depth), C.c_uint32(flags), _p(t), C.c_int(t.size),
+                                     _p(d), C.c_int(d.size), _p(vis), C.byref(nv), C.byref(depth),
+                                     C.byref(left), C.byref(right), C.byref(steps))
+    return dict(visited=vis[:nv.value].tolist(), depth=depth.value, termination=(left.value, right.value),
+                steps=steps.value)

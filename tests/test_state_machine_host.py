@@ -140,3 +140,28 @@ def test_slot_pool_is_large_enough():
     r = hs.run(0, q, 1e-3, 9, 9, max_depth=12, N=2)      # tiny ϵ: never turns, reaches depth 12
     assert np.all(r["tree_statistics"]["depth"] == 12)
     assert np.all(r["tree_statistics"]["steps"] == 2 ** 12 - 1)
+
+
+# ---- the flattened machine on the reference's DummyTrajectory (test/test_trees.jl) ----
+def test_dummy_sampled_tree_known_answer():
+    """test_trees.jl:156-165: sample_trajectory(…, 0, 3, Directions(0b101))."""
+    r = hs.dummy_sample_trajectory(0, 3, 0b101)
+    assert r["visited"] == [1, -1, -2, 2, 3, 4, 5]
+    assert r["termination"] == (1, 0) and r["depth"] == 3 and r["steps"] == 7
+
+
+@pytest.mark.parametrize("kw,z", [(dict(), 0), (dict(turning=[1, 2]), 3), (dict(divergent=[10, 11]), 3),
+                                  (dict(divergent=[10, 11, 12], turning=[-3, -2]), 3),
+                                  (dict(turning=[5, 6, 7]), 0), (dict(divergent=[5, 6, 7]), 0),
+                                  (dict(turning=[-1, -2, -3, -4]), 0)])
+def test_flattened_tree_matches_reference_recursion_exhaustively(po, kw, z):
+    """Every direction word up to depth 6 (the sets of test_trees.jl:238-262 and :126-142): visited
+    order, depth, termination code (incl. the unsorted backward turning span) and step count of the
+    flattened explicit-stack tree equal those of the reference-style recursion."""
+    for depth in range(1, 7):
+        for flags in range(2 ** depth):
+            o = po.dummy_sample_trajectory(z, depth, flags, **kw)
+            h = hs.dummy_sample_trajectory(z, depth, flags, **kw)
+            assert h["visited"] == o["visited"], (depth, flags)
+            assert h["depth"] == o["depth"] and h["termination"] == o["termination"], (depth, flags, h, o)
+            assert h["steps"] == o["v"][1]
