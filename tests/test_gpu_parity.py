@@ -22,7 +22,7 @@ def _models(pkg, rng, D):
             (pkg.Funnel(D), 2, None)]
 
 
-@pytest.mark.parametrize("D", [3, 10, 100, 200, 500, 1000])
+@pytest.mark.parametrize("D", [2, 3, 10, 100, 200, 500, 1000, 2000])
 def test_leapfrog_matches_oracle(pkg, po, D):
     rng = np.random.default_rng(D)
     K = 8
@@ -54,7 +54,7 @@ def test_leapfrog_matches_oracle(pkg, po, D):
         eng.close()
 
 
-@pytest.mark.parametrize("D,K", [(2, 64), (10, 96), (100, 48), (256, 16), (1000, 12)])
+@pytest.mark.parametrize("D,K", [(2, 64), (10, 96), (100, 48), (256, 16), (1000, 12), (2000, 6)])
 def test_sample_tree_matches_oracle(pkg, po, D, K):
     rng = np.random.default_rng(1000 + D)
     for ℓ, fam, hasp in _models(pkg, rng, D):
@@ -622,3 +622,25 @@ def test_diagnostics_host_and_device(pkg):
     eb = np.array([pkg.diagnostics.EBFMI(host[k]) for k in range(K)])
     np.testing.assert_allclose(dev["EBFMI"], eb, rtol=1e-10)
     assert len(summ.a_quantiles) == 5 and sum(summ.termination_counts.values()) == K * N
+
+
+def test_one_dimensional_problem(pkg, po):
+    """dimension(ℓ) = 1 (the reference's variance-5e8 / 5e-8 univariate targets, sample-correctness_tests.jl:48-60)."""
+    K = 40
+    for var in (5e8, 5e-8, 1.0):
+        ℓ = pkg.DiagNormal(np.array([0.3]), np.array([var]))
+        eng = _engine(pkg, ℓ, K, seed=2)
+        T, _ = eng.layout()
+        q = np.random.default_rng(1).normal(size=(K, 1)) * np.sqrt(var)
+        eng.set_position(q); eng.set_metric(np.array([var])); eng.set_stepsize(0.7)
+        stats = eng.sample_tree()
+        new = eng.get_state(("q",))["q"]
+        for k in range(0, K, 7):
+            o = po.sample_tree(1, q[k], 0.7, 2, k, 0, minv=np.array([var]), params=ℓ.params(), T=T)
+            for f in INT_FIELDS:
+                assert o["stats"][f] == stats[k][f]
+            assert np.array_equal(new[k], o["q"])
+        eng.close()
+    res = pkg.mcmc_with_warmup(7, pkg.DiagNormal(np.array([1.0]), np.array([5e8])), 500, chains=32)
+    Z = pkg.pool_posterior_matrices(res)
+    assert abs(Z.std() / np.sqrt(5e8) - 1) < 0.1
