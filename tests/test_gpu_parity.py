@@ -276,7 +276,7 @@ def _spd(rng, D):
     return A @ A.T / D + np.diag(rng.uniform(0.5, 2.0, D))
 
 
-@pytest.mark.parametrize("D", [3, 10, 40, 100, 256])
+@pytest.mark.parametrize("D", [3, 10, 40, 100, 256, 400])
 def test_dense_metric_leapfrog_and_tree_match_oracle(pkg, po, D):
     """GaussianKineticEnergy(Symmetric M⁻¹) (hamiltonian.jl:73): W = cholesky(inv(M⁻¹)).L on
     device, p♯ = M⁻¹p mat-vec, rand_p = W·randn — against the oracle, bit for bit."""
@@ -358,7 +358,7 @@ def test_full_warmup_symmetric_matches_oracle(pkg, po, D):
 
 
 # --------------------------------------------------------------- logistic regression family
-@pytest.mark.parametrize("N,p", [(50, 3), (333, 40), (1000, 100), (2000, 256)])
+@pytest.mark.parametrize("N,p", [(50, 3), (333, 40), (1000, 100), (2000, 256), (600, 400)])
 def test_logistic_regression_matches_oracle(pkg, po, N, p):
     rng = np.random.default_rng(N + p)
     X = rng.normal(size=(N, p)) / np.sqrt(p)

@@ -165,3 +165,29 @@ def test_flattened_tree_matches_reference_recursion_exhaustively(po, kw, z):
             assert h["visited"] == o["visited"], (depth, flags)
             assert h["depth"] == o["depth"] and h["termination"] == o["termination"], (depth, flags, h, o)
             assert h["steps"] == o["v"][1]
+
+
+# ---- property-based sweep (hypothesis): flattened machine == recursive oracle on arbitrary inputs ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=150, deadline=None)
+@given(family=st.sampled_from([0, 1, 2, 3]), D=st.integers(2, 70), T=st.sampled_from([32, 64]),
+       logeps=st.floats(-6.0, 1.0), max_depth=st.integers(1, 9), seed=st.integers(0, 2 ** 40),
+       chain=st.integers(0, 2 ** 30), t=st.integers(0, 5000), dirs=st.one_of(st.none(), st.integers(0, 2 ** 32 - 1)),
+       min_delta=st.sampled_from([-1000.0, -1.0, -0.01]))
+def test_hypothesis_single_transition(po, family, D, T, logeps, max_depth, seed, chain, t, dirs, min_delta):
+    rng = np.random.default_rng(seed % (2 ** 32))
+    params = _problem(rng, family, D)
+    minv = np.exp(rng.uniform(-2, 2, D))
+    q = rng.normal(size=D)
+    eps = float(np.exp(logeps))
+    try:
+        o = po.sample_tree(family, q, eps, seed, chain, t, minv=minv, params=params, T=T, max_depth=max_depth,
+                           min_delta=min_delta, directions=dirs)
+    except po.OracleError:
+        return      # non-finite position: the reference throws (hamiltonian.jl:203); the device flags the chain
+    h = hs.run(family, q, eps, seed, chain, t0=t, N=1, minv=minv, params=params, T=T, max_depth=max_depth,
+               min_delta=min_delta, directions=dirs)
+    _same_stats(o["stats"], h["tree_statistics"][0])
+    assert np.array_equal(o["q"], h["q"]) and o["lq"] == h["lq"]
