@@ -61,11 +61,220 @@ __host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride
   return L;
 }
 
+// ---- packed chain groups (logistic family): one likelihood round of a whole CTA ----
+// Every warp of the CTA calls this the same number of times: a warp with a chain calls it
+// from eval_model (active, its β already published in cb_beta), a warp that has run out of
+// chains attends from coop_finish until all warps are done, so the CTA barriers below
+// always see all 32·G threads.
+//   phase 1:  rows n are split over all threads (four per thread and pass); a thread computes
+//             η_n of all G chains, then the ll term and the residual per chain;
+//   phase 1b: each active warp sums its chain's ll terms in the lane-strided order;
+//   phase 2:  columns j are split over the threads; a thread accumulates (Xᵀr)_j of all G
+//             chains over n = 0..N-1.
+// Both passes over the design matrix (Xᵀ in phase 1, X in phase 2) are fed through a
+// three-stage cp.async ring in shared memory: each element of X reaches the SM once per G
+// gradients and two tiles are always in flight, so neither L2 nor HBM latency is exposed.
+// Returns this lane's partial Σ ll (<= 0, or NaN), or +1.0 when no warp is active any more
+// (which means that every warp is done).  Requires D <= 32·G.
+constexpr int kCoopStages = 3;
+constexpr int kCoopTile = 4096;                                       // doubles of X / Xᵀ per stage
+constexpr int kCoopMaxRows = 64;                                      // rows of X per phase-2 tile, at most
+__host__ __device__ constexpr int coop_stage_doubles(int G) { return kCoopTile + kCoopMaxRows * G; }   // + residuals [rows][G]
+__host__ __device__ inline int coop_rows(int D) {                     // even, rows·D <= kCoopTile (D <= 256)
+  int r = (kCoopTile / (D < 1 ? 1 : D)) & ~1;
+  return r < 2 ? 2 : r > kCoopMaxRows ? kCoopMaxRows : r;
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// lXt has leading dimension ldn (even, >= N); lres is [N][G] (row-major), lll is [G][N].
+template <int G>
+__device__ __noinline__ double coop_core(bool active, int lane, int grp, int ctid, int D, int lN, int ldn,
+                                         const double* __restrict__ lX, const double* __restrict__ lXt,
+                                         const double* __restrict__ ly, double* lres, double* lll,
+                                         int* cb_flags, const double* cb_beta, double* cb_grad, double* cb_stage) {
+  constexpr int NT = 32 * G;
+  constexpr int S = kCoopStages;
+  constexpr int STG = coop_stage_doubles(G);
+  if (lane == 0) cb_flags[grp] = active ? 1 : 0;
+  __syncthreads();
+  unsigned amask = 0;
+#pragma unroll
+  for (int gg = 0; gg < G; ++gg)
+    if (cb_flags[gg]) amask |= 1u << gg;
+  if (amask == 0) return 1.0;
+
+  // ---------------- phase 1: tiles of J rows of Xᵀ × RB observations
+  {
+    constexpr int RB = 4 * NT;             // observations per pass
+    constexpr int J = kCoopTile / RB;      // coefficients per tile
+    static_assert(J >= 1 && J * RB == kCoopTile, "tile shape");
+    const int nchunks = (D + J - 1) / J;
+    const int npass = (lN + RB - 1) / RB;
+    const int ntiles = npass * nchunks;
+    auto issue = [&](int t) {
+      if (t < ntiles) {
+        const int ps = t / nchunks, ch = t - ps * nchunks;
+        const int n0 = ps * RB;
+        const int cnt = ldn - n0 < RB ? ldn - n0 : RB;     // doubles per row segment (even)
+        const int cpr = cnt >> 1;                           // 16-byte pieces per row segment
+        double* dst = cb_stage + (size_t)(t % S) * STG;
+#pragma unroll
+        for (int jj = 0; jj < J; ++jj) {
+          const int j = ch * J + jj;
+          if (j < D) {
+            const double* sj = lXt + (size_t)j * ldn + n0;
+            for (int k = ctid; k < cpr; k += NT) cp_async16(dst + jj * RB + 2 * k, sj + 2 * k);
+          }
+        }
+      }
+      cp_async_commit();                   // always: group counting stays uniform
+    };
+    issue(0);
+    issue(1);
+    double eta[4][G];
+    for (int t = 0; t < ntiles; ++t) {
+      cp_async_wait<1>();                  // this thread's pieces of tile t have landed
+      __syncthreads();                     // everyone's have, and everyone is done with tile t-1
+      issue(t + 2);                        // refills the stage of tile t-1
+      const int ps = t / nchunks, ch = t - ps * nchunks;
+      if (ch == 0) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int gg = 0; gg < G; ++gg) eta[u][gg] = 0.0;
+      }
+      const double* src = cb_stage + (size_t)(t % S) * STG + ctid;
+#pragma unroll
+      for (int jj = 0; jj < J; ++jj) {
+        const int j = ch * J + jj;
+        if (j < D) {
+          double x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = src[jj * RB + u * NT];
+          const double* bj = cb_beta + (size_t)j * G;
+#pragma unroll
+          for (int gg = 0; gg < G; ++gg) {
+            const double bv = bj[gg];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) eta[u][gg] = eta[u][gg] + x[u] * bv;
+          }
+        }
+      }
+      if (ch == nchunks - 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int n = ps * RB + ctid + u * NT;
+          if (n < lN) {
+            const double yn = __ldg(ly + n);
+#pragma unroll
+            for (int gg = 0; gg < G; ++gg) {
+              if (amask & (1u << gg)) {
+                lll[(size_t)gg * lN + n] = dhmc_logit_ll(yn, eta[u][gg]);
+                lres[(size_t)n * G + gg] = dhmc_logit_resid(yn, eta[u][gg]);
+              }
+            }
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+  // ---------------- phase 1b
+  double sll = 0.0;
+  if (active) {
+    const double* t = lll + (size_t)grp * lN;
+    for (int n = lane; n < lN; n += 32) sll = sll + t[n];
+  }
+  // ---------------- phase 2: tiles of R rows of X with their residuals [R][G]
+  {
+    const int R = coop_rows(D);
+    const int ntiles = (lN + R - 1) / R;
+    auto issue = [&](int t) {
+      if (t < ntiles) {
+        const int n0 = t * R;
+        const int rows = lN - n0 < R ? lN - n0 : R;
+        double* dst = cb_stage + (size_t)(t % S) * STG;
+        const double* sx = lX + (size_t)n0 * D;            // 16-byte aligned: R is even
+        const int cx = (rows * D + 1) >> 1;                 // X is allocated with two doubles of slack
+        for (int c = ctid; c < cx; c += NT) cp_async16(dst + 2 * c, sx + 2 * c);
+        const double* sr = lres + (size_t)n0 * G;
+        const int cr = (rows * G) >> 1;
+        for (int c = ctid; c < cr; c += NT) cp_async16(dst + kCoopTile + 2 * c, sr + 2 * c);
+      }
+      cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    double acc[G];
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg) acc[gg] = 0.0;
+    for (int t = 0; t < ntiles; ++t) {
+      cp_async_wait<1>();
+      __syncthreads();
+      issue(t + 2);
+      const int n0 = t * R;
+      const int rows = lN - n0 < R ? lN - n0 : R;
+      if (ctid < D) {
+        // rows in increasing n; operands are fetched from shared memory one row ahead of their use
+        const double* xr = cb_stage + (size_t)(t % S) * STG + ctid;
+        const double* rr = cb_stage + (size_t)(t % S) * STG + kCoopTile;
+        double r0[G], r1[G];
+        double x0 = 0.0, x1 = 0.0;
+#define DHMC_COOP_LD(r, x, nn)                                   \
+        if ((nn) < rows) {                                       \
+          x = xr[(size_t)(nn) * D];                              \
+          _Pragma("unroll") for (int gg = 0; gg < G; ++gg) r[gg] = rr[(nn) * G + gg]; \
+        }
+#define DHMC_COOP_ACC(r, x, nn)                                  \
+        if ((nn) < rows) {                                       \
+          _Pragma("unroll") for (int gg = 0; gg < G; ++gg) acc[gg] = acc[gg] + x * r[gg]; \
+        }
+        DHMC_COOP_LD(r0, x0, 0)
+        for (int nn = 0; nn < rows; nn += 2) {
+          DHMC_COOP_LD(r1, x1, nn + 1)
+          DHMC_COOP_ACC(r0, x0, nn)
+          DHMC_COOP_LD(r0, x0, nn + 2)
+          DHMC_COOP_ACC(r1, x1, nn + 1)
+        }
+#undef DHMC_COOP_LD
+#undef DHMC_COOP_ACC
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();                       // cb_grad lives in stage 0 of the ring: everyone is done with the tiles
+    if (ctid < D) {
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) cb_grad[(size_t)gg * NT + ctid] = acc[gg];
+    }
+    __syncthreads();
+  }
+  return sll;
+}
+
 // DENSE = Symmetric M⁻¹ per chain (hamiltonian.jl:73): p♯ = M⁻¹p is a D×D mat-vec
 // streamed from HBM, kept in registers next to p and stored with it — a momentum
 // slot holds the pair (p, p♯), so the state machine's bookkeeping is unchanged.
-template <int EPL, int FAM, int WARPS, bool DENSE = false>
+//
+// PACK > 1 ("packed chain groups", logistic family, one warp per chain): a CTA holds PACK
+// independent chains, one per warp.  Everything except the likelihood is private to the
+// warp; the likelihood is evaluated by the whole CTA for all PACK chains at once
+// (coop_round), so every element of X is read once per PACK gradients instead of once per
+// gradient — the family is bound by L2 traffic on X otherwise.  The per-chain arithmetic
+// and its order are unchanged (η_n sequential in j, (Xᵀr)_j sequential in n, Σ ll lane-strided).
+template <int EPL, int FAM, int WARPS, bool DENSE = false, int PACK = 1>
 struct DeviceBackend {
+  static_assert(PACK == 1 || (WARPS == 1 && FAM == DHMC_FAMILY_LOGISTIC), "packed groups: one warp per chain, logistic family");
+  static constexpr int G = PACK;
+  int grp, ctid;                            // warp (= chain group) within the CTA, thread within the CTA
+  int* cb_flags; double* cb_beta; double* cb_grad; double* cb_stage;   // CTA-shared exchange area
+  double* lll;                              // per-CTA scratch [G][N]: log-likelihood terms (lr holds residuals)
   // geometry: T = 32·WARPS threads per chain, compile-time so that strides fold
   static constexpr int W = WARPS;
   static constexpr int T = 32 * WARPS;
@@ -82,7 +291,7 @@ struct DeviceBackend {
   // accumulator (transposed lower) and the shared-memory staging vector
   const double* Mrow; const double* Wt; double* covt; double* xs;
   // logistic regression: X [N][D], Xᵀ [D][N], y [N], per-CTA residual scratch [N]
-  const double* lX; const double* lXt; const double* ly; double* lr; int lN;
+  const double* lX; const double* lXt; const double* ly; double* lr; int lN; int lLd;   // lLd: leading dimension of Xᵀ
   // memory
   double* red; int red_buf;
   Entry* ctl;
@@ -375,6 +584,39 @@ struct DeviceBackend {
     return -dm_inf();
   }
 
+  // ---- packed chain groups: one likelihood round of the whole CTA (coop_core above) ----
+  // Returns false (attendants only) when every warp of the CTA is done.
+  __device__ __forceinline__ bool coop_round(bool active, double& sum_ll, double (&xtr)[EPL]) {
+    static_assert(PACK > 1, "packed groups only");
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        if (i < D) cb_beta[(size_t)i * G + grp] = q[e];
+      }
+    }
+    const double sll = coop_core<G>(active, lane, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
+                                    cb_flags, cb_beta, cb_grad, cb_stage);
+    if (sll > 0.0) return false;         // sentinel: ll terms are <= 0, so are their sums
+    sum_ll = sll;
+    if (active) {
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        xtr[e] = i < D ? cb_grad[(size_t)grp * (32 * G) + i] : 0.0;
+      }
+    }
+    return true;
+  }
+  // a warp without further chains keeps attending the CTA's likelihood rounds
+  __device__ __forceinline__ void coop_finish() {
+    if constexpr (PACK > 1) {
+      double dummy_ll = 0.0;
+      double dummy[EPL];
+      while (coop_round(false, dummy_ll, dummy)) {}
+    }
+  }
+
   // Model evaluation at the current q: fills g, sets lq (sanitised).  If
   // `with_p`, also performs the second momentum half-step p += h·∇ℓ(q′) and
   // returns Σ p·(M⁻¹p) through *ksum (fused into the same reductions).
@@ -382,7 +624,37 @@ struct DeviceBackend {
   // bit2: ℓq was replaced by −Inf (what `strict` turns into an error, :212-215).
   __device__ __forceinline__ void eval_model(bool with_p, double h, double qbad_in, double* ksum,
                                              int* flags) {
-    if (FAM == DHMC_FAMILY_LOGISTIC) {
+    if constexpr (FAM == DHMC_FAMILY_LOGISTIC && PACK > 1) {
+      double r[5] = {0.0, 0.0, qbad_in, 0.0, 0.0};   // Σ ll, Σ β², bad q, bad ∇ℓ, Σ p·p♯
+      double acc[EPL];
+      coop_round(true, r[0], acc);
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = tid + e * T;
+        double ge = 0.0;
+        if (i < D) {
+          ge = dhmc_logit_grad(acc[e], q[e]);
+          if (!dm_isfinite(ge)) r[3] = 1.0;
+        }
+        r[1] = r[1] + q[e] * q[e];
+        g[e] = ge;
+        if (with_p) {
+          p[e] = p[e] + h * ge;
+          if constexpr (!DENSE) {
+            double psv = minv[e] * p[e];
+            r[4] = r[4] + p[e] * psv;
+          }
+        }
+      }
+      reduce(r);
+      double l = dhmc_logit_lq(r[0], r[1]);
+      if (!((dm_isfinite(l) && r[3] == 0.0) || l == -dm_inf())) *flags |= 4;
+      l = sanitise(l, r[3] != 0.0);
+      if (r[2] != 0.0) { *flags |= 1; l = -dm_inf(); }
+      if (r[3] != 0.0) *flags |= 2;
+      lq = l;
+      *ksum = r[4];
+    } else if (FAM == DHMC_FAMILY_LOGISTIC) {
       // η = Xβ: β is staged in shared memory, thread t handles rows n = t, t+T, …
       // (Xᵀ read coalesced over n); residuals go to the per-CTA scratch, then every
       // thread accumulates its own gradient elements over n = 0..N-1 (X read coalesced over j).
@@ -393,7 +665,7 @@ struct DeviceBackend {
       for (int n0 = tid; n0 < lN; n0 += 4 * T) {     // four rows per pass for ILP
         double eta[4] = {0.0, 0.0, 0.0, 0.0};
         const double* col = lXt + n0;
-        for (int j = 0; j < D; ++j, col += lN) {
+        for (int j = 0; j < D; ++j, col += lLd) {
           const double bj = xs[j];
 #pragma unroll
           for (int u = 0; u < 4; ++u)

@@ -61,7 +61,7 @@ struct KArgs {
   int xs_doubles;               // shared-memory staging vector (0 unless the dense arrays exist)
   const double *lX, *lXt, *ly;  // logistic regression data
   double* lr;                   // per-CTA residual scratch [grid][lN]
-  int lN;
+  int lN, lLd;                  // observations, leading dimension of Xᵀ (even)
 };
 
 // Register budget: minimum resident CTAs per SM the compiler must allow for.
@@ -72,29 +72,65 @@ __host__ __device__ constexpr int min_ctas(int W, int EPL) {
   return W == 1 ? 16 : W == 2 ? 8 : W == 4 ? (EPL >= 8 ? DHMC_MINCTAS_W4E8 : 4) : 2;
 }
 
-template <int EPL, int FAM, int W, bool DN>
-__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN>& b, const KArgs& a,
+// packed chain groups (G chains per CTA, one per warp): shared-memory bytes of the CTA-wide
+// exchange area behind the G per-group blocks — flags, β [32G][G], cp.async ring (Xᵀr [G][32G] is
+// handed back in stage 0 of the ring, which is idle between two rounds)
+__host__ __device__ constexpr size_t coop_smem_bytes(int G) {
+  return 64 + sizeof(double) * ((size_t)32 * G * G + (size_t)kCoopStages * coop_stage_doubles(G));
+}
+__host__ __device__ inline size_t group_smem_bytes(int W, int n_sm, size_t stride, size_t xs) {
+  return (smem_layout(W, n_sm, stride, xs).total + 15) & ~(size_t)15;
+}
+
+template <int EPL, int FAM, int W, bool DN, int G>
+__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G>& b, const KArgs& a,
                                               unsigned char* smem) {
+  b.ctid = threadIdx.x; b.grp = 0;
   b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5;
   b.D = a.D;
   const SmemLayout L = smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles);
+  b.lX = a.lX; b.lXt = a.lXt; b.ly = a.ly; b.lN = a.lN; b.lLd = a.lLd;
+  b.lr = a.lr ? a.lr + (size_t)blockIdx.x * a.lN : nullptr;
+  b.lll = nullptr; b.cb_flags = nullptr; b.cb_beta = b.cb_grad = b.cb_stage = nullptr;
+  size_t group = blockIdx.x;
+  if constexpr (G > 1) {
+    b.grp = threadIdx.x >> 5; b.tid = b.lane; b.warp = 0;
+    group = (size_t)blockIdx.x * G + b.grp;
+    const size_t per = group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles);
+    unsigned char* shared = smem + per * G;
+    b.cb_flags = reinterpret_cast<int*>(shared);
+    b.cb_beta = reinterpret_cast<double*>(shared + 64);
+    b.cb_stage = b.cb_beta + (size_t)32 * G * G;
+    b.cb_grad = b.cb_stage;
+    static_assert(coop_stage_doubles(G) >= 32 * G * G, "Xᵀr fits in one stage");
+    for (int i = threadIdx.x; i < 32 * G * G; i += 32 * G) b.cb_beta[i] = 0.0;
+    for (int i = threadIdx.x; i < kCoopStages * coop_stage_doubles(G); i += 32 * G) b.cb_stage[i] = 0.0;
+    b.lr = a.lr + (size_t)blockIdx.x * 2 * G * a.lN;       // residuals [N][G]
+    b.lll = b.lr + (size_t)G * a.lN;                       // ll terms   [G][N]
+    smem += per * b.grp;
+    __syncthreads();
+  }
   b.xs = reinterpret_cast<double*>(smem + L.xs_off);
   b.Mrow = nullptr; b.Wt = nullptr; b.covt = nullptr;
-  b.lX = a.lX; b.lXt = a.lXt; b.ly = a.ly; b.lN = a.lN;
-  b.lr = a.lr ? a.lr + (size_t)blockIdx.x * a.lN : nullptr;
   b.red = reinterpret_cast<double*>(smem + L.red_off);
   b.red_buf = 0;
   b.rexp_cache = 0.0; b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;
   b.ctl = reinterpret_cast<Entry*>(smem + L.ctl_off) + b.warp * (kMaxLevels + 1);
   b.tops = reinterpret_cast<TopState*>(smem + L.top_off + b.warp * ((sizeof(TopState) + 15) & ~(size_t)15));
   b.sm_slots = reinterpret_cast<double*>(smem + L.slots_off);
-  b.gl_slots = a.scratch + (size_t)blockIdx.x * a.scratch_per_cta;
+  b.gl_slots = a.scratch + group * a.scratch_per_cta;
   b.n_sm = a.n_sm; b.n_slots = a.n_slots;
   b.slot_tab = reinterpret_cast<double**>(smem + L.tab_off);
   b.build_slot_table();
   b.mparams = a.mparams;
 }
 
+// packed groups: every warp draws its own chains
+__device__ __forceinline__ int next_chain_warp(unsigned* counter, int begin, int lane) {
+  int c = 0;
+  if (lane == 0) c = begin + (int)atomicAdd(counter, 1u);
+  return __shfl_sync(0xffffffffu, c, 0);
+}
 __device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc, int begin) {
   __syncthreads();
   if (threadIdx.x == 0) s_misc[0] = begin + (int)atomicAdd(counter, 1u);
@@ -102,8 +138,8 @@ __device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc, int be
   return s_misc[0];
 }
 
-template <int EPL, int FAM, int W, bool DN>
-__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN>& b, const KArgs& a, long c,
+template <int EPL, int FAM, int W, bool DN, int G>
+__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN, G>& b, const KArgs& a, long c,
                                            bool with_p) {
   b.chain = c;
   b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;   // the randexp batch belongs to one chain
@@ -127,8 +163,8 @@ __device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN>& b, co
     if (with_p) b.matvec(b.p, b.ps);
   }
 }
-template <int EPL, int FAM, int W, bool DN>
-__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN>& b, double* dst,
+template <int EPL, int FAM, int W, bool DN, int G>
+__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN, G>& b, double* dst,
                                           const double (&v)[EPL], size_t base, int D) {
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
@@ -138,9 +174,9 @@ __device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN>& 
 }
 
 // ------------------------------------------------------------------ k_nuts
-template <int EPL, int FAM, int W, bool DN>
+template <int EPL, int FAM, int W, bool DN, int G>
 struct DrawSink {
-  DeviceBackend<EPL, FAM, W, DN>& b;
+  DeviceBackend<EPL, FAM, W, DN, G>& b;
   const KArgs& a;
   long c;
   __device__ __forceinline__ void operator()(int n, const dhmc_tree_stats& ts, double e) {
@@ -154,19 +190,21 @@ struct DrawSink {
   }
 };
 
-template <int EPL, int FAM, int W, bool DN>
-__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_nuts(const KArgs a) {
+template <int EPL, int FAM, int W, bool DN, int G = 1>
+__global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nuts(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN> b;
+  DeviceBackend<EPL, FAM, W, DN, G> b;
   setup_backend(b, a, smem);
   int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
   for (;;) {
-    const int c = next_chain(a.counter, s_misc, a.chain_begin);
+    int c;
+    if constexpr (G > 1) c = next_chain_warp(a.counter, a.chain_begin, b.lane);
+    else c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W, DN>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
-    DrawSink<EPL, FAM, W, DN> sink{b, a, c};
+    DrawSink<EPL, FAM, W, DN, G> sink{b, a, c};
     const double eps_next = m.run(a.t0, a.N, a.eps[c], a.cfg, a.p_override,
                                   a.dir_override ? a.dir_override + c : nullptr, sink);
     const size_t base = (size_t)c * a.D;
@@ -180,20 +218,23 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_nuts(const KArgs a
       atomicAdd(a.total_steps, (unsigned long long)m.steps_out);
     }
   }
+  b.coop_finish();
 }
 
 // ------------------------------------------------------------------ k_search
-template <int EPL, int FAM, int W, bool DN>
-__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_search(const KArgs a) {
+template <int EPL, int FAM, int W, bool DN, int G = 1>
+__global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_search(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN> b;
+  DeviceBackend<EPL, FAM, W, DN, G> b;
   setup_backend(b, a, smem);
   int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
   for (;;) {
-    const int c = next_chain(a.counter, s_misc, a.chain_begin);
+    int c;
+    if constexpr (G > 1) c = next_chain_warp(a.counter, a.chain_begin, b.lane);
+    else c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W, DN>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
     const double eps = m.find_initial_stepsize(a.s_init, a.s_thresh, a.s_maxiter, a.p_override);
     if (b.tid == 0) {
@@ -201,6 +242,7 @@ __global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_search(const KArgs
       if (m.status) atomicOr(a.status + c, m.status);
     }
   }
+  b.coop_finish();
 }
 
 // ------------------------------------------------------------------ k_leapfrog
@@ -354,11 +396,12 @@ __global__ void k_broadcast_mat(double* dst, const double* src, size_t dd, size_
     dst[i] = src[i % dd];
 }
 
-__global__ void k_transpose(const double* X, double* Xt, size_t N, size_t D) {   // Xt[j][n] = X[n][j]
-  const size_t tot = N * D;
+// Xt[j][n] = X[n][j], rows of Xt padded to ld >= N (pad = 0)
+__global__ void k_transpose(const double* X, double* Xt, size_t N, size_t D, size_t ld) {
+  const size_t tot = ld * D;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t j = i / N, n = i % N;
-    Xt[i] = X[n * D + j];
+    const size_t j = i / ld, n = i % ld;
+    Xt[i] = n < N ? X[n * D + j] : 0.0;
   }
 }
 // Device-side reduction of tree statistics (Diagnostics.summarize_tree_statistics /
@@ -410,6 +453,7 @@ __global__ void k_fill(double* dst, double v, size_t n) {
 struct dhmc_handle {
   dhmc_config cfg;
   int T = 0, W = 0, EPL = 0;
+  int G = 1;                        // chains per CTA of the persistent kernels (packed chain groups)
   size_t stride = 0;
   int n_slots = 0, n_sm = 0, grid = 0, sm_count = 0, light_grid = 0;
   size_t smem_bytes = 0, smem_light = 0;
@@ -434,7 +478,7 @@ struct dhmc_handle {
   bool dense = false;               // κ is a Symmetric (dense) metric
   double *minv_dense = nullptr, *wt = nullptr, *covt = nullptr, *dense_tmp = nullptr;
   double *lX = nullptr, *lXt = nullptr, *ly = nullptr, *lr = nullptr;   // logistic regression
-  int lN = 0;
+  int lN = 0, lLd = 0;
   int reg_ctas[2] = {0, 0};         // occupancy of k_nuts (diag, dense)
   size_t smem_sm = 0, smem_cta_max = 0;
   std::string err;
@@ -491,8 +535,15 @@ struct dhmc_handle;
 
 // dense (Symmetric metric) kernels are instantiated for the layouts of D <= 512
 constexpr bool dense_layout(int W, int EPL) { return W == 1 || (W == 2) || (W == 4 && EPL == 4); }
+constexpr int kPack = 8;            // packed chain groups: chains per CTA (logistic family, dim <= 256)
 template <int EPL, int FAM, int W>
-static const void* kernel_ptr(KernelId k, bool dense) {
+static const void* kernel_ptr(KernelId k, bool dense, int G = 1) {
+  if constexpr (FAM == DHMC_FAMILY_LOGISTIC && W == 1) {
+    if (G > 1) {
+      if (k == K_NUTS) return dense ? (const void*)k_nuts<EPL, FAM, 1, true, kPack> : (const void*)k_nuts<EPL, FAM, 1, false, kPack>;
+      if (k == K_SEARCH) return dense ? (const void*)k_search<EPL, FAM, 1, true, kPack> : (const void*)k_search<EPL, FAM, 1, false, kPack>;
+    }
+  }
   if (dense) {
     if constexpr (dense_layout(W, EPL)) {
       switch (k) {
@@ -515,6 +566,12 @@ static const void* kernel_ptr(KernelId k, bool dense) {
   }
 }
 
+// rows of N doubles in the logistic scratch: one per CTA of the light kernels, 2·G per CTA
+// (residuals and ll terms of every packed chain) of the persistent kernels
+static size_t lr_rows(const dhmc_handle* h) {
+  return std::max<size_t>((size_t)h->grid * (h->G > 1 ? 2 * (size_t)h->G : 1), (size_t)h->light_grid);
+}
+
 // Plan the persistent kernels for the current metric kind: CTAs per SM (register
 // limited), how many slots fit in shared memory, and the global scratch arena.
 static int plan(dhmc_handle* h) {
@@ -523,17 +580,23 @@ static int plan(dhmc_handle* h) {
   const size_t slot_doubles = h->stride * (h->dense ? 2 : 1);
   const size_t slot_bytes = sizeof(double) * slot_doubles;
   const size_t xs = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? h->stride : 0;
-  const SmemLayout L0 = smem_layout(h->W, 0, slot_doubles, xs);
-  h->smem_light = L0.total;
+  const int G = h->G;
+  auto heavy_smem = [&](int n_sm) -> size_t {
+    return G > 1 ? (size_t)G * group_smem_bytes(h->W, n_sm, slot_doubles, xs) + coop_smem_bytes(G)
+                 : smem_layout(h->W, n_sm, slot_doubles, xs).total;
+  };
+  struct { size_t total; } L0{heavy_smem(0)};
+  h->smem_light = smem_layout(h->W, 0, slot_doubles, xs).total;
   int& reg_ctas = h->reg_ctas[h->dense ? 1 : 0];
   if (reg_ctas == 0) {
     int rc = dispatch(h->W, h->EPL, h->cfg.family, [&](auto Wc, auto E, auto Fm) -> int {
       constexpr int WW = decltype(Wc)::value;
       constexpr int EP = decltype(E)::value;
       constexpr int FA = decltype(Fm)::value;
-      const void* fn = kernel_ptr<EP, FA, WW>(K_NUTS, h->dense);
+      const void* fn = kernel_ptr<EP, FA, WW>(K_NUTS, h->dense, G);
       if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
-      cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, fn, T, L0.total);
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L0.total);
+      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, fn, T * G, L0.total);
       if (e != cudaSuccess) { h->err = std::string("occupancy query: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
       return DHMC_OK;
     });
@@ -546,19 +609,19 @@ static int plan(dhmc_handle* h) {
   if (const char* ev = std::getenv("DHMC_L1_RESERVE_KB")) l1_reserve = (size_t)std::atol(ev) * 1024;
   size_t per_cta = (h->smem_sm - std::min(l1_reserve, h->smem_sm / 2)) / ctas - 1024;   // 1 KB system reservation per CTA
   if (per_cta > h->smem_cta_max) per_cta = h->smem_cta_max;
-  long n_sm = per_cta > L0.total ? (long)((per_cta - L0.total) / slot_bytes) : 0;
+  long n_sm = per_cta > L0.total ? (long)((per_cta - L0.total) / (slot_bytes * (size_t)G)) : 0;
   const int pool = h->n_slots - kWelfordSlots;   // the two highest slots stay in global memory
   if (n_sm > pool) n_sm = pool;
   h->n_sm = (int)n_sm;
-  h->smem_bytes = smem_layout(h->W, h->n_sm, slot_doubles, xs).total;
-  h->grid = (int)std::min<size_t>((size_t)ctas * h->sm_count, B);
+  h->smem_bytes = heavy_smem(h->n_sm);
+  h->grid = (int)std::min<size_t>((size_t)ctas * h->sm_count, (B + G - 1) / G);
   h->light_grid = (int)std::min<size_t>((size_t)h->sm_count * 16, B);
   h->scratch_per_cta = (size_t)(h->n_slots - h->n_sm) * slot_doubles;
   cudaFree(h->scratch); h->scratch = nullptr;
-  CK(cudaMalloc(&h->scratch, sizeof(double) * h->scratch_per_cta * (size_t)h->grid));
+  CK(cudaMalloc(&h->scratch, sizeof(double) * h->scratch_per_cta * (size_t)h->grid * (size_t)G));
   if (h->lN) {   // residual scratch of the logistic family follows the grid
     cudaFree(h->lr); h->lr = nullptr;
-    CK(cudaMalloc(&h->lr, sizeof(double) * (size_t)h->lN * (size_t)std::max(h->grid, h->light_grid)));
+    CK(cudaMalloc(&h->lr, sizeof(double) * (size_t)h->lN * lr_rows(h)));
   }
   return DHMC_OK;
 }
@@ -578,7 +641,7 @@ static KArgs base_args(dhmc_handle* h) {
   a.chain_begin = 0; a.chain_end = (int)h->cfg.n_chains;
   a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr;
   a.xs_doubles = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? (int)((size_t)h->T * h->EPL) : 0;
-  a.lX = h->lX; a.lXt = h->lXt; a.ly = h->ly; a.lr = h->lr; a.lN = h->lN;
+  a.lX = h->lX; a.lXt = h->lXt; a.ly = h->ly; a.lr = h->lr; a.lN = h->lN; a.lLd = h->lLd;
   return a;
 }
 
@@ -598,7 +661,8 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_st
   if (!heavy) { a.n_sm = 0; }
   const size_t smem = heavy ? h->smem_bytes : smem_layout(h->W, 0, a.stride, (size_t)a.xs_doubles).total;
   int grid = heavy ? h->grid : h->light_grid;
-  if (heavy) grid = std::max(1, std::min(grid, a.chain_end - a.chain_begin));
+  const int G = heavy ? h->G : 1;
+  if (heavy) grid = std::max(1, std::min(grid, (a.chain_end - a.chain_begin + G - 1) / G));
   if (heavy) {
     CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned), h->stream));
     if (reset_steps) CK(cudaMemsetAsync(h->total_steps, 0, sizeof(unsigned long long), h->stream));
@@ -608,12 +672,12 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_st
     constexpr int WW = decltype(Wc)::value;
     constexpr int EPL = decltype(E)::value;
     constexpr int FAM = decltype(Fm)::value;
-    const void* fn = kernel_ptr<EPL, FAM, WW>(k, h->dense);
+    const void* fn = kernel_ptr<EPL, FAM, WW>(k, h->dense, G);
     if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
     void* params[] = {(void*)&a};
-    e = cudaLaunchKernel(fn, dim3(grid), dim3(h->T), params, smem, h->stream);
+    e = cudaLaunchKernel(fn, dim3(grid), dim3(h->T * G), params, smem, h->stream);
     if (e != cudaSuccess) { h->err = std::string("cudaLaunchKernel: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
     return DHMC_OK;
   });
@@ -699,6 +763,17 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   const int rt = cfg->threads_per_chain;
   if (rt != 0 && !(rt == 32 || rt == 64 || rt == 128 || rt == 256)) { g_create_err = "threads_per_chain in {0,32,64,128,256}"; return DHMC_EARG; }
   choose_layout(cfg->dim, rt, &T, &EPL);
+  // logistic regression, dim <= 256: one warp per chain, kPack chains per CTA sharing every
+  // pass over X (packed chain groups); an explicit threads_per_chain keeps one chain per CTA
+  int pack = 1;
+  if (cfg->family == DHMC_FAMILY_LOGISTIC && rt == 0 && cfg->dim <= 32 * kPack) {
+    const char* ev = std::getenv("DHMC_PACK");
+    if (!(ev && std::atoi(ev) == 0)) {
+      pack = kPack; T = 32;
+      const int64_t e = (cfg->dim + 31) / 32;
+      EPL = e <= 1 ? 1 : e <= 2 ? 2 : e <= 4 ? 4 : 8;
+    }
+  }
   if (T == 0 || EPL == 0) { g_create_err = "dim too large for this build (dim <= 8 * threads_per_chain <= 2048)"; return DHMC_EARG; }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -709,7 +784,7 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   }
   if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "bad device ordinal"; return DHMC_EARG; }
   dhmc_handle* h = new dhmc_handle();
-  h->cfg = *cfg; h->T = T; h->W = T / 32; h->EPL = EPL; h->stride = (size_t)T * EPL;
+  h->cfg = *cfg; h->T = T; h->W = T / 32; h->EPL = EPL; h->stride = (size_t)T * EPL; h->G = pack;
   h->n_slots = slots_needed(cfg->max_depth);
   auto fail = [&](int rc) { g_create_err = h->err; dhmc_destroy(h); return rc; };
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return fail(e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA); } } while (0)
@@ -775,15 +850,17 @@ int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n) {
     if (N < 1 || n != 1 + N * D + N) { h->err = "dhmc_set_problem: expected 1 + N*D + N values"; return DHMC_EARG; }
     cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr);
     h->lX = h->lXt = h->ly = h->lr = nullptr;
-    CK(cudaMalloc(&h->lX, sizeof(double) * N * D));
-    CK(cudaMalloc(&h->lXt, sizeof(double) * N * D));
+    const size_t ld = (N + 1) & ~(size_t)1;                 // even leading dimension: 16-byte aligned row segments
+    CK(cudaMalloc(&h->lX, sizeof(double) * (N * D + 2)));  // slack for the last 16-byte piece of a tile
+    CK(cudaMemsetAsync(h->lX, 0, sizeof(double) * (N * D + 2), h->stream));
+    CK(cudaMalloc(&h->lXt, sizeof(double) * ld * D));
     CK(cudaMalloc(&h->ly, sizeof(double) * N));
-    CK(cudaMalloc(&h->lr, sizeof(double) * N * (size_t)std::max(h->grid, h->light_grid)));
+    CK(cudaMalloc(&h->lr, sizeof(double) * N * lr_rows(h)));
     CK(cudaMemcpyAsync(h->lX, params + 1, sizeof(double) * N * D, cudaMemcpyHostToDevice, h->stream));
     CK(cudaMemcpyAsync(h->ly, params + 1 + N * D, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
-    k_transpose<<<1024, 256, 0, h->stream>>>(h->lX, h->lXt, N, D);
+    k_transpose<<<1024, 256, 0, h->stream>>>(h->lX, h->lXt, N, D, ld);
     h->launches += 1;
-    h->lN = (int)N;
+    h->lN = (int)N; h->lLd = (int)ld;
     CK(cudaStreamSynchronize(h->stream));
     return DHMC_OK;
   }

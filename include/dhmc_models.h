@@ -61,7 +61,11 @@ DHMC_HD double dhmc_funnel_grad(int i, double x, double v, double ev, double S,
 
 /* --- LOGISTIC */
 DHMC_HD double dhmc_logit_sigma(double eta) { return 1.0 / (1.0 + dm_exp(-eta)); }
-DHMC_HD double dhmc_logit_ll(double y, double eta) { return y * eta - dm_log1pexp(eta); }
+/* y·η − log(1+e^η) with log(1+e^η) = max(η,0) + log(1+e^{−|η|}): one table-driven softplus (absolute
+ * accuracy, no division) instead of log1p(exp(η)) */
+DHMC_HD double dhmc_logit_ll(double y, double eta) {
+  return y * eta - ((eta > 0.0 ? eta : 0.0) + dm_softplus_neg(dm_fabs(eta)));
+}
 DHMC_HD double dhmc_logit_resid(double y, double eta) { return y - dhmc_logit_sigma(eta); }
 DHMC_HD double dhmc_logit_lq(double sum_ll, double sum_b2) { return sum_ll - 0.5 * sum_b2; }
 DHMC_HD double dhmc_logit_grad(double xtr, double beta) { return xtr - beta; }
