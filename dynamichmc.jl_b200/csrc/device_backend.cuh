@@ -162,7 +162,7 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
           for (int gg = 0; gg < G; ++gg) {
             const double bv = bj[gg];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) eta[u][gg] = eta[u][gg] + x[u] * bv;
+            for (int u = 0; u < 4; ++u) eta[u][gg] = dhmc_logit_mac(eta[u][gg], x[u], bv);
           }
         }
       }
@@ -234,7 +234,7 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
         }
 #define DHMC_COOP_ACC(r, x, nn)                                  \
         if ((nn) < rows) {                                       \
-          _Pragma("unroll") for (int gg = 0; gg < G; ++gg) acc[gg] = acc[gg] + x * r[gg]; \
+          _Pragma("unroll") for (int gg = 0; gg < G; ++gg) acc[gg] = dhmc_logit_mac(acc[gg], x, r[gg]); \
         }
         DHMC_COOP_LD(r0, x0, 0)
         for (int nn = 0; nn < rows; nn += 2) {
@@ -669,7 +669,7 @@ struct DeviceBackend {
           const double bj = xs[j];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            if (n0 + u * T < lN) eta[u] = eta[u] + __ldg(col + u * T) * bj;
+            if (n0 + u * T < lN) eta[u] = dhmc_logit_mac(eta[u], __ldg(col + u * T), bj);
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -690,7 +690,7 @@ struct DeviceBackend {
         const double rn = lr[n];
 #pragma unroll
         for (int e = 0; e < EPL; ++e)
-          if (tid + e * T < D) acc[e] = acc[e] + __ldg(row + e * T) * rn;
+          if (tid + e * T < D) acc[e] = dhmc_logit_mac(acc[e], __ldg(row + e * T), rn);
       }
       group_sync();
 #pragma unroll

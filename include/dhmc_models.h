@@ -15,8 +15,8 @@
  *   LOGISTIC    logistic regression with a N(0, I) prior, X [N x p], y in {0,1}:
  *               eta = X beta;  l = sum_n [y_n eta_n - log1pexp(eta_n)] - 1/2 |beta|^2
  *               grad = X' (y - sigma(eta)) - beta
- *               params = [N, X row-major (N*p), y (N)];  eta_n and (X' r)_j are sequential sums
- *               over j resp. n, the two scalar sums use the canonical reduction.
+ *               params = [N, X row-major (N*p), y (N)];  eta_n and (X' r)_j are sequential fused
+ *               multiply-adds over j resp. n, the two scalar sums use the canonical reduction.
  */
 #ifndef DHMC_MODELS_H
 #define DHMC_MODELS_H
@@ -60,6 +60,8 @@ DHMC_HD double dhmc_funnel_grad(int i, double x, double v, double ev, double S,
 }
 
 /* --- LOGISTIC */
+/* one multiply-accumulate of η_n = Σ_j X_nj β_j and of (Xᵀr)_j = Σ_n X_nj r_n: fused, as a BLAS would */
+DHMC_HD double dhmc_logit_mac(double acc, double x, double b) { return dm_fma(x, b, acc); }
 DHMC_HD double dhmc_logit_sigma(double eta) { return 1.0 / (1.0 + dm_exp(-eta)); }
 /* y·η − log(1+e^η) with log(1+e^η) = max(η,0) + log(1+e^{−|η|}): one table-driven softplus (absolute
  * accuracy, no division) instead of log1p(exp(η)) */

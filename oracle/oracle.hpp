@@ -125,7 +125,7 @@ struct Model {
         vec r(N), ll(N);
         for (int n = 0; n < N; ++n) {
           double eta = 0.0;
-          for (int j = 0; j < D; ++j) eta = eta + X[(size_t)n * D + j] * q[j];
+          for (int j = 0; j < D; ++j) eta = dhmc_logit_mac(eta, X[(size_t)n * D + j], q[j]);
           ll[n] = dhmc_logit_ll(y[n], eta);
           r[n] = dhmc_logit_resid(y[n], eta);
         }
@@ -133,7 +133,7 @@ struct Model {
         double sb = canon_sum(T, D, [&](int i) { return q[i] * q[i]; });
         for (int j = 0; j < D; ++j) {
           double acc = 0.0;
-          for (int n = 0; n < N; ++n) acc = acc + X[(size_t)n * D + j] * r[n];
+          for (int n = 0; n < N; ++n) acc = dhmc_logit_mac(acc, X[(size_t)n * D + j], r[n]);
           g[j] = dhmc_logit_grad(acc, q[j]);
         }
         return dhmc_logit_lq(sll, sb);

@@ -114,14 +114,14 @@ struct HostBackend {
         vec r(N), ll(N);
         for (int n = 0; n < N; ++n) {
           double eta = 0.0;
-          for (int j = 0; j < D; ++j) eta = eta + X[(size_t)n * D + j] * q[j];
+          for (int j = 0; j < D; ++j) eta = dhmc_logit_mac(eta, X[(size_t)n * D + j], q[j]);
           ll[n] = dhmc_logit_ll(y[n], eta); r[n] = dhmc_logit_resid(y[n], eta);
         }
         double sll = canon_sum(T, N, [&](int n) { return ll[n]; });
         double sb = canon_sum(T, D, [&](int i) { return q[i] * q[i]; });
         for (int j = 0; j < D; ++j) {
           double acc = 0.0;
-          for (int n = 0; n < N; ++n) acc = acc + X[(size_t)n * D + j] * r[n];
+          for (int n = 0; n < N; ++n) acc = dhmc_logit_mac(acc, X[(size_t)n * D + j], r[n]);
           g[j] = dhmc_logit_grad(acc, q[j]);
         }
         l = dhmc_logit_lq(sll, sb);
