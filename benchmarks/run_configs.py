@@ -133,7 +133,103 @@ def c5(scale):
 
 def c4(scale):
     """Logistic regression N=10 000, p=256, dense (Symmetric) metric — in-framework version:
-    every chain group evaluates its own X·β / Xᵀr from the L2-resident design matrix."""
+    packed chain groups, 8 chains per CTA evaluate X·β / Xᵀr together."""
+    pkg = entry.load_package()
+    K, N = max(64, int(32768 * scale)), 8
+    ℓ, beta = pkg.LogisticRegression.synthetic(N=10000, p=256, seed=7)
+    eng = pkg.Engine(ℓ, chains=K, seed=2026)
+    eng.random_position()
+    t0 = time.perf_counter()
+    eng.find_initial_stepsize()
+    stages = pkg.default_warmup_stages(M=pkg.Symmetric, init_steps=75, middle_steps=25, doubling_stages=3,
+                                       terminating_steps=50)
+    rows, steps, ms = [], 0, 0.0
+    for st in stages[1:]:
+        _, dt, s, m = _timed(eng, lambda: eng.warmup_stage(st))
+        rows.append({"N": st.N, "M": st.M, "leapfrog_steps": s, "kernel_ms": m, "dense_kernels": eng.metric_is_dense()})
+        steps += s; ms += m
+    warm_wall = time.perf_counter() - t0
+    out, dt, s, m = _timed(eng, lambda: eng.mcmc(N))
+    post = out["posterior_matrix"]
+    flops = 4.0 * 10000 * 256 + 2 * 2 * 256 * 256          # likelihood + two dense mat-vecs per leapfrog
+    line = {"config": "C4", "dim": 256, "n_obs": 10000, "chains": K, "threads_per_chain": eng.layout()[0],
+            "warmup": {"transitions": sum(r["N"] for r in rows), "leapfrog_steps": steps, "kernel_ms": ms,
+                       "wall_s": warm_wall, "leapfrog_steps_per_sec": steps / (ms * 1e-3), "stages": rows},
+            "sampling": {"draws": N, "leapfrog_steps": s, "kernel_ms": m,
+                         "leapfrog_steps_per_sec": s / (m * 1e-3),
+                         "fp64_tflops": s * flops / (m * 1e-3) / 1e12,
+                         "mean_depth": float(out["tree_statistics"]["depth"].mean())},
+            "posterior_mean_vs_truth_corr": float(np.corrcoef(post.mean((0, 1)), beta)[0, 1]),
+            "mean_eps": float(eng.get_state(("eps",))["eps"].mean()),
+            "note": "packed chain groups: 8 chains per CTA share every pass over X (cp.async ring); per-chain dense "
+                    "metric (GEMV-shaped); the lock-step GEMM/DMMA formulation is round-2 work"}
+    eng.close()
+    return line
+
+
+def c5(scale):
+    import torch
+    import torch.distributed as dist
+    pkg = entry.load_package()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D, Kg, N = 1000, int(65536 * scale), 4
+    sigma2 = 10.0 ** (4 * np.arange(D) / (D - 1))
+    off, K = pkg.parallel.shard(world * Kg, world, rank)
+    eng = pkg.Engine(pkg.DiagNormal(np.zeros(D), sigma2), chains=K, seed=2026, device=local, chain_offset=off)
+    eng.random_position()
+    t0 = time.perf_counter()
+    eng.find_initial_stepsize()
+    stage_rows, steps, ms = [], 0, eng.last_kernel_ms()
+    for st in pkg.default_warmup_stages()[1:]:
+        _, dt, s, m = _timed(eng, lambda: eng.warmup_stage(st))
+        stage_rows.append({"N": st.N, "M": st.M, "leapfrog_steps": s, "kernel_ms": m})
+        steps += s; ms += m
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    warm_wall = time.perf_counter() - t0
+    draws = torch.empty((K, N, D), dtype=torch.float64, device=f"cuda:{local}")
+    stats = torch.empty((K, N, 56), dtype=torch.uint8, device=f"cuda:{local}")
+    eng.mcmc_dev(N, draws.data_ptr(), stats.data_ptr(), 0)
+    s_samp, m_samp = eng.last_total_steps(), eng.last_kernel_ms()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    last = draws[:, N - 1, :].contiguous()
+    torch.cuda.synchronize()
+    e0.record()
+    full = pkg.parallel.gather_draws(last, world * Kg) if world > 1 else last
+    e1.record()
+    torch.cuda.synchronize()
+    st = eng.get_state(("minv", "eps"))
+    ratio = st["minv"] / sigma2
+    sd = (full.std(0).cpu().numpy() / np.sqrt(sigma2))
+    tot = torch.tensor([float(steps), float(s_samp)], dtype=torch.float64, device=f"cuda:{local}")
+    mx = torch.tensor([ms, m_samp, warm_wall], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tot); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    line = {"config": "C5", "n_gpus": world, "dim": D, "chains_total": world * Kg, "kappa": 1e4,
+            "warmup": {"transitions": 900, "leapfrog_steps": tot[0].item(), "kernel_ms_max": mx[0].item(),
+                       "wall_s_max": mx[2].item(), "leapfrog_steps_per_sec": tot[0].item() / (mx[0].item() * 1e-3),
+                       "stages_rank0": stage_rows},
+            "sampling": {"draws": N, "leapfrog_steps": tot[1].item(),
+                         "leapfrog_steps_per_sec": tot[1].item() / (mx[1].item() * 1e-3)},
+            "allgather": {"ms": e0.elapsed_time(e1), "bytes_per_rank": K * D * 8},
+            "adapted_metric_over_truth": {"median": float(np.median(ratio)), "p05": float(np.quantile(ratio, 0.05)),
+                                          "p95": float(np.quantile(ratio, 0.95))},
+            "mean_eps": float(st["eps"].mean()),
+            "final_draw_sd_over_sigma": {"min": float(sd.min()), "max": float(sd.max())}}
+    eng.close()
+    return line if rank == 0 else None
+
+
+def c4(scale):
+    """Logistic regression N=10 000, p=256, dense (Symmetric) metric — in-framework version:
+    packed chain groups, 8 chains per CTA evaluate X·β / Xᵀr together."""
     pkg = entry.load_package()
     K, N = max(64, int(32768 * scale)), 8
     ℓ, beta = pkg.LogisticRegression.synthetic(N=10000, p=256, seed=7)
