@@ -93,15 +93,18 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // lXt has leading dimension ldn (even, >= N); lres is [N][G] (row-major), lll is [G][N].
-template <int G>
-__device__ __noinline__ double coop_core(bool active, int lane, int grp, int ctid, int D, int lN, int ldn,
+// A chain group is W warps (T = 32·W threads: tid within the group, grp = group within the CTA).
+template <int G, int W>
+__device__ __noinline__ double coop_core(bool active, int tid, int grp, int ctid, int D, int lN, int ldn,
                                          const double* __restrict__ lX, const double* __restrict__ lXt,
                                          const double* __restrict__ ly, double* lres, double* lll,
                                          int* cb_flags, const double* cb_beta, double* cb_grad, double* cb_stage) {
-  constexpr int NT = 32 * G;
+  constexpr int T = 32 * W;
+  constexpr int NT = T * G;                // threads of the CTA
+  constexpr int NC = 32 * G;               // columns handled per pass of phase 2 (D <= NC)
   constexpr int S = kCoopStages;
   constexpr int STG = coop_stage_doubles(G);
-  if (lane == 0) cb_flags[grp] = active ? 1 : 0;
+  if (tid == 0) cb_flags[grp] = active ? 1 : 0;
   __syncthreads();
   unsigned amask = 0;
 #pragma unroll
@@ -111,9 +114,10 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
 
   // ---------------- phase 1: tiles of J rows of Xᵀ × RB observations
   {
-    constexpr int RB = 4 * NT;             // observations per pass
+    constexpr int U = 4 / W;               // observations per thread and pass
+    constexpr int RB = U * NT;             // observations per pass
     constexpr int J = kCoopTile / RB;      // coefficients per tile
-    static_assert(J >= 1 && J * RB == kCoopTile, "tile shape");
+    static_assert(U >= 1 && J >= 1 && J * RB == kCoopTile, "tile shape");
     const int nchunks = (D + J - 1) / J;
     const int npass = (lN + RB - 1) / RB;
     const int ntiles = npass * nchunks;
@@ -137,7 +141,7 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
     };
     issue(0);
     issue(1);
-    double eta[4][G];
+    double eta[U][G];
     for (int t = 0; t < ntiles; ++t) {
       cp_async_wait<1>();                  // this thread's pieces of tile t have landed
       __syncthreads();                     // everyone's have, and everyone is done with tile t-1
@@ -145,7 +149,7 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
       const int ps = t / nchunks, ch = t - ps * nchunks;
       if (ch == 0) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
 #pragma unroll
           for (int gg = 0; gg < G; ++gg) eta[u][gg] = 0.0;
       }
@@ -154,21 +158,21 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
       for (int jj = 0; jj < J; ++jj) {
         const int j = ch * J + jj;
         if (j < D) {
-          double x[4];
+          double x[U];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) x[u] = src[jj * RB + u * NT];
+          for (int u = 0; u < U; ++u) x[u] = src[jj * RB + u * NT];
           const double* bj = cb_beta + (size_t)j * G;
 #pragma unroll
           for (int gg = 0; gg < G; ++gg) {
             const double bv = bj[gg];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) eta[u][gg] = dhmc_logit_mac(eta[u][gg], x[u], bv);
+            for (int u = 0; u < U; ++u) eta[u][gg] = dhmc_logit_mac(eta[u][gg], x[u], bv);
           }
         }
       }
       if (ch == nchunks - 1) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int n = ps * RB + ctid + u * NT;
           if (n < lN) {
             const double yn = __ldg(ly + n);
@@ -186,14 +190,18 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
     cp_async_wait<0>();
     __syncthreads();
   }
-  // ---------------- phase 1b
+  // ---------------- phase 1b: thread v of the group sums n = v, v+T, … (the canonical partials)
   double sll = 0.0;
   if (active) {
     const double* t = lll + (size_t)grp * lN;
-    for (int n = lane; n < lN; n += 32) sll = sll + t[n];
+    for (int n = tid; n < lN; n += T) sll = sll + t[n];
   }
-  // ---------------- phase 2: tiles of R rows of X with their residuals [R][G]
+  // ---------------- phase 2: tiles of R rows of X with their residuals [R][G]; thread = (column j,
+  // set of GH chains): with two warps per chain the two halves of the CTA take half the chains each
   {
+    constexpr int GH = G / W;
+    static_assert(GH * W == G, "chains split evenly over the column sets");
+    const int col = ctid % NC, g0 = (ctid / NC) * GH;
     const int R = coop_rows(D);
     const int ntiles = (lN + R - 1) / R;
     auto issue = [&](int t) {
@@ -212,29 +220,29 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
     };
     issue(0);
     issue(1);
-    double acc[G];
+    double acc[GH];
 #pragma unroll
-    for (int gg = 0; gg < G; ++gg) acc[gg] = 0.0;
+    for (int gg = 0; gg < GH; ++gg) acc[gg] = 0.0;
     for (int t = 0; t < ntiles; ++t) {
       cp_async_wait<1>();
       __syncthreads();
       issue(t + 2);
       const int n0 = t * R;
       const int rows = lN - n0 < R ? lN - n0 : R;
-      if (ctid < D) {
+      if (col < D) {
         // rows in increasing n; operands are fetched from shared memory one row ahead of their use
-        const double* xr = cb_stage + (size_t)(t % S) * STG + ctid;
-        const double* rr = cb_stage + (size_t)(t % S) * STG + kCoopTile;
-        double r0[G], r1[G];
+        const double* xr = cb_stage + (size_t)(t % S) * STG + col;
+        const double* rr = cb_stage + (size_t)(t % S) * STG + kCoopTile + g0;
+        double r0[GH], r1[GH];
         double x0 = 0.0, x1 = 0.0;
 #define DHMC_COOP_LD(r, x, nn)                                   \
         if ((nn) < rows) {                                       \
           x = xr[(size_t)(nn) * D];                              \
-          _Pragma("unroll") for (int gg = 0; gg < G; ++gg) r[gg] = rr[(nn) * G + gg]; \
+          _Pragma("unroll") for (int gg = 0; gg < GH; ++gg) r[gg] = rr[(nn) * G + gg]; \
         }
 #define DHMC_COOP_ACC(r, x, nn)                                  \
         if ((nn) < rows) {                                       \
-          _Pragma("unroll") for (int gg = 0; gg < G; ++gg) acc[gg] = dhmc_logit_mac(acc[gg], x, r[gg]); \
+          _Pragma("unroll") for (int gg = 0; gg < GH; ++gg) acc[gg] = dhmc_logit_mac(acc[gg], x, r[gg]); \
         }
         DHMC_COOP_LD(r0, x0, 0)
         for (int nn = 0; nn < rows; nn += 2) {
@@ -249,9 +257,9 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
     }
     cp_async_wait<0>();
     __syncthreads();                       // cb_grad lives in stage 0 of the ring: everyone is done with the tiles
-    if (ctid < D) {
+    if (col < D) {
 #pragma unroll
-      for (int gg = 0; gg < G; ++gg) cb_grad[(size_t)gg * NT + ctid] = acc[gg];
+      for (int gg = 0; gg < GH; ++gg) cb_grad[(size_t)(g0 + gg) * NC + col] = acc[gg];
     }
     __syncthreads();
   }
@@ -262,15 +270,15 @@ __device__ __noinline__ double coop_core(bool active, int lane, int grp, int cti
 // streamed from HBM, kept in registers next to p and stored with it — a momentum
 // slot holds the pair (p, p♯), so the state machine's bookkeeping is unchanged.
 //
-// PACK > 1 ("packed chain groups", logistic family, one warp per chain): a CTA holds PACK
-// independent chains, one per warp.  Everything except the likelihood is private to the
-// warp; the likelihood is evaluated by the whole CTA for all PACK chains at once
+// PACK > 1 ("packed chain groups", logistic family, one or two warps per chain): a CTA holds PACK
+// independent chains.  Everything except the likelihood is private to the chain's warps (which
+// meet at a named barrier of their own); the likelihood is evaluated by the whole CTA for all PACK chains at once
 // (coop_round), so every element of X is read once per PACK gradients instead of once per
 // gradient — the family is bound by L2 traffic on X otherwise.  The per-chain arithmetic
 // and its order are unchanged (η_n sequential in j, (Xᵀr)_j sequential in n, Σ ll lane-strided).
 template <int EPL, int FAM, int WARPS, bool DENSE = false, int PACK = 1>
 struct DeviceBackend {
-  static_assert(PACK == 1 || (WARPS == 1 && FAM == DHMC_FAMILY_LOGISTIC), "packed groups: one warp per chain, logistic family");
+  static_assert(PACK == 1 || (WARPS <= 2 && FAM == DHMC_FAMILY_LOGISTIC), "packed groups: one or two warps per chain, logistic family");
   static constexpr int G = PACK;
   int grp, ctid;                            // warp (= chain group) within the CTA, thread within the CTA
   int* cb_flags; double* cb_beta; double* cb_grad; double* cb_stage;   // CTA-shared exchange area
@@ -307,7 +315,7 @@ struct DeviceBackend {
   __device__ __forceinline__ void build_slot_table() {
     for (int s = tid; s < 64; s += T)
       slot_tab[s] = s < n_sm ? sm_slots + (size_t)s * stride : gl_slots + (size_t)(s - n_sm) * stride;
-    if (W > 1) __syncthreads(); else __syncwarp();
+    group_sync();
   }
   __device__ __forceinline__ double* slot(int s) const { return slot_tab[s] + tid; }
 
@@ -351,7 +359,7 @@ struct DeviceBackend {
     double* buf = red + red_buf * (kMaxWarps * kRedWidth);
     red_buf ^= 1;
     buf[warp * kRedWidth + idx] = w[0];
-    if (W > 1) __syncthreads(); else __syncwarp();
+    group_sync();
 #pragma unroll
     for (int n = 0; n < N; ++n) {
       const double* b = buf + n;
@@ -452,8 +460,11 @@ struct DeviceBackend {
   }
   __device__ __forceinline__ Entry get_entry(int j) const { return ctl[j]; }
 
+  // all threads of the chain: the CTA barrier, or — packed groups — named barrier 1 + grp
   __device__ __forceinline__ void group_sync() const {
-    if (W > 1) __syncthreads(); else __syncwarp();
+    if constexpr (W == 1) __syncwarp();
+    else if constexpr (PACK > 1) asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "n"(32 * WARPS) : "memory");
+    else __syncthreads();
   }
   // y = M⁻¹ x for this chain (Symmetric M⁻¹ * v, hamiltonian.jl:110): x is staged in shared
   // memory, every thread accumulates its own rows over j = 0..D-1 in increasing j (the
@@ -595,7 +606,7 @@ struct DeviceBackend {
         if (i < D) cb_beta[(size_t)i * G + grp] = q[e];
       }
     }
-    const double sll = coop_core<G>(active, lane, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
+    const double sll = coop_core<G, W>(active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
                                     cb_flags, cb_beta, cb_grad, cb_stage);
     if (sll > 0.0) return false;         // sentinel: ll terms are <= 0, so are their sums
     sum_ll = sll;

@@ -94,7 +94,7 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G>&
   b.lll = nullptr; b.cb_flags = nullptr; b.cb_beta = b.cb_grad = b.cb_stage = nullptr;
   size_t group = blockIdx.x;
   if constexpr (G > 1) {
-    b.grp = threadIdx.x >> 5; b.tid = b.lane; b.warp = 0;
+    b.grp = threadIdx.x / (32 * W); b.tid = threadIdx.x % (32 * W); b.warp = b.tid >> 5;
     group = (size_t)blockIdx.x * G + b.grp;
     const size_t per = group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles);
     unsigned char* shared = smem + per * G;
@@ -103,8 +103,8 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G>&
     b.cb_stage = b.cb_beta + (size_t)32 * G * G;
     b.cb_grad = b.cb_stage;
     static_assert(coop_stage_doubles(G) >= 32 * G * G, "Xᵀr fits in one stage");
-    for (int i = threadIdx.x; i < 32 * G * G; i += 32 * G) b.cb_beta[i] = 0.0;
-    for (int i = threadIdx.x; i < kCoopStages * coop_stage_doubles(G); i += 32 * G) b.cb_stage[i] = 0.0;
+    for (int i = threadIdx.x; i < 32 * G * G; i += 32 * W * G) b.cb_beta[i] = 0.0;
+    for (int i = threadIdx.x; i < kCoopStages * coop_stage_doubles(G); i += 32 * W * G) b.cb_stage[i] = 0.0;
     b.lr = a.lr + (size_t)blockIdx.x * 2 * G * a.lN;       // residuals [N][G]
     b.lll = b.lr + (size_t)G * a.lN;                       // ll terms   [G][N]
     smem += per * b.grp;
@@ -125,11 +125,19 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G>&
   b.mparams = a.mparams;
 }
 
-// packed groups: every warp draws its own chains
-__device__ __forceinline__ int next_chain_warp(unsigned* counter, int begin, int lane) {
-  int c = 0;
-  if (lane == 0) c = begin + (int)atomicAdd(counter, 1u);
-  return __shfl_sync(0xffffffffu, c, 0);
+// packed groups: every chain group draws its own chains
+template <class B>
+__device__ __forceinline__ int next_chain_group(B& b, unsigned* counter, int* s_misc, int begin) {
+  if constexpr (B::W == 1) {
+    int c = 0;
+    if (b.lane == 0) c = begin + (int)atomicAdd(counter, 1u);
+    return __shfl_sync(0xffffffffu, c, 0);
+  } else {
+    b.group_sync();
+    if (b.tid == 0) s_misc[0] = begin + (int)atomicAdd(counter, 1u);
+    b.group_sync();
+    return s_misc[0];
+  }
 }
 __device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc, int begin) {
   __syncthreads();
@@ -195,10 +203,11 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nu
   extern __shared__ __align__(16) unsigned char smem[];
   DeviceBackend<EPL, FAM, W, DN, G> b;
   setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
+  int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles) : 0) +
+                                       smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
   for (;;) {
     int c;
-    if constexpr (G > 1) c = next_chain_warp(a.counter, a.chain_begin, b.lane);
+    if constexpr (G > 1) c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
     else c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
@@ -227,10 +236,11 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_se
   extern __shared__ __align__(16) unsigned char smem[];
   DeviceBackend<EPL, FAM, W, DN, G> b;
   setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
+  int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles) : 0) +
+                                       smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
   for (;;) {
     int c;
-    if constexpr (G > 1) c = next_chain_warp(a.counter, a.chain_begin, b.lane);
+    if constexpr (G > 1) c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
     else c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
@@ -536,12 +546,14 @@ struct dhmc_handle;
 // dense (Symmetric metric) kernels are instantiated for the layouts of D <= 512
 constexpr bool dense_layout(int W, int EPL) { return W == 1 || (W == 2) || (W == 4 && EPL == 4); }
 constexpr int kPack = 8;            // packed chain groups: chains per CTA (logistic family, dim <= 256)
+// the layouts choose_layout picks for dim <= 256: one warp per chain up to 128, two above
+constexpr bool packed_layout(int W, int EPL) { return (W == 1 && EPL <= 4) || (W == 2 && EPL == 4); }
 template <int EPL, int FAM, int W>
 static const void* kernel_ptr(KernelId k, bool dense, int G = 1) {
-  if constexpr (FAM == DHMC_FAMILY_LOGISTIC && W == 1) {
+  if constexpr (FAM == DHMC_FAMILY_LOGISTIC && packed_layout(W, EPL)) {
     if (G > 1) {
-      if (k == K_NUTS) return dense ? (const void*)k_nuts<EPL, FAM, 1, true, kPack> : (const void*)k_nuts<EPL, FAM, 1, false, kPack>;
-      if (k == K_SEARCH) return dense ? (const void*)k_search<EPL, FAM, 1, true, kPack> : (const void*)k_search<EPL, FAM, 1, false, kPack>;
+      if (k == K_NUTS) return dense ? (const void*)k_nuts<EPL, FAM, W, true, kPack> : (const void*)k_nuts<EPL, FAM, W, false, kPack>;
+      if (k == K_SEARCH) return dense ? (const void*)k_search<EPL, FAM, W, true, kPack> : (const void*)k_search<EPL, FAM, W, false, kPack>;
     }
   }
   if (dense) {
@@ -763,16 +775,13 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   const int rt = cfg->threads_per_chain;
   if (rt != 0 && !(rt == 32 || rt == 64 || rt == 128 || rt == 256)) { g_create_err = "threads_per_chain in {0,32,64,128,256}"; return DHMC_EARG; }
   choose_layout(cfg->dim, rt, &T, &EPL);
-  // logistic regression, dim <= 256: one warp per chain, kPack chains per CTA sharing every
-  // pass over X (packed chain groups); an explicit threads_per_chain keeps one chain per CTA
+  // logistic regression, dim <= 256: kPack chains per CTA (one warp per chain up to dim 128, two
+  // above) sharing every pass over X (packed chain groups); an explicit threads_per_chain keeps
+  // one chain per CTA
   int pack = 1;
   if (cfg->family == DHMC_FAMILY_LOGISTIC && rt == 0 && cfg->dim <= 32 * kPack) {
     const char* ev = std::getenv("DHMC_PACK");
-    if (!(ev && std::atoi(ev) == 0)) {
-      pack = kPack; T = 32;
-      const int64_t e = (cfg->dim + 31) / 32;
-      EPL = e <= 1 ? 1 : e <= 2 ? 2 : e <= 4 ? 4 : 8;
-    }
+    if (!(ev && std::atoi(ev) == 0) && packed_layout(T / 32, EPL)) pack = kPack;
   }
   if (T == 0 || EPL == 0) { g_create_err = "dim too large for this build (dim <= 8 * threads_per_chain <= 2048)"; return DHMC_EARG; }
   int ndev = 0;

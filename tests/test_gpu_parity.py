@@ -419,16 +419,19 @@ def test_logistic_dense_warmup_matches_oracle(pkg, po):
 @pytest.mark.parametrize("N,p,K", [(300, 20, 21), (1100, 130, 9)])
 def test_logistic_packed_groups_equal_one_chain_per_cta(pkg, N, p, K, M):
     """Packed chain groups (8 chains per CTA sharing every pass over X, the default for
-    dim <= 256) against one chain per CTA with the same 32 threads per chain: the per-chain
+    dim <= 256) against one chain per CTA with the same threads per chain (32 resp. 64): the per-chain
     arithmetic and its order are the same, so everything is bit-identical — also for a ragged
     last CTA and for warps that run out of chains early and only attend the likelihood rounds."""
     ℓ, _ = pkg.LogisticRegression.synthetic(N=N, p=p, seed=N + p)
     stages = pkg.default_warmup_stages(M=getattr(pkg, M), init_steps=20, middle_steps=20, doubling_stages=1,
                                        terminating_steps=20)
     out = []
-    for opts in (None, dict(threads_per_chain=32)):
-        r = pkg.mcmc_keep_warmup(77, ℓ, 12, chains=K, warmup_stages=stages, engine_opts=opts)
-        assert r["engine"].layout()[0] == 32
+    T = None
+    for packed in (True, False):      # an explicit threads_per_chain selects one chain per CTA
+        r = pkg.mcmc_keep_warmup(77, ℓ, 12, chains=K, warmup_stages=stages,
+                                 engine_opts=None if packed else dict(threads_per_chain=T))
+        T = r["engine"].layout()[0] if packed else T
+        assert r["engine"].layout()[0] == T
         out.append(r)
     for k in range(K):
         a, b = out[0]["inference"][k], out[1]["inference"][k]
