@@ -61,7 +61,8 @@ typedef struct {
   int64_t chain_offset;      /* global id of local chain 0 (RNG key), §8e */
   uint64_t seed;             /* RNG seed (stands in for the rng argument) */
   int32_t max_depth;         /* NUTS.max_depth, 0 < . <= 12 in this build */
-  int32_t threads_per_chain; /* 0 = auto; 32..256, power of two */
+  int32_t threads_per_chain; /* 0 = auto; 32..256, power of two.  LOGISTIC, dim <= 256: auto also packs 8 chains
+                              * per CTA (shared passes over X, same results); an explicit value keeps one chain per CTA */
   double min_delta;          /* NUTS.min_Δ < 0 */
   int32_t ctas_per_sm;       /* 0 = auto */
   int32_t reserved;
@@ -91,7 +92,7 @@ const char* dhmc_last_error(dhmc_handle* h);
 int dhmc_get_layout(dhmc_handle* h, int32_t* threads_per_chain, int32_t* elems_per_thread);
 
 /* ---- problem: replaces the ℓ argument (LogDensityProblems object) ------ */
-/* params: DIAG_NORMAL [mu(D), prec(D)]; STD_NORMAL / FUNNEL: n == 0. */
+/* params: DIAG_NORMAL [mu(D), prec(D)]; LOGISTIC [N, X row-major (N*D), y (N)]; STD_NORMAL / FUNNEL: n == 0. */
 int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n);
 
 /* ---- state: initialization = (q, κ, ϵ), mcmc.jl:111-132 ---------------- */
