@@ -1,6 +1,7 @@
 // device_backend.cuh — sm_100a vector backend of the NUTS state machine.
 //
-// One chain = one chain group of T = 32·W threads (= one CTA).  Element i of
+// One chain = one chain group of T = 32·W threads (= one CTA; packed chain groups of the
+// logistic family put 8 groups in a CTA, see coop_core).  Element i of
 // every D-vector belongs to thread (i mod T), register slot e = i div T, so a
 // vector is EPL doubles per thread, HBM accesses of a chain row are fully
 // coalesced, shared-memory slot accesses are conflict-free, and — because the
@@ -298,7 +299,7 @@ struct DeviceBackend {
   // dense metric: this chain's M⁻¹ (symmetric, [D][D]), Wᵀ (column-major lower W), co-moment
   // accumulator (transposed lower) and the shared-memory staging vector
   const double* Mrow; const double* Wt; double* covt; double* xs;
-  // logistic regression: X [N][D], Xᵀ [D][N], y [N], per-CTA residual scratch [N]
+  // logistic regression: X [N][D], Xᵀ [D][lLd], y [N], residual scratch (per CTA [N]; packed groups [N][G])
   const double* lX; const double* lXt; const double* ly; double* lr; int lN; int lLd;   // lLd: leading dimension of Xᵀ
   // memory
   double* red; int red_buf;

@@ -8,6 +8,9 @@
 //   k_leapfrog  leapfrog (streaming, HBM-bound)               hamiltonian.jl:273-282
 //   k_eval      evaluate_ℓ(strict) / random_position          hamiltonian.jl:202-217, mcmc.jl:108
 //   k_phase     logdensity(H, z)                              hamiltonian.jl:251-256
+// Logistic family, dim <= 256: k_nuts / k_search run as "packed chain groups" — 8 chains per
+// CTA, each with its own warps and state machine, the likelihood evaluated by the whole CTA
+// (device_backend.cuh: coop_core).
 //
 // There is NO CPU fallback: without a CUDA device dhmc_create fails with
 // DHMC_ECUDA and nothing else can be called.
@@ -60,7 +63,7 @@ struct KArgs {
   double *minv_dense, *wt, *covt;   // Symmetric metric: M⁻¹, Wᵀ, co-moments, each [B][D][D]
   int xs_doubles;               // shared-memory staging vector (0 unless the dense arrays exist)
   const double *lX, *lXt, *ly;  // logistic regression data
-  double* lr;                   // per-CTA residual scratch [grid][lN]
+  double* lr;                   // logistic scratch: [grid][lN] residuals, or per CTA of packed groups [lN][G] residuals + [G][lN] ll terms
   int lN, lLd;                  // observations, leading dimension of Xᵀ (even)
 };
 
