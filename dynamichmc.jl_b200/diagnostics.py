@@ -45,3 +45,80 @@ def summarize_tree_statistics(tree_statistics):
     return TreeStatisticsSummary(int(a.size), float(a.mean()),
                                  [float(v) for v in np.quantile(a, ACCEPTANCE_QUANTILES)],
                                  count_terminations(tree_statistics), count_depths(tree_statistics))
+
+
+# ------------------------------------------------------------------ trajectory diagnostics
+# These drive the device path itself (dhmc_leapfrog / dhmc_phase_logdensity); there is no host
+# re-implementation of the integrator here.
+def _rand_ps(κ, D, N, seed):
+    """rand_p(rng, κ) hamiltonian.jl:124 for the default `ps` (host RNG: the reference draws
+    them from the caller's rng, so there is nothing to be bit-compatible with)."""
+    z = np.random.default_rng(seed).normal(size=(N, D))
+    if κ is None:
+        return z
+    minv = np.asarray(κ.minv, float)
+    if κ.dense:
+        W = np.linalg.cholesky(np.linalg.inv(minv))          # hamiltonian.jl:73
+        return z @ W.T
+    return z / np.sqrt(minv)
+
+
+def explore_log_acceptance_ratios(ℓ, q, log2ϵs, κ=None, N=20, ps=None, seed=0, device=0):
+    """diagnostics.jl:139-147.  From the position `q`, the uncapped log acceptance ratio
+    `logdensity(H, leapfrog(H, z, ϵ)) − logdensity(H, z)` (stepsize.jl:83-85) for every
+    ϵ = 2^log2ϵ and every momentum in `ps` (N random ones by default).  Returns the matrix
+    [len(log2ϵs), len(ps)]; every (ϵ, p) pair is one chain of a single device pass."""
+    from . import api
+    q = np.asarray(q, float)
+    D = q.size
+    ps = _rand_ps(κ, D, N, seed) if ps is None else np.asarray(ps, float).reshape(-1, D)
+    eps = 2.0 ** np.asarray(log2ϵs, float).reshape(-1)
+    E, P = eps.size, ps.shape[0]
+    eng = api.Engine(ℓ, chains=E * P, seed=seed, device=device)
+    try:
+        if κ is not None:
+            eng.set_kinetic_energy(κ)
+        eng.set_position(np.broadcast_to(q, (E * P, D)))
+        eng.set_momentum(np.tile(ps, (E, 1)))                # chain e·P + j = (ϵ_e, p_j)
+        eng.set_stepsize(np.repeat(eps, P))
+        h0 = eng.phase_logdensity()
+        eng.leapfrog(1, 1)
+        h1 = eng.phase_logdensity()
+    finally:
+        eng.close()
+    return (h1 - h0).reshape(E, P)
+
+
+def leapfrog_trajectory(ℓ, q, ϵ, positions, κ=None, p=None, seed=0, device=0):
+    """diagnostics.jl:200-216.  Leapfrog trajectory visiting `positions` (a range containing 0)
+    relative to `q` with stepsize ϵ, tracked in each direction up to the first non-finite log
+    density.  Returns a list of dicts (z = (q, p, ℓq), position, Δ) ordered by position, where
+    Δ is the log density + kinetic energy relative to position 0."""
+    from . import api
+    lo, hi = positions[0], positions[-1]
+    api._argcheck(lo <= 0 <= hi, "0 ∈ positions")
+    q = np.asarray(q, float)
+    D = q.size
+    p = _rand_ps(κ, D, 1, seed)[0] if p is None else np.asarray(p, float)
+    eng = api.Engine(ℓ, chains=1, seed=seed, device=device)
+    out = {}
+    try:
+        if κ is not None:
+            eng.set_kinetic_energy(κ)
+        eng.set_stepsize(float(ϵ))
+        for sgn, last in ((+1, hi), (-1, -lo)):
+            eng.set_position(q[None, :])
+            eng.set_momentum(p[None, :])
+            st = eng.get_state(("q", "p", "lq"))
+            π0 = eng.phase_logdensity()[0]
+            out[0] = dict(z=dict(q=st["q"][0], p=st["p"][0], lq=float(st["lq"][0])), position=0, Δ=0.0)
+            for i in range(1, last + 1):
+                if not np.isfinite(st["lq"][0]):            # iterate(::LeapfrogTrajectory), diagnostics.jl:176-186
+                    break
+                eng.leapfrog(1, sgn)
+                st = eng.get_state(("q", "p", "lq"))
+                out[sgn * i] = dict(z=dict(q=st["q"][0], p=st["p"][0], lq=float(st["lq"][0])),
+                                    position=sgn * i, Δ=float(eng.phase_logdensity()[0] - π0))
+    finally:
+        eng.close()
+    return [out[i] for i in sorted(out)]

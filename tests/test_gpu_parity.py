@@ -444,6 +444,43 @@ def test_logistic_packed_groups_equal_one_chain_per_cta(pkg, N, p, K, M):
         r["engine"].close()
 
 
+# --------------------------------------------------------------- trajectory diagnostics (diagnostics.jl:139-216)
+def test_trajectory_diagnostics_match_oracle(pkg, po):
+    D = 37
+    rng = np.random.default_rng(12)
+    mu, sigma2 = rng.normal(size=D), rng.uniform(0.3, 4, D)
+    ℓ = pkg.DiagNormal(mu, sigma2)
+    params = ℓ.params()                      # [μ, 1/σ²]
+    minv = rng.uniform(0.5, 2, D)
+    κ = pkg.GaussianKineticEnergy(minv)
+    q = rng.normal(size=D)
+    ps = rng.normal(size=(4, D))
+    log2eps = [-6, -3, -1, 0, 1]
+    A = pkg.diagnostics.explore_log_acceptance_ratios(ℓ, q, log2eps, κ=κ, ps=ps)
+    assert A.shape == (5, 4)
+    T = 32 if D <= 128 else 64
+    for i, l2 in enumerate(log2eps):
+        for j in range(4):
+            assert A[i, j] == po.local_log_acceptance_ratio(po.FAMILY_DIAG_NORMAL, q, ps[j], 2.0 ** l2, minv=minv,
+                                                            params=params, T=T)
+    assert pkg.diagnostics.explore_log_acceptance_ratios(ℓ, q, [-2.0], κ=κ, N=7, seed=3).shape == (1, 7)
+    traj = pkg.diagnostics.leapfrog_trajectory(ℓ, q, 0.11, range(-3, 5), κ=κ, p=ps[0])
+    assert [t["position"] for t in traj] == list(range(-3, 5)) and traj[3]["Δ"] == 0.0
+    lq0, _ = po.logdensity_and_gradient(po.FAMILY_DIAG_NORMAL, q, params, T)
+    π0 = po.phase_logdensity(minv, lq0, ps[0], T)
+    for t in traj:
+        i = t["position"]
+        if i == 0:
+            assert np.array_equal(t["z"]["q"], q) and t["z"]["lq"] == lq0
+            continue
+        qo, p_o, _, lqo = po.leapfrog(po.FAMILY_DIAG_NORMAL, q, ps[0], 0.11 if i > 0 else -0.11, minv=minv,
+                                     params=params, T=T, n_steps=abs(i))
+        assert np.array_equal(t["z"]["q"], qo) and np.array_equal(t["z"]["p"], p_o) and t["z"]["lq"] == lqo
+        assert t["Δ"] == po.phase_logdensity(minv, lqo, p_o, T) - π0
+    with pytest.raises(pkg.ArgumentError):
+        pkg.diagnostics.leapfrog_trajectory(ℓ, q, 0.1, range(1, 4), κ=κ)
+
+
 # --------------------------------------------------------------- full-size properties (BASELINE configs[1])
 def test_full_size_properties_c2(pkg):
     """65 536 chains × D=1000 (config C2): size-independent properties the domain offers —
