@@ -619,10 +619,7 @@ static int plan(dhmc_handle* h) {
   }
   if (reg_ctas < 1) { h->err = "kernel does not fit on an SM"; return DHMC_ECUDA; }
   const int ctas = h->cfg.ctas_per_sm > 0 ? std::min(h->cfg.ctas_per_sm, reg_ctas) : reg_ctas;
-  // optionally leave part of the unified SM memory to L1
-  size_t l1_reserve = 0;
-  if (const char* ev = std::getenv("DHMC_L1_RESERVE_KB")) l1_reserve = (size_t)std::atol(ev) * 1024;
-  size_t per_cta = (h->smem_sm - std::min(l1_reserve, h->smem_sm / 2)) / ctas - 1024;   // 1 KB system reservation per CTA
+  size_t per_cta = h->smem_sm / ctas - 1024;   // 1 KB system reservation per CTA
   if (per_cta > h->smem_cta_max) per_cta = h->smem_cta_max;
   long n_sm = per_cta > L0.total ? (long)((per_cta - L0.total) / (slot_bytes * (size_t)G)) : 0;
   const int pool = h->n_slots - kWelfordSlots;   // the two highest slots stay in global memory
