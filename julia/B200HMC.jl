@@ -68,12 +68,21 @@ abstract type DeviceLogDensity end
 struct StandardNormal <: DeviceLogDensity; D::Int; end
 struct DiagNormal <: DeviceLogDensity; μ::Vector{Float64}; σ²::Vector{Float64}; end
 struct Funnel <: DeviceLogDensity; D::Int; end
+"Logistic regression with a N(0, I) prior: X is N×p, y ∈ {0,1}ᴺ (include/dhmc_models.h, LOGISTIC)."
+struct LogisticRegression <: DeviceLogDensity; X::Matrix{Float64}; y::Vector{Float64}; end
 family(::StandardNormal) = Int32(0); family(::DiagNormal) = Int32(1); family(::Funnel) = Int32(2)
+family(::LogisticRegression) = Int32(3)
 params(::DeviceLogDensity) = Float64[]
 params(ℓ::DiagNormal) = vcat(ℓ.μ, 1 ./ ℓ.σ²)
+params(ℓ::LogisticRegression) = vcat(Float64(size(ℓ.X, 1)), vec(permutedims(ℓ.X)), ℓ.y)   # [N, X row-major, y]
 LogDensityProblems.capabilities(::Type{<:DeviceLogDensity}) = LogDensityProblems.LogDensityOrder{1}()
 LogDensityProblems.dimension(ℓ::Union{StandardNormal,Funnel}) = ℓ.D
 LogDensityProblems.dimension(ℓ::DiagNormal) = length(ℓ.μ)
+LogDensityProblems.dimension(ℓ::LogisticRegression) = size(ℓ.X, 2)
+function LogDensityProblems.logdensity_and_gradient(ℓ::LogisticRegression, β)
+    η = ℓ.X * β
+    sum(ℓ.y .* η .- log1p.(exp.(η))) - sum(abs2, β) / 2, ℓ.X' * (ℓ.y .- 1 ./ (1 .+ exp.(-η))) .- β
+end
 LogDensityProblems.logdensity_and_gradient(::StandardNormal, q) = (-sum(abs2, q) / 2, -q)
 function LogDensityProblems.logdensity_and_gradient(ℓ::DiagNormal, q)
     t = (q .- ℓ.μ) ./ ℓ.σ²
