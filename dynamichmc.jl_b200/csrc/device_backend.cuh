@@ -267,6 +267,188 @@ __device__ __noinline__ double coop_core(bool active, int tid, int grp, int ctid
   return sll;
 }
 
+// ---- EXPERIMENTAL (compiled, selected only with DHMC_COOP_MMA=1, not yet validated on hardware):
+// the same likelihood round on the FP64 tensor cores.  mma.sync.m8n8k4.f64 computes
+// fma(a3,b3, fma(a2,b2, fma(a1,b1, fma(a0,b0, c)))) (measured: profiles/r01_dmma_order_probe.txt),
+// i.e. the model's own sequential order, so the results are those of coop_core bit for bit.
+//   phase 1: D[8 obs × 8 chains] += A[8 obs × 4 coeff] · B[4 coeff × 8 chains]; A from the Xᵀ ring
+//            tile (4 rows of stride kMmaRS ≡ 4 mod 16 doubles: conflict-free LDS.64 fragments), B = β
+//            stored [chain][kMmaBS];
+//   phase 2: D[8 coeff × 8 chains] += A[8 coeff × 4 obs] · B[4 obs × 8 chains]; A from the X ring tile
+//            (row stride XS ≡ 4 mod 16), B = residuals stored [obs][kMmaRr].
+// k-padding (coefficients >= D in phase 1, observations >= N in phase 2) is zero-filled so that the
+// padded steps are fma(0, 0, acc) = acc.  Index formulas and strides: benchmarks/dmma_layout_check.py.
+// Requires G == 8, D even (16-byte aligned rows of X) and D <= 256.
+constexpr int kMmaRB = 1024;                 // observations per pass of phase 1
+constexpr int kMmaRS = kMmaRB + 4;           // row stride of the Xᵀ tile
+constexpr int kMmaBS = 260;                  // row stride of β [chain][·]  (>= 256, ≡ 4 mod 16)
+constexpr int kMmaRr = 12;                   // row stride of the residual tile [obs][8 + 4]
+constexpr int kMmaStage = 4 * kMmaRS + 64 * kMmaRr;   // doubles per ring stage (>= 4 rows of Xᵀ; X tile + residuals)
+__host__ __device__ inline int mma_xs(int D) { int x = D; while ((x & 15) != 4) ++x; return x; }
+__host__ __device__ inline int mma_rows(int D) {     // observations per phase-2 tile: multiple of 4, rows·XS <= 4·kMmaRS
+  int r = ((4 * kMmaRS) / mma_xs(D)) & ~3;
+  return r < 4 ? 4 : r > 64 ? 64 : r;
+}
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int G, int W>
+__device__ __noinline__ double coop_core_mma(bool active, int tid, int grp, int ctid, int D, int lN, int ldn,
+                                             const double* __restrict__ lX, const double* __restrict__ lXt,
+                                             const double* __restrict__ ly, double* lres, double* lll,
+                                             int* cb_flags, const double* cb_beta, double* cb_grad, double* cb_stage) {
+  static_assert(G == 8, "the n-dimension of the MMA is the chain");
+  constexpr int T = 32 * W;
+  constexpr int NT = T * G;
+  constexpr int NW = W * G;                // warps of the CTA
+  constexpr int NC = 32 * G;
+  constexpr int S = kCoopStages;
+  constexpr int STG = kMmaStage;
+  const int lane = ctid & 31, wq = ctid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index of this lane
+  if (tid == 0) cb_flags[grp] = active ? 1 : 0;
+  __syncthreads();
+  unsigned amask = 0;
+#pragma unroll
+  for (int gg = 0; gg < G; ++gg)
+    if (cb_flags[gg]) amask |= 1u << gg;
+  if (amask == 0) return 1.0;
+
+  // ---------------- phase 1
+  {
+    constexpr int RW = kMmaRB / NW;        // observations per warp and pass
+    constexpr int TW = RW / 8;             // 8-row tiles per warp
+    const int nchunks = (D + 3) / 4;
+    const int npass = (lN + kMmaRB - 1) / kMmaRB;
+    const int ntiles = npass * nchunks;
+    auto issue = [&](int t) {
+      if (t < ntiles) {
+        const int ps = t / nchunks, ch = t - ps * nchunks;
+        const int n0 = ps * kMmaRB;
+        const int cnt = ldn - n0 < kMmaRB ? ldn - n0 : kMmaRB;
+        const int cpr = cnt >> 1;
+        double* dst = cb_stage + (size_t)(t % S) * STG;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = ch * 4 + jj;
+          if (j < D) {
+            const double* sj = lXt + (size_t)j * ldn + n0;
+            for (int k = ctid; k < cpr; k += NT) cp_async16(dst + jj * kMmaRS + 2 * k, sj + 2 * k);
+          } else {
+            for (int k = ctid; k < kMmaRB; k += NT) dst[jj * kMmaRS + k] = 0.0;   // k-padding
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    double c[TW][2];
+    for (int t = 0; t < ntiles; ++t) {
+      cp_async_wait<1>();
+      __syncthreads();
+      issue(t + 2);
+      const int ps = t / nchunks, ch = t - ps * nchunks;
+      if (ch == 0) {
+#pragma unroll
+        for (int rt = 0; rt < TW; ++rt) { c[rt][0] = 0.0; c[rt][1] = 0.0; }
+      }
+      const double* src = cb_stage + (size_t)(t % S) * STG + fk * kMmaRS + wq * RW + fr;
+      const double b = cb_beta[(size_t)fr * kMmaBS + ch * 4 + fk];
+#pragma unroll
+      for (int rt = 0; rt < TW; ++rt) dmma_8x8x4(c[rt][0], c[rt][1], src[rt * 8], b);
+      if (ch == nchunks - 1) {
+#pragma unroll
+        for (int rt = 0; rt < TW; ++rt) {
+          const int n = ps * kMmaRB + wq * RW + rt * 8 + fr;
+          if (n < lN) {
+            const double yn = __ldg(ly + n);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int gg = 2 * fk + i;
+              if (amask & (1u << gg)) {
+                lll[(size_t)gg * lN + n] = dhmc_logit_ll(yn, c[rt][i]);
+                lres[(size_t)n * G + gg] = dhmc_logit_resid(yn, c[rt][i]);
+              }
+            }
+          }
+        }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+  }
+  // ---------------- phase 1b
+  double sll = 0.0;
+  if (active) {
+    const double* t = lll + (size_t)grp * lN;
+    for (int n = tid; n < lN; n += T) sll = sll + t[n];
+  }
+  // ---------------- phase 2
+  {
+    const int XS = mma_xs(D);
+    const int R = mma_rows(D);
+    const int ntiles = (lN + R - 1) / R;
+    const int hd = D >> 1;                  // 16-byte pieces per row of X (D even)
+    constexpr int JTW = (NC / 8 + NW - 1) / NW;   // 8-coefficient tiles per warp
+    auto issue = [&](int t) {
+      if (t < ntiles) {
+        const int n0 = t * R;
+        const int rows = lN - n0 < R ? lN - n0 : R;
+        const int rows4 = (rows + 3) & ~3;
+        double* dst = cb_stage + (size_t)(t % S) * STG;
+        for (int r = wq; r < rows4; r += NW) {
+          if (r < rows) {
+            const double* sx = lX + (size_t)(n0 + r) * D;
+            for (int k = lane; k < hd; k += 32) cp_async16(dst + (size_t)r * XS + 2 * k, sx + 2 * k);
+            if (lane < G / 2) cp_async16(dst + 4 * kMmaRS + r * kMmaRr + 2 * lane, lres + (size_t)(n0 + r) * G + 2 * lane);
+          } else {                          // k-padding of the last tile
+            for (int k = lane; k < XS; k += 32) dst[(size_t)r * XS + k] = 0.0;
+            if (lane < kMmaRr) dst[4 * kMmaRS + r * kMmaRr + lane] = 0.0;
+          }
+        }
+      }
+      cp_async_commit();
+    };
+    issue(0);
+    issue(1);
+    double c[JTW][2];
+#pragma unroll
+    for (int q = 0; q < JTW; ++q) { c[q][0] = 0.0; c[q][1] = 0.0; }
+    for (int t = 0; t < ntiles; ++t) {
+      cp_async_wait<1>();
+      __syncthreads();
+      issue(t + 2);
+      const int n0 = t * R;
+      const int rows = lN - n0 < R ? lN - n0 : R;
+      const double* xt = cb_stage + (size_t)(t % S) * STG;
+      const double* rt = xt + 4 * kMmaRS;
+      for (int nn = 0; nn < rows; nn += 4) {
+        const double b = rt[(nn + fk) * kMmaRr + fr];
+#pragma unroll
+        for (int q = 0; q < JTW; ++q) {
+          const int jt = wq + q * NW;
+          if (jt * 8 < D) dmma_8x8x4(c[q][0], c[q][1], xt[(size_t)(nn + fk) * XS + jt * 8 + fr], b);
+        }
+      }
+    }
+    cp_async_wait<0>();
+    __syncthreads();                       // cb_grad lives in stage 0 of the ring
+#pragma unroll
+    for (int q = 0; q < JTW; ++q) {
+      const int j = (wq + q * NW) * 8 + fr;
+      if (j < D) {
+        cb_grad[(size_t)(2 * fk) * NC + j] = c[q][0];
+        cb_grad[(size_t)(2 * fk + 1) * NC + j] = c[q][1];
+      }
+    }
+    __syncthreads();
+  }
+  return sll;
+}
+
 // DENSE = Symmetric M⁻¹ per chain (hamiltonian.jl:73): p♯ = M⁻¹p is a D×D mat-vec
 // streamed from HBM, kept in registers next to p and stored with it — a momentum
 // slot holds the pair (p, p♯), so the state machine's bookkeeping is unchanged.
@@ -277,8 +459,9 @@ __device__ __noinline__ double coop_core(bool active, int tid, int grp, int ctid
 // (coop_round), so every element of X is read once per PACK gradients instead of once per
 // gradient — the family is bound by L2 traffic on X otherwise.  The per-chain arithmetic
 // and its order are unchanged (η_n sequential in j, (Xᵀr)_j sequential in n, Σ ll lane-strided).
-template <int EPL, int FAM, int WARPS, bool DENSE = false, int PACK = 1>
+template <int EPL, int FAM, int WARPS, bool DENSE = false, int PACK = 1, bool MMA = false>
 struct DeviceBackend {
+  static constexpr bool kMma = MMA;      // experimental tensor-core likelihood (packed groups only)
   static_assert(PACK == 1 || (WARPS <= 2 && FAM == DHMC_FAMILY_LOGISTIC), "packed groups: one or two warps per chain, logistic family");
   static constexpr int G = PACK;
   int grp, ctid;                            // warp (= chain group) within the CTA, thread within the CTA
@@ -604,11 +787,19 @@ struct DeviceBackend {
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {
         const int i = tid + e * T;
-        if (i < D) cb_beta[(size_t)i * G + grp] = q[e];
+        if (i < D) {
+          if constexpr (MMA) cb_beta[(size_t)grp * kMmaBS + i] = q[e];      // [chain][coefficient]
+          else cb_beta[(size_t)i * G + grp] = q[e];                          // [coefficient][chain]
+        }
       }
     }
-    const double sll = coop_core<G, W>(active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
-                                    cb_flags, cb_beta, cb_grad, cb_stage);
+    double sll;
+    if constexpr (MMA)
+      sll = coop_core_mma<G, W>(active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
+                                cb_flags, cb_beta, cb_grad, cb_stage);
+    else
+      sll = coop_core<G, W>(active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
+                            cb_flags, cb_beta, cb_grad, cb_stage);
     if (sll > 0.0) return false;         // sentinel: ll terms are <= 0, so are their sums
     sum_ll = sll;
     if (active) {

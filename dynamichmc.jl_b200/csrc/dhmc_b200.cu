@@ -78,15 +78,19 @@ __host__ __device__ constexpr int min_ctas(int W, int EPL) {
 // packed chain groups (G chains per CTA, one per warp): shared-memory bytes of the CTA-wide
 // exchange area behind the G per-group blocks — flags, β [32G][G], cp.async ring (Xᵀr [G][32G] is
 // handed back in stage 0 of the ring, which is idle between two rounds)
-__host__ __device__ constexpr size_t coop_smem_bytes(int G) {
-  return 64 + sizeof(double) * ((size_t)32 * G * G + (size_t)kCoopStages * coop_stage_doubles(G));
+__host__ __device__ constexpr size_t coop_beta_doubles(int G, bool mma) { return mma ? (size_t)G * kMmaBS : (size_t)32 * G * G; }
+__host__ __device__ constexpr size_t coop_ring_doubles(int G, bool mma) {
+  return (size_t)kCoopStages * (mma ? kMmaStage : coop_stage_doubles(G));
+}
+__host__ __device__ constexpr size_t coop_smem_bytes(int G, bool mma = false) {
+  return 64 + sizeof(double) * (coop_beta_doubles(G, mma) + coop_ring_doubles(G, mma));
 }
 __host__ __device__ inline size_t group_smem_bytes(int W, int n_sm, size_t stride, size_t xs) {
   return (smem_layout(W, n_sm, stride, xs).total + 15) & ~(size_t)15;
 }
 
-template <int EPL, int FAM, int W, bool DN, int G>
-__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G>& b, const KArgs& a,
+template <int EPL, int FAM, int W, bool DN, int G, bool MM>
+__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G, MM>& b, const KArgs& a,
                                               unsigned char* smem) {
   b.ctid = threadIdx.x; b.grp = 0;
   b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5;
@@ -103,11 +107,11 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G>&
     unsigned char* shared = smem + per * G;
     b.cb_flags = reinterpret_cast<int*>(shared);
     b.cb_beta = reinterpret_cast<double*>(shared + 64);
-    b.cb_stage = b.cb_beta + (size_t)32 * G * G;
+    b.cb_stage = b.cb_beta + coop_beta_doubles(G, MM);
     b.cb_grad = b.cb_stage;
-    static_assert(coop_stage_doubles(G) >= 32 * G * G, "Xᵀr fits in one stage");
-    for (int i = threadIdx.x; i < 32 * G * G; i += 32 * W * G) b.cb_beta[i] = 0.0;
-    for (int i = threadIdx.x; i < kCoopStages * coop_stage_doubles(G); i += 32 * W * G) b.cb_stage[i] = 0.0;
+    static_assert(coop_stage_doubles(G) >= 32 * G * G && kMmaStage >= 32 * G * G, "Xᵀr fits in one stage");
+    for (int i = threadIdx.x; i < (int)coop_beta_doubles(G, MM); i += 32 * W * G) b.cb_beta[i] = 0.0;
+    for (int i = threadIdx.x; i < (int)coop_ring_doubles(G, MM); i += 32 * W * G) b.cb_stage[i] = 0.0;
     b.lr = a.lr + (size_t)blockIdx.x * 2 * G * a.lN;       // residuals [N][G]
     b.lll = b.lr + (size_t)G * a.lN;                       // ll terms   [G][N]
     smem += per * b.grp;
@@ -149,8 +153,8 @@ __device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc, int be
   return s_misc[0];
 }
 
-template <int EPL, int FAM, int W, bool DN, int G>
-__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN, G>& b, const KArgs& a, long c,
+template <int EPL, int FAM, int W, bool DN, int G, bool MM>
+__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN, G, MM>& b, const KArgs& a, long c,
                                            bool with_p) {
   b.chain = c;
   b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;   // the randexp batch belongs to one chain
@@ -174,8 +178,8 @@ __device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN, G>& b,
     if (with_p) b.matvec(b.p, b.ps);
   }
 }
-template <int EPL, int FAM, int W, bool DN, int G>
-__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN, G>& b, double* dst,
+template <int EPL, int FAM, int W, bool DN, int G, bool MM>
+__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN, G, MM>& b, double* dst,
                                           const double (&v)[EPL], size_t base, int D) {
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
@@ -185,9 +189,9 @@ __device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN, G
 }
 
 // ------------------------------------------------------------------ k_nuts
-template <int EPL, int FAM, int W, bool DN, int G>
+template <int EPL, int FAM, int W, bool DN, int G, bool MM>
 struct DrawSink {
-  DeviceBackend<EPL, FAM, W, DN, G>& b;
+  DeviceBackend<EPL, FAM, W, DN, G, MM>& b;
   const KArgs& a;
   long c;
   __device__ __forceinline__ void operator()(int n, const dhmc_tree_stats& ts, double e) {
@@ -201,10 +205,10 @@ struct DrawSink {
   }
 };
 
-template <int EPL, int FAM, int W, bool DN, int G = 1>
+template <int EPL, int FAM, int W, bool DN, int G = 1, bool MM = false>
 __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nuts(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN, G> b;
+  DeviceBackend<EPL, FAM, W, DN, G, MM> b;
   setup_backend(b, a, smem);
   int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles) : 0) +
                                        smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
@@ -214,9 +218,9 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nu
     else c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
-    DrawSink<EPL, FAM, W, DN, G> sink{b, a, c};
+    DrawSink<EPL, FAM, W, DN, G, MM> sink{b, a, c};
     const double eps_next = m.run(a.t0, a.N, a.eps[c], a.cfg, a.p_override,
                                   a.dir_override ? a.dir_override + c : nullptr, sink);
     const size_t base = (size_t)c * a.D;
@@ -234,10 +238,10 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nu
 }
 
 // ------------------------------------------------------------------ k_search
-template <int EPL, int FAM, int W, bool DN, int G = 1>
+template <int EPL, int FAM, int W, bool DN, int G = 1, bool MM = false>
 __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_search(const KArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN, G> b;
+  DeviceBackend<EPL, FAM, W, DN, G, MM> b;
   setup_backend(b, a, smem);
   int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles) : 0) +
                                        smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_se
     else c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
     const double eps = m.find_initial_stepsize(a.s_init, a.s_thresh, a.s_maxiter, a.p_override);
     if (b.tid == 0) {
@@ -467,6 +471,7 @@ struct dhmc_handle {
   dhmc_config cfg;
   int T = 0, W = 0, EPL = 0;
   int G = 1;                        // chains per CTA of the persistent kernels (packed chain groups)
+  bool coop_mma = false;            // experimental: likelihood rounds on the FP64 tensor cores
   size_t stride = 0;
   int n_slots = 0, n_sm = 0, grid = 0, sm_count = 0, light_grid = 0;
   size_t smem_bytes = 0, smem_light = 0;
@@ -552,8 +557,12 @@ constexpr int kPack = 8;            // packed chain groups: chains per CTA (logi
 // the layouts choose_layout picks for dim <= 256: one warp per chain up to 128, two above
 constexpr bool packed_layout(int W, int EPL) { return (W == 1 && EPL <= 4) || (W == 2 && EPL == 4); }
 template <int EPL, int FAM, int W>
-static const void* kernel_ptr(KernelId k, bool dense, int G = 1) {
+static const void* kernel_ptr(KernelId k, bool dense, int G = 1, bool mma = false) {
   if constexpr (FAM == DHMC_FAMILY_LOGISTIC && packed_layout(W, EPL)) {
+    if (G > 1 && mma) {     // experimental tensor-core likelihood (DHMC_COOP_MMA=1)
+      if (k == K_NUTS) return dense ? (const void*)k_nuts<EPL, FAM, W, true, kPack, true> : (const void*)k_nuts<EPL, FAM, W, false, kPack, true>;
+      if (k == K_SEARCH) return dense ? (const void*)k_search<EPL, FAM, W, true, kPack, true> : (const void*)k_search<EPL, FAM, W, false, kPack, true>;
+    }
     if (G > 1) {
       if (k == K_NUTS) return dense ? (const void*)k_nuts<EPL, FAM, W, true, kPack> : (const void*)k_nuts<EPL, FAM, W, false, kPack>;
       if (k == K_SEARCH) return dense ? (const void*)k_search<EPL, FAM, W, true, kPack> : (const void*)k_search<EPL, FAM, W, false, kPack>;
@@ -597,7 +606,7 @@ static int plan(dhmc_handle* h) {
   const size_t xs = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? h->stride : 0;
   const int G = h->G;
   auto heavy_smem = [&](int n_sm) -> size_t {
-    return G > 1 ? (size_t)G * group_smem_bytes(h->W, n_sm, slot_doubles, xs) + coop_smem_bytes(G)
+    return G > 1 ? (size_t)G * group_smem_bytes(h->W, n_sm, slot_doubles, xs) + coop_smem_bytes(G, h->coop_mma)
                  : smem_layout(h->W, n_sm, slot_doubles, xs).total;
   };
   struct { size_t total; } L0{heavy_smem(0)};
@@ -608,7 +617,7 @@ static int plan(dhmc_handle* h) {
       constexpr int WW = decltype(Wc)::value;
       constexpr int EP = decltype(E)::value;
       constexpr int FA = decltype(Fm)::value;
-      const void* fn = kernel_ptr<EP, FA, WW>(K_NUTS, h->dense, G);
+      const void* fn = kernel_ptr<EP, FA, WW>(K_NUTS, h->dense, G, h->coop_mma);
       if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
       cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L0.total);
       if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, fn, T * G, L0.total);
@@ -684,7 +693,7 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_st
     constexpr int WW = decltype(Wc)::value;
     constexpr int EPL = decltype(E)::value;
     constexpr int FAM = decltype(Fm)::value;
-    const void* fn = kernel_ptr<EPL, FAM, WW>(k, h->dense, G);
+    const void* fn = kernel_ptr<EPL, FAM, WW>(k, h->dense, G, h->coop_mma);
     if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
@@ -783,6 +792,8 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
     const char* ev = std::getenv("DHMC_PACK");
     if (!(ev && std::atoi(ev) == 0) && packed_layout(T / 32, EPL)) pack = kPack;
   }
+  const char* evm = std::getenv("DHMC_COOP_MMA");
+  const bool coop_mma = pack > 1 && evm && std::atoi(evm) == 1 && cfg->dim % 2 == 0;
   if (T == 0 || EPL == 0) { g_create_err = "dim too large for this build (dim <= 8 * threads_per_chain <= 2048)"; return DHMC_EARG; }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -793,7 +804,7 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   }
   if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "bad device ordinal"; return DHMC_EARG; }
   dhmc_handle* h = new dhmc_handle();
-  h->cfg = *cfg; h->T = T; h->W = T / 32; h->EPL = EPL; h->stride = (size_t)T * EPL; h->G = pack;
+  h->cfg = *cfg; h->T = T; h->W = T / 32; h->EPL = EPL; h->stride = (size_t)T * EPL; h->G = pack; h->coop_mma = coop_mma;
   h->n_slots = slots_needed(cfg->max_depth);
   auto fail = [&](int rc) { g_create_err = h->err; dhmc_destroy(h); return rc; };
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return fail(e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA); } } while (0)

@@ -3,6 +3,8 @@
 Bar (BASELINE.json north_star): integer tree decisions bit-exact; θ/p after a
 leapfrog step within 1e-10 relative (we observe bit-equality because both sides
 use the same canonical reduction order and deterministic math)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -438,6 +440,28 @@ def test_logistic_packed_groups_equal_one_chain_per_cta(pkg, N, p, K, M):
         assert a["ϵ"] == b["ϵ"] and np.array_equal(a["κ"].minv, b["κ"].minv)
         assert np.array_equal(a["posterior_matrix"], b["posterior_matrix"])
         assert np.array_equal(a["logdensities"], b["logdensities"])
+        for f in INT_FIELDS:
+            assert np.array_equal(a["tree_statistics"][f], b["tree_statistics"][f])
+    for r in out:
+        r["engine"].close()
+
+
+@pytest.mark.skipif(os.environ.get("DHMC_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental tensor-core likelihood (DHMC_COOP_MMA=1): compiled, not yet validated on hardware")
+@pytest.mark.parametrize("N,p,K", [(300, 20, 21), (1100, 130, 9), (2000, 256, 16)])
+def test_logistic_mma_likelihood_equals_fma_loops(pkg, monkeypatch, N, p, K):
+    """mma.sync.m8n8k4.f64 accumulates as sequential FMAs (profiles/r01_dmma_order_probe.txt), so the
+    tensor-core version of the cooperative likelihood must reproduce the default path bit for bit."""
+    ℓ, _ = pkg.LogisticRegression.synthetic(N=N, p=p, seed=N + p)
+    stages = pkg.default_warmup_stages(M=pkg.Diagonal, init_steps=20, middle_steps=20, doubling_stages=1,
+                                       terminating_steps=20)
+    out = []
+    for mma in ("0", "1"):
+        monkeypatch.setenv("DHMC_COOP_MMA", mma)
+        out.append(pkg.mcmc_keep_warmup(77, ℓ, 12, chains=K, warmup_stages=stages))
+    for k in range(K):
+        a, b = out[0]["inference"][k], out[1]["inference"][k]
+        assert a["ϵ"] == b["ϵ"] and np.array_equal(a["posterior_matrix"], b["posterior_matrix"])
         for f in INT_FIELDS:
             assert np.array_equal(a["tree_statistics"][f], b["tree_statistics"][f])
     for r in out:
