@@ -68,3 +68,54 @@ def test_device_models_match_oracle_models(pkg, po):
         lq, g = po.logdensity_and_gradient(fam, q, pr)
         lq2, g2 = ℓ.logdensity_and_gradient(q)
         assert lq == pytest.approx(lq2, rel=1e-13) and np.allclose(g, g2, rtol=1e-13)
+
+
+def _split_top_level(argstr):
+    out, depth, cur = [], 0, ""
+    for ch in argstr:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur)
+    return out
+
+
+def _call_sites(text, start=0):
+    """(name, n_args, has_star) for every `dhmc_xxx(` call in Python source text."""
+    for m in re.finditer(r"\.(dhmc_[a-z_]+)\(", text):
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(text[i], 0)
+            i += 1
+        args = _split_top_level(text[m.end():i - 1])
+        yield m.group(1), len(args), any(a.strip().startswith("*") for a in args)
+
+
+def test_python_call_sites_pass_the_declared_number_of_arguments():
+    """ctypes does not check arity for undeclared argtypes: every call of the C ABI from the host
+    mirror must pass exactly as many arguments as the prototype in include/dhmc.h has."""
+    src = open(os.path.join(ROOT, "include", "dhmc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(dhmc_[a-z_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        params = [p for p in _split_top_level(m.group(2)) if p.strip() and p.strip() != "void"]
+        protos[m.group(1)] = len(params)
+    assert len(protos) >= 20
+    seen = set()
+    for rel in ("dynamichmc.jl_b200/api.py", "dynamichmc.jl_b200/_lib.py", "dynamichmc.jl_b200/parallel.py",
+                "dynamichmc.jl_b200/diagnostics.py", "bench.py", "__graft_entry__.py"):
+        text = open(os.path.join(ROOT, rel)).read()
+        for name, n, star in _call_sites(text):
+            if name not in protos:
+                continue
+            seen.add(name)
+            if not star:                                   # get_state(*args) is checked at run time
+                assert n == protos[name], f"{rel}: {name} called with {n} arguments, prototype has {protos[name]}"
+    assert len(seen) >= 20
