@@ -119,3 +119,30 @@ def test_python_call_sites_pass_the_declared_number_of_arguments():
             if not star:                                   # get_state(*args) is checked at run time
                 assert n == protos[name], f"{rel}: {name} called with {n} arguments, prototype has {protos[name]}"
     assert len(seen) >= 20
+
+
+def test_julia_shim_ccall_signatures_match_the_header():
+    """julia/B200HMC.jl cannot be executed in this image; at least its ccall type tuples must have
+    the arity of the prototypes they bind (and every argument list must match its type tuple)."""
+    src = open(os.path.join(ROOT, "include", "dhmc.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(dhmc_[a-z_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
+        protos[m.group(1)] = len([p for p in _split_top_level(m.group(2)) if p.strip() and p.strip() != "void"])
+    jl = open(os.path.join(ROOT, "julia", "B200HMC.jl")).read()
+    jl = re.sub(r"#[^\n]*", "", jl)                        # drop comments
+    n = 0
+    for m in re.finditer(r"ccall\(\(:(dhmc_[a-z_]+),\s*LIB\)\s*,", jl):
+        i, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(jl[i], 0)
+            i += 1
+        parts = _split_top_level(jl[m.end():i - 1])        # [rettype, (argtypes...), args...]
+        types = parts[1].strip()
+        assert types.startswith("(") and types.endswith(")"), (m.group(1), types)
+        ntypes = len([t for t in _split_top_level(types[1:-1]) if t.strip()])
+        assert m.group(1) in protos, f"{m.group(1)} is not declared in dhmc.h"
+        assert ntypes == protos[m.group(1)], f"{m.group(1)}: {ntypes} ccall types, prototype has {protos[m.group(1)]}"
+        assert len(parts) - 2 == ntypes, f"{m.group(1)}: {len(parts) - 2} arguments for {ntypes} types"
+        n += 1
+    assert n >= 10
