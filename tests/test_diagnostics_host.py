@@ -104,3 +104,65 @@ def test_leapfrog_trajectory_positions_and_stopping(pkg_with_oracle_engine):
     assert far[-1]["position"] < 5 and not np.isfinite(far[-1]["z"]["lq"])
     with pytest.raises(pkg.ArgumentError):
         pkg.diagnostics.leapfrog_trajectory(ℓ, q, 0.1, range(1, 4))
+
+
+# ---------------------------------------------------------------- the reference's own diagnostics tests
+def test_reference_kat_summarize_tree_statistics(pkg_with_oracle_engine):
+    """test/test_diagnostics.jl:5-40 ("summarize tree statistics")."""
+    pkg, _ = pkg_with_oracle_engine
+    rng = np.random.default_rng(1)
+    N = 1000
+    ts = np.zeros(N, dtype=pkg._lib.tree_stats_dtype)
+    ts["pi"] = rng.normal(size=N)
+    ts["depth"] = rng.integers(0, 6, N)
+    maxd = rng.uniform(size=N) < 0.1                          # REACHED_MAX_DEPTH = InvalidTree(1, 0)
+    left = rng.integers(-5, 6, N)
+    right = left + rng.integers(0, 6, N)
+    ts["left"] = np.where(maxd, 1, left)
+    ts["right"] = np.where(maxd, 0, right)
+    ts["acceptance_rate"] = rng.uniform(size=N)
+    ts["steps"] = rng.integers(1, 31, N)
+    s = pkg.diagnostics.summarize_tree_statistics(ts)
+    assert s.N == N and np.isclose(s.a_mean, ts["acceptance_rate"].mean())
+    assert s.a_quantiles == [float(v) for v in np.quantile(ts["acceptance_rate"], pkg.diagnostics.ACCEPTANCE_QUANTILES)]
+    div = int(((ts["left"] == ts["right"])).sum())            # is_divergent: left == right, trees.jl:197
+    assert s.termination_counts["divergence"] == div and s.termination_counts["max_depth"] == int(maxd.sum())
+    assert s.termination_counts["turning"] == N - div - int(maxd.sum())
+    for i, c in enumerate(s.depth_counts):
+        assert int((ts["depth"] == i).sum()) == c
+    assert sum(s.depth_counts) == N
+    assert 1.8 <= pkg.diagnostics.EBFMI(ts) <= 2.2            # "nonsensical value, just checking calculation"
+
+
+def test_reference_kat_log_acceptance_ratios(pkg_with_oracle_engine):
+    """test/test_diagnostics.jl:42-49."""
+    pkg, _ = pkg_with_oracle_engine
+    ℓ = pkg.DiagNormal(np.ones(5), np.ones(5))               # multivariate_normal(ones(5))
+    log2eps = list(range(-5, 6))
+    A = pkg.diagnostics.explore_log_acceptance_ratios(ℓ, np.zeros(5), log2eps, N=13)
+    assert np.all(np.isfinite(A)) and A.shape == (len(log2eps), 13)
+
+
+def test_reference_kat_leapfrog_trajectory(pkg_with_oracle_engine):
+    """test/test_diagnostics.jl:51-80: a manually stepped trajectory against leapfrog_trajectory
+    started from its fifth point."""
+    pkg, po = pkg_with_oracle_engine
+    K = 2
+    ℓ = pkg.DiagNormal(np.ones(K), np.ones(K))
+    params = ℓ.params()
+    κ = pkg.GaussianKineticEnergy.identity(K)
+    q, p, eps, ix0 = np.zeros(K), np.full(K, 0.98), 0.1, 5
+    zs, πs = [], []
+    for _ in range(15):
+        lq, _ = po.logdensity_and_gradient(ℓ.family, q, params, 32)
+        zs.append((q.copy(), p.copy()))
+        πs.append(po.phase_logdensity(None, lq, p, 32))
+        q, p, _, _ = po.leapfrog(ℓ.family, q, p, eps, params=params)
+    Δs = np.array(πs) - πs[ix0 - 1]
+    traj = pkg.diagnostics.leapfrog_trajectory(ℓ, zs[ix0 - 1][0], eps, range(1 - ix0, 15 - ix0 + 1), κ=κ,
+                                               p=zs[ix0 - 1][1])
+    assert len(traj) == 15
+    np.testing.assert_allclose([t["Δ"] for t in traj], Δs, atol=1e-5)
+    for t, (qq, pp) in zip(traj, zs):
+        np.testing.assert_allclose(t["z"]["q"], qq, rtol=1e-8, atol=1e-12)
+        np.testing.assert_allclose(t["z"]["p"], pp, rtol=1e-8, atol=1e-12)
