@@ -118,6 +118,7 @@ class LogisticRegression(DeviceLogDensity):
         self.X = np.ascontiguousarray(self.X, float)
         self.y = np.ascontiguousarray(self.y, float)
         _argcheck(self.X.ndim == 2 and self.y.shape == (self.X.shape[0],), "X: [N, p], y: [N]")
+        _argcheck(bool(np.all((self.y >= 0.0) & (self.y <= 1.0))), "0 ≤ y ≤ 1 (Bernoulli responses)")
         self.D = self.X.shape[1]
 
     def params(self):

@@ -75,8 +75,8 @@ __host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride
 // Both passes over the design matrix (Xᵀ in phase 1, X in phase 2) are fed through a
 // three-stage cp.async ring in shared memory: each element of X reaches the SM once per G
 // gradients and two tiles are always in flight, so neither L2 nor HBM latency is exposed.
-// Returns this lane's partial Σ ll (<= 0, or NaN), or +1.0 when no warp is active any more
-// (which means that every warp is done).  Requires D <= 32·G.
+// Returns false when no warp is active any more (every warp is done); otherwise true with this
+// lane's partial Σ ll in *sll_out.  Requires D <= 32·G.
 constexpr int kCoopStages = 3;
 constexpr int kCoopTile = 4096;                                       // doubles of X / Xᵀ per stage
 constexpr int kCoopMaxRows = 64;                                      // rows of X per phase-2 tile, at most
@@ -96,7 +96,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // lXt has leading dimension ldn (even, >= N); lres is [N][G] (row-major), lll is [G][N].
 // A chain group is W warps (T = 32·W threads: tid within the group, grp = group within the CTA).
 template <int G, int W>
-__device__ __noinline__ double coop_core(bool active, int tid, int grp, int ctid, int D, int lN, int ldn,
+__device__ __noinline__ bool coop_core(double* sll_out, bool active, int tid, int grp, int ctid, int D, int lN, int ldn,
                                          const double* __restrict__ lX, const double* __restrict__ lXt,
                                          const double* __restrict__ ly, double* lres, double* lll,
                                          int* cb_flags, const double* cb_beta, double* cb_grad, double* cb_stage) {
@@ -111,7 +111,7 @@ __device__ __noinline__ double coop_core(bool active, int tid, int grp, int ctid
 #pragma unroll
   for (int gg = 0; gg < G; ++gg)
     if (cb_flags[gg]) amask |= 1u << gg;
-  if (amask == 0) return 1.0;
+  if (amask == 0) return false;        // no warp has a chain any more: every warp is done
 
   // ---------------- phase 1: tiles of J rows of Xᵀ × RB observations
   {
@@ -264,7 +264,8 @@ __device__ __noinline__ double coop_core(bool active, int tid, int grp, int ctid
     }
     __syncthreads();
   }
-  return sll;
+  *sll_out = sll;
+  return true;
 }
 
 // ---- EXPERIMENTAL (compiled, selected only with DHMC_COOP_MMA=1, not yet validated on hardware):
@@ -295,7 +296,7 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
 }
 
 template <int G, int W>
-__device__ __noinline__ double coop_core_mma(bool active, int tid, int grp, int ctid, int D, int lN, int ldn,
+__device__ __noinline__ bool coop_core_mma(double* sll_out, bool active, int tid, int grp, int ctid, int D, int lN, int ldn,
                                              const double* __restrict__ lX, const double* __restrict__ lXt,
                                              const double* __restrict__ ly, double* lres, double* lll,
                                              int* cb_flags, const double* cb_beta, double* cb_grad, double* cb_stage) {
@@ -314,7 +315,7 @@ __device__ __noinline__ double coop_core_mma(bool active, int tid, int grp, int 
 #pragma unroll
   for (int gg = 0; gg < G; ++gg)
     if (cb_flags[gg]) amask |= 1u << gg;
-  if (amask == 0) return 1.0;
+  if (amask == 0) return false;        // no warp has a chain any more: every warp is done
 
   // ---------------- phase 1
   {
@@ -446,7 +447,8 @@ __device__ __noinline__ double coop_core_mma(bool active, int tid, int grp, int 
     }
     __syncthreads();
   }
-  return sll;
+  *sll_out = sll;
+  return true;
 }
 
 // DENSE = Symmetric M⁻¹ per chain (hamiltonian.jl:73): p♯ = M⁻¹p is a D×D mat-vec
@@ -793,14 +795,15 @@ struct DeviceBackend {
         }
       }
     }
-    double sll;
+    double sll = 0.0;
+    bool more;
     if constexpr (MMA)
-      sll = coop_core_mma<G, W>(active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
-                                cb_flags, cb_beta, cb_grad, cb_stage);
+      more = coop_core_mma<G, W>(&sll, active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
+                                 cb_flags, cb_beta, cb_grad, cb_stage);
     else
-      sll = coop_core<G, W>(active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
-                            cb_flags, cb_beta, cb_grad, cb_stage);
-    if (sll > 0.0) return false;         // sentinel: ll terms are <= 0, so are their sums
+      more = coop_core<G, W>(&sll, active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
+                             cb_flags, cb_beta, cb_grad, cb_stage);
+    if (!more) return false;             // explicit flag (uniform over the CTA), not a property of the data
     sum_ll = sll;
     if (active) {
 #pragma unroll

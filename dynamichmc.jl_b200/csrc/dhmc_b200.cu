@@ -868,6 +868,10 @@ int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n) {
     if (!params || n < 1) { h->err = "dhmc_set_problem: logistic regression needs [N, X, y]"; return DHMC_EARG; }
     const size_t N = (size_t)params[0];
     if (N < 1 || n != 1 + N * D + N) { h->err = "dhmc_set_problem: expected 1 + N*D + N values"; return DHMC_EARG; }
+    for (size_t i = 0; i < N; ++i) {       // the model is a Bernoulli likelihood: responses (or their means) in [0, 1]
+      const double yv = params[1 + N * D + i];
+      if (!(yv >= 0.0 && yv <= 1.0)) { h->err = "dhmc_set_problem: logistic regression needs 0 <= y <= 1"; return DHMC_EARG; }
+    }
     cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr);
     h->lX = h->lXt = h->ly = h->lr = nullptr;
     const size_t ld = (N + 1) & ~(size_t)1;                 // even leading dimension: 16-byte aligned row segments
@@ -1082,9 +1086,11 @@ int dhmc_find_initial_stepsize(dhmc_handle* h, double initial_eps, double log_th
   a.s_init = initial_eps; a.s_thresh = log_threshold; a.s_maxiter = maxiter;
   int rc = launch(h, K_SEARCH, a, 1);
   if (rc != DHMC_OK) return rc;
-  h->has_eps = true;
-  return sync_and_check_status(h, DHMC_CHAIN_SEARCH_FAILED | DHMC_CHAIN_NONFINITE_Q,
-                               "initial stepsize search failed (no crossing, or non-finite starting density)");
+  // the reference aborts when the search fails (stepsize.jl:58,78): ϵ counts as set only if every chain found one
+  rc = sync_and_check_status(h, DHMC_CHAIN_SEARCH_FAILED | DHMC_CHAIN_NONFINITE_Q,
+                             "initial stepsize search failed (no crossing, or non-finite starting density)");
+  h->has_eps = (rc == DHMC_OK);
+  return rc;
 }
 
 // common driver of sample_tree / warmup stage / mcmc.
@@ -1180,9 +1186,9 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   h->last_steps = (int64_t)steps;
   if (advance_t) h->t += (uint32_t)N;
   if (q_host) h->has_position = true;
-  rc = sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q | DHMC_CHAIN_BAD_ACCEPTANCE | (q_host ? DHMC_CHAIN_BAD_INITIAL : 0),
-                             q_host ? "invalid initial position, or non-finite position / acceptance rate while sampling"
-                                    : "sampling: non-finite position or acceptance rate");
+  rc = sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q | DHMC_CHAIN_BAD_ACCEPTANCE | DHMC_CHAIN_BAD_STEPSIZE | (q_host ? DHMC_CHAIN_BAD_INITIAL : 0),
+                             q_host ? "invalid initial position, or non-finite position / acceptance rate / step size while sampling"
+                                    : "sampling: non-finite position, acceptance rate or step size");
   if (rc != DHMC_OK) return rc;
   if (cfg.metric == DHMC_METRIC_DIAGONAL && h->dense) {   // κ ← Diagonal: back to the diagonal kernels
     h->dense = false;

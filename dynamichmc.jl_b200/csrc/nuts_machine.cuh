@@ -359,8 +359,13 @@ struct NutsMachine {
   DHMC_M double run(uint32_t t0, int N, double eps, const AdaptConfig& cfg,
                      const double* p_override, const uint32_t* dir_override, Sink& sink) {
     TopState& S = b.top();
+    if (!(eps > 0)) {                      // @argcheck ϵ > 0, stepsize.jl:135 (NaN after a failed search included)
+      status |= DHMC_CHAIN_BAD_STEPSIZE;
+      steps_out = 0;
+      return eps;
+    }
     {
-      DA A0 = da_init(eps > 0 ? eps : 1.0);
+      DA A0 = da_init(eps);
       S.da_mu = A0.mu; S.da_m = A0.m; S.da_Hbar = A0.Hbar; S.da_logeps = A0.logeps; S.da_logepsbar = A0.logepsbar;
     }
     if (cfg.metric != DHMC_METRIC_NOTHING) b.metric_reset(cfg.metric);

@@ -44,7 +44,8 @@ enum {
   DHMC_CHAIN_SEARCH_FAILED = 2, /* find_initial_stepsize, stepsize.jl:58 / :78 */
   DHMC_CHAIN_NONFINITE_Q = 4,   /* evaluate_ℓ: non-finite position, hamiltonian.jl:203 */
   DHMC_CHAIN_BAD_ACCEPTANCE = 8, /* adapt_stepsize @argcheck 0 ≤ a ≤ 1, stepsize.jl:148 */
-  DHMC_CHAIN_NOT_POSDEF = 16     /* cholesky(inv(M⁻¹)) failed, hamiltonian.jl:73 (PosDefException) */
+  DHMC_CHAIN_NOT_POSDEF = 16,    /* cholesky(inv(M⁻¹)) failed, hamiltonian.jl:73 (PosDefException) */
+  DHMC_CHAIN_BAD_STEPSIZE = 32   /* initial_adaptation_state @argcheck ϵ > 0, stepsize.jl:135 (chain left untouched) */
 };
 
 /* log-density family ids: see include/dhmc_models.h */

@@ -1,9 +1,12 @@
 // oracle_capi.cpp — flat C entry points over oracle.hpp for ctypes
 // (oracle/pyoracle.py).  TEST INFRASTRUCTURE ONLY — see the header of oracle.hpp.
 #include <malloc.h>
+#include <pthread.h>
+#include <sched.h>
 
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
@@ -360,7 +363,19 @@ int orc_bench_mcmc(int family, int D, const double* params, int T, int max_depth
   std::vector<double> mean_acc((size_t)D, 0.0);
   auto stages = make_stages(n_stages, kind, stN, metric, da_on, nullptr, nullptr);
   auto t0 = std::chrono::steady_clock::now();
-  auto work = [&] {
+  // pin worker i to the i-th CPU of the process's affinity mask (stable placement, no migration)
+  cpu_set_t allowed;
+  CPU_ZERO(&allowed);
+  std::vector<int> cpus;
+  if (sched_getaffinity(0, sizeof allowed, &allowed) == 0)
+    for (int i = 0; i < CPU_SETSIZE; ++i) if (CPU_ISSET(i, &allowed)) cpus.push_back(i);
+  auto work = [&](int widx) {
+    if (!cpus.empty() && std::getenv("DHMC_ORACLE_NO_PIN") == nullptr) {
+      cpu_set_t one;
+      CPU_ZERO(&one);
+      CPU_SET(cpus[(size_t)widx % cpus.size()], &one);
+      pthread_setaffinity_np(pthread_self(), sizeof one, &one);
+    }
     for (;;) {
       int c = next.fetch_add(1);
       if (c >= n_chains) break;
@@ -377,7 +392,7 @@ int orc_bench_mcmc(int family, int D, const double* params, int T, int max_depth
     }
   };
   std::vector<std::thread> th;
-  for (int i = 0; i < n_threads; ++i) th.emplace_back(work);
+  for (int i = 0; i < n_threads; ++i) th.emplace_back(work, i);
   for (auto& t : th) t.join();
   auto t1 = std::chrono::steady_clock::now();
   *total_steps = steps.load();
