@@ -142,17 +142,21 @@ __device__ __noinline__ bool coop_core(double* sll_out, bool active, int tid, in
     };
     issue(0);
     issue(1);
-    double eta[U][G];
+    static_assert(DHMC_LOGIT_CHUNK % J == 0, "η chunks are whole tiles");
+    double eta[U][G], etot[U][G];          // running chunk sum, sum of the finished chunks (dhmc_logit_eta)
     for (int t = 0; t < ntiles; ++t) {
       cp_async_wait<1>();                  // this thread's pieces of tile t have landed
       __syncthreads();                     // everyone's have, and everyone is done with tile t-1
       issue(t + 2);                        // refills the stage of tile t-1
       const int ps = t / nchunks, ch = t - ps * nchunks;
-      if (ch == 0) {
+      if ((ch * J) % DHMC_LOGIT_CHUNK == 0) {
 #pragma unroll
         for (int u = 0; u < U; ++u)
 #pragma unroll
-          for (int gg = 0; gg < G; ++gg) eta[u][gg] = 0.0;
+          for (int gg = 0; gg < G; ++gg) {
+            if (ch != 0) etot[u][gg] = (ch * J == DHMC_LOGIT_CHUNK) ? eta[u][gg] : etot[u][gg] + eta[u][gg];
+            eta[u][gg] = 0.0;
+          }
       }
       const double* src = cb_stage + (size_t)(t % S) * STG + ctid;
 #pragma unroll
@@ -172,6 +176,7 @@ __device__ __noinline__ bool coop_core(double* sll_out, bool active, int tid, in
         }
       }
       if (ch == nchunks - 1) {
+        const bool one_chunk = D <= DHMC_LOGIT_CHUNK;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int n = ps * RB + ctid + u * NT;
@@ -180,8 +185,11 @@ __device__ __noinline__ bool coop_core(double* sll_out, bool active, int tid, in
 #pragma unroll
             for (int gg = 0; gg < G; ++gg) {
               if (amask & (1u << gg)) {
-                lll[(size_t)gg * lN + n] = dhmc_logit_ll(yn, eta[u][gg]);
-                lres[(size_t)n * G + gg] = dhmc_logit_resid(yn, eta[u][gg]);
+                double llv, rv;
+                const double etav = one_chunk ? eta[u][gg] : etot[u][gg] + eta[u][gg];
+                dhmc_logit_ll_resid(yn, etav, &llv, &rv);
+                lll[(size_t)gg * lN + n] = llv;
+                lres[(size_t)n * G + gg] = rv;
               }
             }
           }
@@ -268,185 +276,281 @@ __device__ __noinline__ bool coop_core(double* sll_out, bool active, int tid, in
   return true;
 }
 
-// ---- EXPERIMENTAL (compiled, selected only with DHMC_COOP_MMA=1, not yet validated on hardware):
-// the same likelihood round on the FP64 tensor cores.  mma.sync.m8n8k4.f64 computes
-// fma(a3,b3, fma(a2,b2, fma(a1,b1, fma(a0,b0, c)))) (measured: profiles/r01_dmma_order_probe.txt),
-// i.e. the model's own sequential order, so the results are those of coop_core bit for bit.
-//   phase 1: D[8 obs × 8 chains] += A[8 obs × 4 coeff] · B[4 coeff × 8 chains]; A from the Xᵀ ring
-//            tile (4 rows of stride kMmaRS ≡ 4 mod 16 doubles: conflict-free LDS.64 fragments), B = β
-//            stored [chain][kMmaBS];
-//   phase 2: D[8 coeff × 8 chains] += A[8 coeff × 4 obs] · B[4 obs × 8 chains]; A from the X ring tile
-//            (row stride XS ≡ 4 mod 16), B = residuals stored [obs][kMmaRr].
-// k-padding (coefficients >= D in phase 1, observations >= N in phase 2) is zero-filled so that the
-// padded steps are fma(0, 0, acc) = acc.  Index formulas and strides: benchmarks/dmma_layout_check.py.
-// Requires G == 8, D even (16-byte aligned rows of X) and D <= 256.
-constexpr int kMmaRB = 1024;                 // observations per pass of phase 1
-constexpr int kMmaRS = kMmaRB + 4;           // row stride of the Xᵀ tile
-constexpr int kMmaBS = 260;                  // row stride of β [chain][·]  (>= 256, ≡ 4 mod 16)
-constexpr int kMmaRr = 12;                   // row stride of the residual tile [obs][8 + 4]
-constexpr int kMmaStage = 4 * kMmaRS + 64 * kMmaRr;   // doubles per ring stage (>= 4 rows of Xᵀ; X tile + residuals)
-__host__ __device__ inline int mma_xs(int D) { int x = D; while ((x & 15) != 4) ++x; return x; }
-__host__ __device__ inline int mma_rows(int D) {     // observations per phase-2 tile: multiple of 4, rows·XS <= 4·kMmaRS
-  int r = ((4 * kMmaRS) / mma_xs(D)) & ~3;
-  return r < 4 ? 4 : r > 64 ? 64 : r;
+// ---- the likelihood round on the FP64 tensor cores, fed by TMA bulk copies (default for packed groups) ----
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) computes fma(a3,b3, fma(a2,b2, fma(a1,b1, fma(a0,b0, c))))
+// (measured: profiles/r01_dmma_order_probe.txt), i.e. the model's own sequential order, so the results
+// are those of coop_core bit for bit.  Measured on the B200 (profiles/r02_c4_probes.txt): one DMMA per
+// 16 clk per SM sub-partition = 64 FMA/clk/SM (the DFMA peak) with 1/8 of the instructions, latency
+// 26 clk, saturated by two independent accumulator chains per sub-partition.
+//
+// One pass over the design matrix per gradient.  X is kept in HBM/L2 as zero-padded row blocks
+// [32 rows][XS] (XS ≡ 4 mod 16 doubles: every fragment load below is bank-conflict free); one elected
+// thread streams the blocks through a two-stage shared-memory ring with cp.async.bulk (SASS UBLKCP)
+// completing on an mbarrier, consumers release a stage through a second mbarrier.  Per block:
+//   P1  four 8-row tiles × four chunks of 64 coefficients spread over all warps: chunk sums of
+//       η[8 obs × 8 chains] += X[8 × 4] · β[4 × 8] (η is a blocked dot product, dhmc_logit_eta: the chunks are
+//       independent chains of 16 dependent DMMAs, so P1 is bound by the tensor pipe, not by DMMA latency);
+//   E   warp g = chain g, lane = row: η from the chunk sums, ll term into the lane's canonical Σ ll partial,
+//       residual y − σ(η) → shared tile [chain][32]; rows ≥ N give residual 0;
+//   P2  all warps, ⌈D/8⌉ coefficient tiles split over the warps:
+//       (Xᵀr)[8 coeff × 8 chains] += Xᵀ[8 × 4 obs] · r[4 obs × 8] — accumulators live in registers for the round.
+// Zero padding (rows ≥ N, columns ≥ D) only ever adds fma(0, 0, acc) = acc.
+constexpr int kTmaRows = 32;                 // rows of X per block
+constexpr int kTmaStages = 2;
+constexpr int kTmaPieces = 8;                // bulk copies per block (4 rows each: 16-byte multiples)
+constexpr int kTmaBS = 260;                  // row pitch of β [chain][·]            (≡ 4 mod 16)
+constexpr int kTmaES = 36;                   // row pitch of the η / residual tiles  (≡ 4 mod 16)
+__host__ __device__ inline int tma_xs(int D) { int w = (D + 7) & ~7; while ((w & 15) != 4) ++w; return w; }
+__host__ __device__ inline size_t tma_stage_doubles(int D) { return (size_t)kTmaRows * tma_xs(D); }
+// CTA-shared area behind the per-group blocks: [0,32) flags, [64,96) mbarriers full[2] empty[2],
+// [128, …) β, η tile, residual tile, math tables (lanes look up different entries), ring
+__host__ __device__ inline size_t tma_beta_off() { return 128; }
+__host__ __device__ inline size_t tma_eta_off(int G) { return tma_beta_off() + sizeof(double) * (size_t)G * kTmaBS; }
+constexpr int kTmaChunks = 256 / DHMC_LOGIT_CHUNK;     // η chunk sums per row (dim <= 256)
+// η area: kTmaChunks partial tiles [chain][kTmaES], then the residual tile; after the round the first G·64 doubles
+// hand the per-thread Σ ll partials back
+__host__ __device__ inline size_t tma_tabs_off(int G) { return tma_eta_off(G) + sizeof(double) * (kTmaChunks + 1) * (size_t)G * kTmaES; }   // math tables, DM_TABS_DOUBLES
+__host__ __device__ inline size_t tma_ring_off(int G) { return (tma_tabs_off(G) + sizeof(double) * DM_TABS_DOUBLES + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t tma_smem_bytes(int G, int D) { return tma_ring_off(G) + sizeof(double) * kTmaStages * tma_stage_doubles(D); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ double lds64(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// optional cycle accounting of the round's phases (build with -DDHMC_PROFILE_ROUNDS; variants/ only)
+#ifdef DHMC_PROFILE_ROUNDS
+#define DHMC_PROF_DECL long long pf_t = clock64(), pf_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define DHMC_PROF(i) do { const long long t_ = clock64(); pf_acc[i] += t_ - pf_t; pf_t = t_; } while (0)
+#define DHMC_PROF_FLUSH(ptr) do { if (ptr) { for (int i_ = 0; i_ < 8; ++i_) (ptr)[i_] += (unsigned long long)pf_acc[i_]; (ptr)[8] += 1; } } while (0)
+#else
+#define DHMC_PROF_DECL
+#define DHMC_PROF(i) do { } while (0)
+#define DHMC_PROF_FLUSH(ptr) do { } while (0)
+#endif
+
+// lXp: padded row blocks of X, [nblk·32][XS]; lll: unused (the FMA formulation's global ll scratch);
+// shared: the CTA-shared area (layout above); ring_n: blocks streamed so far (same in all threads).
 template <int G, int W>
-__device__ __noinline__ bool coop_core_mma(double* sll_out, bool active, int tid, int grp, int ctid, int D, int lN, int ldn,
-                                             const double* __restrict__ lX, const double* __restrict__ lXt,
-                                             const double* __restrict__ ly, double* lres, double* lll,
-                                             int* cb_flags, const double* cb_beta, double* cb_grad, double* cb_stage) {
+__device__ __noinline__ bool coop_core_tma(double* sll_out, bool active, int tid, int grp, int ctid, int D, int lN,
+                                           const double* __restrict__ lXp, const double* __restrict__ ly, double* lll,
+                                           unsigned char* shared, uint32_t& ring_n, unsigned long long* prof) {
   static_assert(G == 8, "the n-dimension of the MMA is the chain");
+  DHMC_PROF_DECL
   constexpr int T = 32 * W;
   constexpr int NT = T * G;
-  constexpr int NW = W * G;                // warps of the CTA
-  constexpr int NC = 32 * G;
-  constexpr int S = kCoopStages;
-  constexpr int STG = kMmaStage;
+  constexpr int NW = W * G;                 // warps of the CTA
+  constexpr int MW = 8;                     // warps that issue DMMAs (two per sub-partition saturate the pipe; more only add
+                                            // shared-memory traffic: operands are reused across a warp's tiles)
+  constexpr int JT = 32 / MW;               // coefficient tiles per MMA warp in P2 (D <= 256)
+  int* cb_flags = reinterpret_cast<int*>(shared);
+  uint64_t* full = reinterpret_cast<uint64_t*>(shared + 64);
+  uint64_t* empty = full + kTmaStages;
+  // shared-state-space addresses: every access below is an explicit ld/st.shared (the pointers reach this
+  // function as generic addresses; generic loads would be resolved per access and are slower)
+  const uint32_t sh = smem_u32(shared);
+  const uint32_t beta_a = sh + (uint32_t)tma_beta_off();
+  const uint32_t eta_a = sh + (uint32_t)tma_eta_off(G);                       // η chunk sums [chunk][chain][kTmaES]
+  const uint32_t res_a = eta_a + (uint32_t)(sizeof(double) * kTmaChunks * G * kTmaES);   // residuals [chain][kTmaES]
+  const uint32_t ring_a = sh + (uint32_t)tma_ring_off(G);
+  const double* tabs = reinterpret_cast<const double*>(shared + tma_tabs_off(G));
+  double* ring = reinterpret_cast<double*>(shared + tma_ring_off(G));
   const int lane = ctid & 31, wq = ctid >> 5;
   const int fr = lane >> 2, fk = lane & 3;  // fragment row / k index of this lane
   if (tid == 0) cb_flags[grp] = active ? 1 : 0;
-  __syncthreads();
+  __syncthreads();                          // β and flags are published; the ring (last round's Xᵀr) is free
+  DHMC_PROF(0);                             // 0: waiting for the other chains to arrive
   unsigned amask = 0;
 #pragma unroll
   for (int gg = 0; gg < G; ++gg)
     if (cb_flags[gg]) amask |= 1u << gg;
-  if (amask == 0) return false;        // no warp has a chain any more: every warp is done
+  if (amask == 0) return false;
 
-  // ---------------- phase 1
-  {
-    constexpr int RW = kMmaRB / NW;        // observations per warp and pass
-    constexpr int TW = RW / 8;             // 8-row tiles per warp
-    const int nchunks = (D + 3) / 4;
-    const int npass = (lN + kMmaRB - 1) / kMmaRB;
-    const int ntiles = npass * nchunks;
-    auto issue = [&](int t) {
-      if (t < ntiles) {
-        const int ps = t / nchunks, ch = t - ps * nchunks;
-        const int n0 = ps * kMmaRB;
-        const int cnt = ldn - n0 < kMmaRB ? ldn - n0 : kMmaRB;
-        const int cpr = cnt >> 1;
-        double* dst = cb_stage + (size_t)(t % S) * STG;
+  const int XS = tma_xs(D);
+  const int nblk = (lN + kTmaRows - 1) / kTmaRows;
+  const int ng = (D + 15) >> 4;             // groups of four k-steps of P1 (all chunks)
+  const int nch = (D + DHMC_LOGIT_CHUNK - 1) / DHMC_LOGIT_CHUNK;   // η chunks (dhmc_logit_eta)
+  const uint32_t stage_bytes = (uint32_t)(sizeof(double) * kTmaRows * XS);
+  const bool producer = (wq == NW - 1) && (lane == 0);
+  const uint32_t n0 = ring_n;
+  auto issue = [&](int b) {                 // block b of this round -> stage (n0 + b) % 2
+    const uint32_t n = n0 + (uint32_t)b;
+    const int s = (int)(n & 1u);
+    mbar_wait(empty + s, ((n >> 1) & 1u) ^ 1u);             // everyone is done with the stage's previous block
+    mbar_expect_tx(full + s, stage_bytes);
+    // a single bulk copy is paced by its own latency (~20 B/clk measured): kTmaPieces of them run concurrently
+    const uint32_t piece = stage_bytes / kTmaPieces;
+    double* dst = ring + (size_t)s * kTmaRows * XS;
+    const double* src = lXp + (size_t)b * kTmaRows * XS;
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = ch * 4 + jj;
-          if (j < D) {
-            const double* sj = lXt + (size_t)j * ldn + n0;
-            for (int k = ctid; k < cpr; k += NT) cp_async16(dst + jj * kMmaRS + 2 * k, sj + 2 * k);
-          } else {
-            for (int k = ctid; k < kMmaRB; k += NT) dst[jj * kMmaRS + k] = 0.0;   // k-padding
-          }
-        }
-      }
-      cp_async_commit();
-    };
+    for (int pc = 0; pc < kTmaPieces; ++pc)
+      bulk_g2s(reinterpret_cast<char*>(dst) + (size_t)pc * piece, reinterpret_cast<const char*>(src) + (size_t)pc * piece, piece, full + s);
+  };
+  if (producer) {
+    fence_proxy_async();                    // generic writes to the ring (Xᵀr hand-back) precede the async writes
     issue(0);
-    issue(1);
-    double c[TW][2];
-    for (int t = 0; t < ntiles; ++t) {
-      cp_async_wait<1>();
-      __syncthreads();
-      issue(t + 2);
-      const int ps = t / nchunks, ch = t - ps * nchunks;
-      if (ch == 0) {
+    if (nblk > 1) issue(1);
+  }
+  __syncwarp();
+  double acc[JT][2];
 #pragma unroll
-        for (int rt = 0; rt < TW; ++rt) { c[rt][0] = 0.0; c[rt][1] = 0.0; }
-      }
-      const double* src = cb_stage + (size_t)(t % S) * STG + fk * kMmaRS + wq * RW + fr;
-      const double b = cb_beta[(size_t)fr * kMmaBS + ch * 4 + fk];
+  for (int q = 0; q < JT; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; }
+  double sl[W];                             // E: this lane's Σ ll partials = those of threads lane, lane+32 of chain wq
 #pragma unroll
-      for (int rt = 0; rt < TW; ++rt) dmma_8x8x4(c[rt][0], c[rt][1], src[rt * 8], b);
-      if (ch == nchunks - 1) {
-#pragma unroll
-        for (int rt = 0; rt < TW; ++rt) {
-          const int n = ps * kMmaRB + wq * RW + rt * 8 + fr;
-          if (n < lN) {
-            const double yn = __ldg(ly + n);
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int gg = 2 * fk + i;
-              if (amask & (1u << gg)) {
-                lll[(size_t)gg * lN + n] = dhmc_logit_ll(yn, c[rt][i]);
-                lres[(size_t)n * G + gg] = dhmc_logit_resid(yn, c[rt][i]);
-              }
-            }
-          }
+  for (int hh = 0; hh < W; ++hh) sl[hh] = 0.0;
+  // P1 work of an MMA warp: chunk c = wq & 3, row tiles 2·(wq >> 2) and 2·(wq >> 2) + 1 (they share the β fragments)
+  const int pc1 = wq & 3, mp = (wq >> 2) & 1;
+  const uint32_t p1_a = (uint32_t)(sizeof(double) * ((16 * mp + fr) * XS + fk));     // A fragment of P1 within a stage (second tile: + 8 rows)
+  const uint32_t p1_b = beta_a + (uint32_t)(sizeof(double) * (fr * kTmaBS + fk));     // B fragment of P1
+  const uint32_t p2_b = res_a + (uint32_t)(sizeof(double) * (fr * kTmaES + fk));      // B fragment of P2
+  const uint32_t p2_a = (uint32_t)(sizeof(double) * (fk * XS + 8 * wq + fr));         // A fragment of P2 within a stage
+
+  for (int b = 0; b < nblk; ++b) {
+    const uint32_t n = n0 + (uint32_t)b;
+    const int s = (int)(n & 1u);
+    const uint32_t par = (n >> 1) & 1u;
+    const uint32_t xt = ring_a + (uint32_t)s * stage_bytes;
+    // ---- P1: chunk sums of η for rows 8·mt … 8·mt+7: D[8 obs × 8 chains] += X[8 × 4] · β[4 × 8], a dependent
+    // chain of up to 16 DMMAs per chunk (26 clk each), fragments fetched one group of four k-steps ahead;
+    // k-steps beyond ⌈D/4⌉ hit the zero padding of X and β (16·⌈D/16⌉ <= XS)
+    mbar_wait(full + s, par);
+    DHMC_PROF(1);                           // 1: waiting for the block
+    if (wq < MW) {
+      const int g0 = 4 * pc1, g1 = (4 * pc1 + 4 < ng) ? 4 * pc1 + 4 : ng;    // k-step groups of this chunk
+      if (g0 < g1) {
+        const uint32_t ap = xt + p1_a + 128 * g0, ap2 = ap + (uint32_t)(sizeof(double) * 8 * XS), bp = p1_b + 128 * g0;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        // two fragment sets in ping-pong (every statement is a volatile asm: the order below is the issue order,
+        // loads run one group of four k-steps ahead of the DMMAs that consume them)
+        double fa[2][4], fa2[2][4], fb[2][4];
+#define DHMC_P1_LOAD(set, g)                                                                   \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
+          fa[set][u] = lds64(ap + 128 * (g) + 32 * u); fa2[set][u] = lds64(ap2 + 128 * (g) + 32 * u); \
+          fb[set][u] = lds64(bp + 128 * (g) + 32 * u);                                         \
         }
+#define DHMC_P1_MMA(set)                                                                       \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
+          dmma_8x8x4(c0, c1, fa[set][u], fb[set][u]); dmma_8x8x4(d0, d1, fa2[set][u], fb[set][u]); \
+        }
+        const int ngr = g1 - g0;            // 1 … 4
+        DHMC_P1_LOAD(0, 0)
+        if (ngr > 1) { DHMC_P1_LOAD(1, 1) }
+        DHMC_P1_MMA(0)
+        if (ngr > 2) { DHMC_P1_LOAD(0, 2) }
+        if (ngr > 1) { DHMC_P1_MMA(1) }
+        if (ngr > 3) { DHMC_P1_LOAD(1, 3) }
+        if (ngr > 2) { DHMC_P1_MMA(0) }
+        if (ngr > 3) { DHMC_P1_MMA(1) }
+#undef DHMC_P1_LOAD
+#undef DHMC_P1_MMA
+        const uint32_t ea = eta_a + (uint32_t)(sizeof(double) * (pc1 * G * kTmaES + 16 * mp + fr));
+        sts64(ea + (uint32_t)(sizeof(double) * (2 * fk) * kTmaES), c0);
+        sts64(ea + (uint32_t)(sizeof(double) * (2 * fk + 1) * kTmaES), c1);
+        sts64(ea + (uint32_t)(sizeof(double) * ((2 * fk) * kTmaES + 8)), d0);
+        sts64(ea + (uint32_t)(sizeof(double) * ((2 * fk + 1) * kTmaES + 8)), d1);
       }
     }
-    cp_async_wait<0>();
+    DHMC_PROF(2);                           // 2: P1 compute
     __syncthreads();
-  }
-  // ---------------- phase 1b
-  double sll = 0.0;
-  if (active) {
-    const double* t = lll + (size_t)grp * lN;
-    for (int n = tid; n < lN; n += T) sll = sll + t[n];
-  }
-  // ---------------- phase 2
-  {
-    const int XS = mma_xs(D);
-    const int R = mma_rows(D);
-    const int ntiles = (lN + R - 1) / R;
-    const int hd = D >> 1;                  // 16-byte pieces per row of X (D even)
-    constexpr int JTW = (NC / 8 + NW - 1) / NW;   // 8-coefficient tiles per warp
-    auto issue = [&](int t) {
-      if (t < ntiles) {
-        const int n0 = t * R;
-        const int rows = lN - n0 < R ? lN - n0 : R;
-        const int rows4 = (rows + 3) & ~3;
-        double* dst = cb_stage + (size_t)(t % S) * STG;
-        for (int r = wq; r < rows4; r += NW) {
-          if (r < rows) {
-            const double* sx = lX + (size_t)(n0 + r) * D;
-            for (int k = lane; k < hd; k += 32) cp_async16(dst + (size_t)r * XS + 2 * k, sx + 2 * k);
-            if (lane < G / 2) cp_async16(dst + 4 * kMmaRS + r * kMmaRr + 2 * lane, lres + (size_t)(n0 + r) * G + 2 * lane);
-          } else {                          // k-padding of the last tile
-            for (int k = lane; k < XS; k += 32) dst[(size_t)r * XS + k] = 0.0;
-            if (lane < kMmaRr) dst[4 * kMmaRS + r * kMmaRr + lane] = 0.0;
-          }
-        }
-      }
-      cp_async_commit();
-    };
-    issue(0);
-    issue(1);
-    double c[JTW][2];
+    DHMC_PROF(3);                           // 3: barrier after P1
+    // ---- E: warp gg evaluates chain gg, lane = row: η = ((s₀ + s₁) + s₂) + s₃, ll term into this lane's
+    // canonical partial (thread (n mod T) of the chain sums n, n+T, … in increasing n), residual -> shared tile
+    if (wq >= NW - G) {
+      const int gg = wq - (NW - G), r = lane;
+      const int nrow = b * kTmaRows + r;
+      const uint32_t ea = eta_a + (uint32_t)(sizeof(double) * (gg * kTmaES + r));
+      double eta = lds64(ea);
+      for (int c = 1; c < nch; ++c) eta = eta + lds64(ea + (uint32_t)(sizeof(double) * c * G * kTmaES));
+      double rv = 0.0;                      // rows >= N contribute fma(x, 0, acc) = acc
+      if (nrow < lN) {
+        double llv;
+        dhmc_logit_ll_resid_tabs(__ldg(ly + nrow), eta, &llv, &rv, tabs);
 #pragma unroll
-    for (int q = 0; q < JTW; ++q) { c[q][0] = 0.0; c[q][1] = 0.0; }
-    for (int t = 0; t < ntiles; ++t) {
-      cp_async_wait<1>();
-      __syncthreads();
-      issue(t + 2);
-      const int n0 = t * R;
-      const int rows = lN - n0 < R ? lN - n0 : R;
-      const double* xt = cb_stage + (size_t)(t % S) * STG;
-      const double* rt = xt + 4 * kMmaRS;
-      for (int nn = 0; nn < rows; nn += 4) {
-        const double b = rt[(nn + fk) * kMmaRr + fr];
-#pragma unroll
-        for (int q = 0; q < JTW; ++q) {
-          const int jt = wq + q * NW;
-          if (jt * 8 < D) dmma_8x8x4(c[q][0], c[q][1], xt[(size_t)(nn + fk) * XS + jt * 8 + fr], b);
-        }
+        for (int hh = 0; hh < W; ++hh)
+          if ((b & (W - 1)) == hh) sl[hh] = sl[hh] + llv;
       }
+      sts64(res_a + (uint32_t)(sizeof(double) * (gg * kTmaES + r)), rv);
     }
-    cp_async_wait<0>();
-    __syncthreads();                       // cb_grad lives in stage 0 of the ring
-#pragma unroll
-    for (int q = 0; q < JTW; ++q) {
-      const int j = (wq + q * NW) * 8 + fr;
-      if (j < D) {
-        cb_grad[(size_t)(2 * fk) * NC + j] = c[q][0];
-        cb_grad[(size_t)(2 * fk + 1) * NC + j] = c[q][1];
-      }
-    }
+    DHMC_PROF(4);                           // 4: E compute
     __syncthreads();
+    DHMC_PROF(5);                           // 5: barrier after E
+    // ---- P2: (Xᵀr) += Xᵀ[coefficients × rows of the block] · r; operands one k-step ahead
+    if (wq < MW) {
+      const uint32_t ap = xt + p2_a;
+      uint32_t jo[JT];                      // column offset of this warp's coefficient tiles (tiles beyond D are not touched)
+#pragma unroll
+      for (int q = 0; q < JT; ++q) jo[q] = (wq + q * MW) * 8 < D ? (uint32_t)(sizeof(double) * 8 * MW * q) : 0xffffffffu;
+      double bv[2], av[2][JT];              // ping-pong operand sets, one k-step ahead (volatile asm keeps the order)
+      bv[0] = lds64(p2_b);
+#pragma unroll
+      for (int q = 0; q < JT; ++q) av[0][q] = jo[q] != 0xffffffffu ? lds64(ap + jo[q]) : 0.0;
+#pragma unroll
+      for (int ks = 0; ks < kTmaRows / 4; ++ks) {
+        const int cur = ks & 1, nxt = cur ^ 1;
+        if (ks + 1 < kTmaRows / 4) {
+          bv[nxt] = lds64(p2_b + 32 * (ks + 1));
+#pragma unroll
+          for (int q = 0; q < JT; ++q)
+            av[nxt][q] = jo[q] != 0xffffffffu ? lds64(ap + (uint32_t)(sizeof(double) * 4 * (ks + 1) * XS) + jo[q]) : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < JT; ++q)
+          if (jo[q] != 0xffffffffu) dmma_8x8x4(acc[q][0], acc[q][1], av[cur][q], bv[cur]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+    if (producer && b + 2 < nblk) issue(b + 2);
+    __syncwarp();
+    DHMC_PROF(6);                           // 6: P2
   }
+  ring_n = n0 + (uint32_t)nblk;
+  __syncthreads();                          // every warp is done with the ring and the tiles: hand Xᵀr and Σ ll back
+#pragma unroll
+  for (int q = 0; q < JT; ++q) {
+    const int j = (wq + q * MW) * 8 + fr;
+    if (wq < MW && j < D) {
+      sts64(ring_a + (uint32_t)(sizeof(double) * ((2 * fk) * XS + j)), acc[q][0]);        // cb_grad [chain][XS]
+      sts64(ring_a + (uint32_t)(sizeof(double) * ((2 * fk + 1) * XS + j)), acc[q][1]);
+    }
+  }
+  if (wq >= NW - G) {
+#pragma unroll
+    for (int hh = 0; hh < W; ++hh) sts64(eta_a + (uint32_t)(sizeof(double) * ((wq - (NW - G)) * T + 32 * hh + lane)), sl[hh]);   // [chain][T]
+  }
+  __syncthreads();
+  const double sll = active ? lds64(eta_a + (uint32_t)(sizeof(double) * (grp * T + tid))) : 0.0;
+  DHMC_PROF(7);                             // 7: hand-back
+  if (lane == 0) DHMC_PROF_FLUSH(prof ? prof + (size_t)wq * 16 : prof);
   *sll_out = sll;
   return true;
 }
@@ -463,11 +567,15 @@ __device__ __noinline__ bool coop_core_mma(double* sll_out, bool active, int tid
 // and its order are unchanged (η_n sequential in j, (Xᵀr)_j sequential in n, Σ ll lane-strided).
 template <int EPL, int FAM, int WARPS, bool DENSE = false, int PACK = 1, bool MMA = false>
 struct DeviceBackend {
-  static constexpr bool kMma = MMA;      // experimental tensor-core likelihood (packed groups only)
+  static constexpr bool kMma = MMA;      // likelihood rounds on the FP64 tensor cores, X streamed by TMA (packed groups only)
   static_assert(PACK == 1 || (WARPS <= 2 && FAM == DHMC_FAMILY_LOGISTIC), "packed groups: one or two warps per chain, logistic family");
   static constexpr int G = PACK;
   int grp, ctid;                            // warp (= chain group) within the CTA, thread within the CTA
   int* cb_flags; double* cb_beta; double* cb_grad; double* cb_stage;   // CTA-shared exchange area
+  unsigned char* cb_shared;                 // its base (MMA: layout of tma_smem_bytes)
+  uint32_t ring_n;                          // MMA: blocks of X streamed through the ring so far (uniform over the CTA)
+  const double* lXp;                        // MMA: zero-padded row blocks of X, [⌈N/32⌉·32][tma_xs(D)]
+  unsigned long long* prof;                 // cycle accounting of this CTA ([warp][16]) in profiling builds, else null
   double* lll;                              // per-CTA scratch [G][N]: log-likelihood terms (lr holds residuals)
   // geometry: T = 32·WARPS threads per chain, compile-time so that strides fold
   static constexpr int W = WARPS;
@@ -790,7 +898,7 @@ struct DeviceBackend {
       for (int e = 0; e < EPL; ++e) {
         const int i = tid + e * T;
         if (i < D) {
-          if constexpr (MMA) cb_beta[(size_t)grp * kMmaBS + i] = q[e];      // [chain][coefficient]
+          if constexpr (MMA) cb_beta[(size_t)grp * kTmaBS + i] = q[e];      // [chain][coefficient]
           else cb_beta[(size_t)i * G + grp] = q[e];                          // [coefficient][chain]
         }
       }
@@ -798,8 +906,7 @@ struct DeviceBackend {
     double sll = 0.0;
     bool more;
     if constexpr (MMA)
-      more = coop_core_mma<G, W>(&sll, active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
-                                 cb_flags, cb_beta, cb_grad, cb_stage);
+      more = coop_core_tma<G, W>(&sll, active, tid, grp, ctid, D, lN, lXp, ly, lll, cb_shared, ring_n, prof);
     else
       more = coop_core<G, W>(&sll, active, tid, grp, ctid, D, lN, lLd, lX, lXt, ly, lr, lll,
                              cb_flags, cb_beta, cb_grad, cb_stage);
@@ -809,7 +916,7 @@ struct DeviceBackend {
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {
         const int i = tid + e * T;
-        xtr[e] = i < D ? cb_grad[(size_t)grp * (32 * G) + i] : 0.0;
+        xtr[e] = i < D ? cb_grad[(size_t)grp * (MMA ? tma_xs(D) : 32 * G) + i] : 0.0;
       }
     }
     return true;
@@ -871,19 +978,27 @@ struct DeviceBackend {
       for (int n0 = tid; n0 < lN; n0 += 4 * T) {     // four rows per pass for ILP
         double eta[4] = {0.0, 0.0, 0.0, 0.0};
         const double* col = lXt + n0;
-        for (int j = 0; j < D; ++j, col += lLd) {
-          const double bj = xs[j];
+        for (int j0 = 0; j0 < D; j0 += DHMC_LOGIT_CHUNK) {      // blocked dot product: dhmc_logit_eta
+          const int j1 = j0 + DHMC_LOGIT_CHUNK < D ? j0 + DHMC_LOGIT_CHUNK : D;
+          double sacc[4] = {0.0, 0.0, 0.0, 0.0};
+          for (int j = j0; j < j1; ++j, col += lLd) {
+            const double bj = xs[j];
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (n0 + u * T < lN) eta[u] = dhmc_logit_mac(eta[u], __ldg(col + u * T), bj);
+            for (int u = 0; u < 4; ++u)
+              if (n0 + u * T < lN) sacc[u] = dhmc_logit_mac(sacc[u], __ldg(col + u * T), bj);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) eta[u] = j0 == 0 ? sacc[u] : eta[u] + sacc[u];
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int n = n0 + u * T;
           if (n < lN) {
             const double yn = __ldg(ly + n);
-            r[0] = r[0] + dhmc_logit_ll(yn, eta[u]);
-            lr[n] = dhmc_logit_resid(yn, eta[u]);
+            double llv, rv;
+            dhmc_logit_ll_resid(yn, eta[u], &llv, &rv);
+            r[0] = r[0] + llv;
+            lr[n] = rv;
           }
         }
       }

@@ -25,313 +25,25 @@
 #include <vector>
 
 #include "../../include/dhmc.h"
-#include "device_backend.cuh"
+#include "kernels.cuh"      // KArgs, shared-memory planning helpers; the kernels themselves are instantiated in family_tu.cu
 
 using namespace dhmc;
 
-// ------------------------------------------------------------------ kernel args
-struct KArgs {
-  int D, B, T, W;
-  unsigned long long seed;
-  long long chain_offset;
-  double *q, *g, *lq, *p, *minv, *eps;
-  const double* mparams;
-  int* status;
-  int max_depth;
-  double min_delta;
-  unsigned t0;
-  int N;
-  AdaptConfig cfg;
-  const double* p_override;
-  const unsigned* dir_override;
-  double* out_q;
-  dhmc_tree_stats* out_stats;
-  double* out_lq;
-  double* out_eps;
-  double* scratch;
-  size_t scratch_per_cta;  // doubles
-  int n_sm, n_slots;
-  size_t stride;
-  unsigned* counter;
-  unsigned long long* total_steps;
-  double s_init, s_thresh;
-  int s_maxiter;
-  int lf_steps, lf_sign;
-  int strict, randomize;
-  double* out_phase;
-  int chain_begin, chain_end;   // persistent kernels: chains [begin, end) of this launch
-  double *minv_dense, *wt, *covt;   // Symmetric metric: M⁻¹, Wᵀ, co-moments, each [B][D][D]
-  int xs_doubles;               // shared-memory staging vector (0 unless the dense arrays exist)
-  const double *lX, *lXt, *ly;  // logistic regression data
-  double* lr;                   // logistic scratch: [grid][lN] residuals, or per CTA of packed groups [lN][G] residuals + [G][lN] ll terms
-  int lN, lLd;                  // observations, leading dimension of Xᵀ (even)
-};
-
-// Register budget: minimum resident CTAs per SM the compiler must allow for.
-__host__ __device__ constexpr int min_ctas(int W, int EPL) {
-#ifndef DHMC_MINCTAS_W4E8
-#define DHMC_MINCTAS_W4E8 3
-#endif
-  return W == 1 ? 16 : W == 2 ? 8 : W == 4 ? (EPL >= 8 ? DHMC_MINCTAS_W4E8 : 4) : 2;
-}
-
-// packed chain groups (G chains per CTA, one per warp): shared-memory bytes of the CTA-wide
-// exchange area behind the G per-group blocks — flags, β [32G][G], cp.async ring (Xᵀr [G][32G] is
-// handed back in stage 0 of the ring, which is idle between two rounds)
-__host__ __device__ constexpr size_t coop_beta_doubles(int G, bool mma) { return mma ? (size_t)G * kMmaBS : (size_t)32 * G * G; }
-__host__ __device__ constexpr size_t coop_ring_doubles(int G, bool mma) {
-  return (size_t)kCoopStages * (mma ? kMmaStage : coop_stage_doubles(G));
-}
-__host__ __device__ constexpr size_t coop_smem_bytes(int G, bool mma = false) {
-  return 64 + sizeof(double) * (coop_beta_doubles(G, mma) + coop_ring_doubles(G, mma));
-}
-__host__ __device__ inline size_t group_smem_bytes(int W, int n_sm, size_t stride, size_t xs) {
-  return (smem_layout(W, n_sm, stride, xs).total + 15) & ~(size_t)15;
-}
-
-template <int EPL, int FAM, int W, bool DN, int G, bool MM>
-__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G, MM>& b, const KArgs& a,
-                                              unsigned char* smem) {
-  b.ctid = threadIdx.x; b.grp = 0;
-  b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5;
-  b.D = a.D;
-  const SmemLayout L = smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles);
-  b.lX = a.lX; b.lXt = a.lXt; b.ly = a.ly; b.lN = a.lN; b.lLd = a.lLd;
-  b.lr = a.lr ? a.lr + (size_t)blockIdx.x * a.lN : nullptr;
-  b.lll = nullptr; b.cb_flags = nullptr; b.cb_beta = b.cb_grad = b.cb_stage = nullptr;
-  size_t group = blockIdx.x;
-  if constexpr (G > 1) {
-    b.grp = threadIdx.x / (32 * W); b.tid = threadIdx.x % (32 * W); b.warp = b.tid >> 5;
-    group = (size_t)blockIdx.x * G + b.grp;
-    const size_t per = group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles);
-    unsigned char* shared = smem + per * G;
-    b.cb_flags = reinterpret_cast<int*>(shared);
-    b.cb_beta = reinterpret_cast<double*>(shared + 64);
-    b.cb_stage = b.cb_beta + coop_beta_doubles(G, MM);
-    b.cb_grad = b.cb_stage;
-    static_assert(coop_stage_doubles(G) >= 32 * G * G && kMmaStage >= 32 * G * G, "Xᵀr fits in one stage");
-    for (int i = threadIdx.x; i < (int)coop_beta_doubles(G, MM); i += 32 * W * G) b.cb_beta[i] = 0.0;
-    for (int i = threadIdx.x; i < (int)coop_ring_doubles(G, MM); i += 32 * W * G) b.cb_stage[i] = 0.0;
-    b.lr = a.lr + (size_t)blockIdx.x * 2 * G * a.lN;       // residuals [N][G]
-    b.lll = b.lr + (size_t)G * a.lN;                       // ll terms   [G][N]
-    smem += per * b.grp;
-    __syncthreads();
+// kernel lookup, one function per (family, part) translation unit (family_tu.cu)
+#define DHMC_DECL_TU(f, p) const void* dhmc_family_kernel_##f##_##p(int W, int epl, int kernel, int dense);
+DHMC_DECL_TU(0, 0) DHMC_DECL_TU(1, 0) DHMC_DECL_TU(2, 0) DHMC_DECL_TU(3, 0) DHMC_DECL_TU(3, 1) DHMC_DECL_TU(3, 2)
+#undef DHMC_DECL_TU
+// part: 0 = one chain per CTA, 1 = packed chain groups with the FMA likelihood, 2 = packed groups on the tensor cores
+static const void* lookup_kernel(int fam, int part, int W, int epl, KernelId k, bool dense) {
+  switch (fam * 4 + part) {
+    case 0: return dhmc_family_kernel_0_0(W, epl, k, dense);
+    case 4: return dhmc_family_kernel_1_0(W, epl, k, dense);
+    case 8: return dhmc_family_kernel_2_0(W, epl, k, dense);
+    case 12: return dhmc_family_kernel_3_0(W, epl, k, dense);
+    case 13: return dhmc_family_kernel_3_1(W, epl, k, dense);
+    case 14: return dhmc_family_kernel_3_2(W, epl, k, dense);
   }
-  b.xs = reinterpret_cast<double*>(smem + L.xs_off);
-  b.Mrow = nullptr; b.Wt = nullptr; b.covt = nullptr;
-  b.red = reinterpret_cast<double*>(smem + L.red_off);
-  b.red_buf = 0;
-  b.rexp_cache = 0.0; b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;
-  b.ctl = reinterpret_cast<Entry*>(smem + L.ctl_off) + b.warp * (kMaxLevels + 1);
-  b.tops = reinterpret_cast<TopState*>(smem + L.top_off + b.warp * ((sizeof(TopState) + 15) & ~(size_t)15));
-  b.sm_slots = reinterpret_cast<double*>(smem + L.slots_off);
-  b.gl_slots = a.scratch + group * a.scratch_per_cta;
-  b.n_sm = a.n_sm; b.n_slots = a.n_slots;
-  b.slot_tab = reinterpret_cast<double**>(smem + L.tab_off);
-  b.build_slot_table();
-  b.mparams = a.mparams;
-}
-
-// packed groups: every chain group draws its own chains
-template <class B>
-__device__ __forceinline__ int next_chain_group(B& b, unsigned* counter, int* s_misc, int begin) {
-  if constexpr (B::W == 1) {
-    int c = 0;
-    if (b.lane == 0) c = begin + (int)atomicAdd(counter, 1u);
-    return __shfl_sync(0xffffffffu, c, 0);
-  } else {
-    b.group_sync();
-    if (b.tid == 0) s_misc[0] = begin + (int)atomicAdd(counter, 1u);
-    b.group_sync();
-    return s_misc[0];
-  }
-}
-__device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc, int begin) {
-  __syncthreads();
-  if (threadIdx.x == 0) s_misc[0] = begin + (int)atomicAdd(counter, 1u);
-  __syncthreads();
-  return s_misc[0];
-}
-
-template <int EPL, int FAM, int W, bool DN, int G, bool MM>
-__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN, G, MM>& b, const KArgs& a, long c,
-                                           bool with_p) {
-  b.chain = c;
-  b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;   // the randexp batch belongs to one chain
-  const size_t base = (size_t)c * a.D;
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) {
-    const int i = b.tid + e * b.T;
-    const bool ok = i < a.D;
-    b.q[e] = ok ? a.q[base + i] : 0.0;
-    b.g[e] = ok ? a.g[base + i] : 0.0;
-    b.minv[e] = ok ? a.minv[base + i] : 1.0;
-    b.p[e] = (ok && with_p) ? a.p[base + i] : 0.0;
-    b.rhoL[e] = 0.0;
-  }
-  b.lq = a.lq[c];
-  const size_t dd = (size_t)a.D * a.D;
-  if (a.covt) b.covt = a.covt + (size_t)c * dd;
-  if constexpr (DN) {
-    b.Mrow = a.minv_dense + (size_t)c * dd;
-    b.Wt = a.wt + (size_t)c * dd;
-    if (with_p) b.matvec(b.p, b.ps);
-  }
-}
-template <int EPL, int FAM, int W, bool DN, int G, bool MM>
-__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN, G, MM>& b, double* dst,
-                                          const double (&v)[EPL], size_t base, int D) {
-#pragma unroll
-  for (int e = 0; e < EPL; ++e) {
-    const int i = b.tid + e * b.T;
-    if (i < D) dst[base + i] = v[e];
-  }
-}
-
-// ------------------------------------------------------------------ k_nuts
-template <int EPL, int FAM, int W, bool DN, int G, bool MM>
-struct DrawSink {
-  DeviceBackend<EPL, FAM, W, DN, G, MM>& b;
-  const KArgs& a;
-  long c;
-  __device__ __forceinline__ void operator()(int n, const dhmc_tree_stats& ts, double e) {
-    const size_t row = (size_t)c * a.N + n;
-    if (a.out_q) store_vec(b, a.out_q, b.q, row * a.D, a.D);
-    if (b.tid == 0) {
-      if (a.out_stats) a.out_stats[row] = ts;
-      if (a.out_lq) a.out_lq[row] = b.lq;
-      if (a.out_eps) a.out_eps[row] = e;
-    }
-  }
-};
-
-template <int EPL, int FAM, int W, bool DN, int G = 1, bool MM = false>
-__global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nuts(const KArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN, G, MM> b;
-  setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles) : 0) +
-                                       smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
-  for (;;) {
-    int c;
-    if constexpr (G > 1) c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
-    else c = next_chain(a.counter, s_misc, a.chain_begin);
-    if (c >= a.chain_end) break;
-    load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
-                                           a.max_depth, a.min_delta, a.n_slots);
-    DrawSink<EPL, FAM, W, DN, G, MM> sink{b, a, c};
-    const double eps_next = m.run(a.t0, a.N, a.eps[c], a.cfg, a.p_override,
-                                  a.dir_override ? a.dir_override + c : nullptr, sink);
-    const size_t base = (size_t)c * a.D;
-    store_vec(b, a.q, b.q, base, a.D);
-    store_vec(b, a.g, b.g, base, a.D);
-    if (a.cfg.metric == DHMC_METRIC_DIAGONAL) store_vec(b, a.minv, b.minv, base, a.D);
-    if (b.tid == 0) {
-      a.lq[c] = b.lq;
-      a.eps[c] = eps_next;
-      if (m.status) atomicOr(a.status + c, m.status);
-      atomicAdd(a.total_steps, (unsigned long long)m.steps_out);
-    }
-  }
-  b.coop_finish();
-}
-
-// ------------------------------------------------------------------ k_search
-template <int EPL, int FAM, int W, bool DN, int G = 1, bool MM = false>
-__global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_search(const KArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN, G, MM> b;
-  setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles) : 0) +
-                                       smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
-  for (;;) {
-    int c;
-    if constexpr (G > 1) c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
-    else c = next_chain(a.counter, s_misc, a.chain_begin);
-    if (c >= a.chain_end) break;
-    load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
-                                           a.max_depth, a.min_delta, a.n_slots);
-    const double eps = m.find_initial_stepsize(a.s_init, a.s_thresh, a.s_maxiter, a.p_override);
-    if (b.tid == 0) {
-      a.eps[c] = eps;
-      if (m.status) atomicOr(a.status + c, m.status);
-    }
-  }
-  b.coop_finish();
-}
-
-// ------------------------------------------------------------------ k_leapfrog
-// Streaming leapfrog: reads q, p, ∇ℓ, M⁻¹ (32·D B), writes q′, p′, ∇ℓ′ (24·D B).
-template <int EPL, int FAM, int W, bool DN>
-__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_leapfrog(const KArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN> b;
-  setup_backend(b, a, smem);
-  for (long c = a.chain_begin + blockIdx.x; c < a.chain_end; c += gridDim.x) {
-    load_chain(b, a, c, true);
-    const double eps = a.lf_sign >= 0 ? a.eps[c] : -a.eps[c];
-    int flags = 0;
-    for (int s = 0; s < a.lf_steps; ++s) (void)b.leapfrog(eps, &flags);
-    const size_t base = (size_t)c * a.D;
-    store_vec(b, a.q, b.q, base, a.D);
-    store_vec(b, a.p, b.p, base, a.D);
-    store_vec(b, a.g, b.g, base, a.D);
-    if (b.tid == 0) {
-      a.lq[c] = b.lq;
-      if (flags & 1) atomicOr(a.status + c, (int)DHMC_CHAIN_NONFINITE_Q);
-    }
-    if (W > 1) __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------ k_eval
-template <int EPL, int FAM, int W>
-__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_eval(const KArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W> b;
-  setup_backend(b, a, smem);
-  for (long c = a.chain_begin + blockIdx.x; c < a.chain_end; c += gridDim.x) {
-    load_chain(b, a, c, false);
-    double qbad = 0.0;
-    if (a.randomize) {
-      const dm_rng_key key = dm_make_key(a.seed, (uint64_t)(a.chain_offset + c));
-#pragma unroll
-      for (int e = 0; e < EPL; ++e) {
-        const int i = b.tid + e * b.T;
-        b.q[e] = i < a.D ? dm_uniform_elem(key, DHMC_STREAM_Q0, 0, (uint32_t)i) * 4 - 2 : 0.0;
-      }
-    }
-#pragma unroll
-    for (int e = 0; e < EPL; ++e) if (!dm_isfinite(b.q[e])) qbad = 1.0;
-    // raw (unsanitised) validity for the strict check, hamiltonian.jl:205-215
-    int flags = 0;
-    double ks;
-    b.eval_model(false, 0.0, qbad, &ks, &flags);
-    const size_t base = (size_t)c * a.D;
-    store_vec(b, a.q, b.q, base, a.D);
-    store_vec(b, a.g, b.g, base, a.D);
-    if (b.tid == 0) {
-      a.lq[c] = b.lq;
-      if (a.strict && (flags & (1 | 4))) atomicOr(a.status + c, (int)DHMC_CHAIN_BAD_INITIAL);
-    }
-    if (W > 1) __syncthreads();
-  }
-}
-
-// ------------------------------------------------------------------ k_phase
-template <int EPL, int FAM, int W, bool DN>
-__global__ void __launch_bounds__(32 * W, min_ctas(W, EPL)) k_phase(const KArgs a) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN> b;
-  setup_backend(b, a, smem);
-  for (long c = a.chain_begin + blockIdx.x; c < a.chain_end; c += gridDim.x) {
-    load_chain(b, a, c, true);
-    const double H = b.phase_logdensity();
-    if (b.tid == 0) a.out_phase[c] = H;
-    if (W > 1) __syncthreads();
-  }
+  return nullptr;
 }
 
 // ------------------------------------------------------------------ Symmetric metric
@@ -413,6 +125,14 @@ __global__ void k_broadcast_mat(double* dst, const double* src, size_t dd, size_
     dst[i] = src[i % dd];
 }
 
+// Xp[n][j] = X[n][j] for n < N, j < D, zero elsewhere (rows x xs)
+__global__ void k_pad_rows(const double* X, double* Xp, size_t N, size_t D, size_t rows, size_t xs) {
+  const size_t tot = rows * xs;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < tot; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / xs, j = i % xs;
+    Xp[i] = (n < N && j < D) ? X[n * D + j] : 0.0;
+  }
+}
 // Xt[j][n] = X[n][j], rows of Xt padded to ld >= N (pad = 0)
 __global__ void k_transpose(const double* X, double* Xt, size_t N, size_t D, size_t ld) {
   const size_t tot = ld * D;
@@ -471,7 +191,7 @@ struct dhmc_handle {
   dhmc_config cfg;
   int T = 0, W = 0, EPL = 0;
   int G = 1;                        // chains per CTA of the persistent kernels (packed chain groups)
-  bool coop_mma = false;            // experimental: likelihood rounds on the FP64 tensor cores
+  bool coop_mma = false;            // packed groups: likelihood rounds on the FP64 tensor cores, X streamed by TMA
   size_t stride = 0;
   int n_slots = 0, n_sm = 0, grid = 0, sm_count = 0, light_grid = 0;
   size_t smem_bytes = 0, smem_light = 0;
@@ -496,6 +216,7 @@ struct dhmc_handle {
   bool dense = false;               // κ is a Symmetric (dense) metric
   double *minv_dense = nullptr, *wt = nullptr, *covt = nullptr, *dense_tmp = nullptr;
   double *lX = nullptr, *lXt = nullptr, *ly = nullptr, *lr = nullptr;   // logistic regression
+  double* lXp = nullptr;            // … zero-padded row blocks of X for the tensor-core likelihood
   int lN = 0, lLd = 0;
   int reg_ctas[2] = {0, 0};         // occupancy of k_nuts (diag, dense)
   size_t smem_sm = 0, smem_cta_max = 0;
@@ -513,83 +234,6 @@ static std::string g_create_err;
     }                                                                                 \
   } while (0)
 
-template <int W, int EPL, class F>
-static int dispatch_f(int fam, F&& f) {
-  using IW = std::integral_constant<int, W>;
-  using IE = std::integral_constant<int, EPL>;
-  switch (fam) {
-    case DHMC_FAMILY_STD_NORMAL: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_STD_NORMAL>{});
-    case DHMC_FAMILY_DIAG_NORMAL: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_DIAG_NORMAL>{});
-    case DHMC_FAMILY_FUNNEL: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_FUNNEL>{});
-    case DHMC_FAMILY_LOGISTIC: return f(IW{}, IE{}, std::integral_constant<int, DHMC_FAMILY_LOGISTIC>{});
-  }
-  return DHMC_EARG;
-}
-// supported (warps per chain, elements per thread) layouts
-static bool layout_supported(int W, int epl) {
-  if (W == 1) return epl == 1 || epl == 2 || epl == 4 || epl == 8;
-  if (W == 2 || W == 4 || W == 8) return epl == 4 || epl == 8;
-  return false;
-}
-template <class F>
-static int dispatch(int W, int epl, int fam, F&& f) {
-  switch (W * 16 + epl) {
-    case 1 * 16 + 1: return dispatch_f<1, 1>(fam, f);
-    case 1 * 16 + 2: return dispatch_f<1, 2>(fam, f);
-    case 1 * 16 + 4: return dispatch_f<1, 4>(fam, f);
-    case 1 * 16 + 8: return dispatch_f<1, 8>(fam, f);
-    case 2 * 16 + 4: return dispatch_f<2, 4>(fam, f);
-    case 2 * 16 + 8: return dispatch_f<2, 8>(fam, f);
-    case 4 * 16 + 4: return dispatch_f<4, 4>(fam, f);
-    case 4 * 16 + 8: return dispatch_f<4, 8>(fam, f);
-    case 8 * 16 + 4: return dispatch_f<8, 4>(fam, f);
-    case 8 * 16 + 8: return dispatch_f<8, 8>(fam, f);
-  }
-  return DHMC_EARG;
-}
-
-enum KernelId { K_NUTS, K_SEARCH, K_LEAPFROG, K_EVAL, K_PHASE };
-struct dhmc_handle;
-
-// dense (Symmetric metric) kernels are instantiated for the layouts of D <= 512
-constexpr bool dense_layout(int W, int EPL) { return W == 1 || (W == 2) || (W == 4 && EPL == 4); }
-constexpr int kPack = 8;            // packed chain groups: chains per CTA (logistic family, dim <= 256)
-// the layouts choose_layout picks for dim <= 256: one warp per chain up to 128, two above
-constexpr bool packed_layout(int W, int EPL) { return (W == 1 && EPL <= 4) || (W == 2 && EPL == 4); }
-template <int EPL, int FAM, int W>
-static const void* kernel_ptr(KernelId k, bool dense, int G = 1, bool mma = false) {
-  if constexpr (FAM == DHMC_FAMILY_LOGISTIC && packed_layout(W, EPL)) {
-    if (G > 1 && mma) {     // experimental tensor-core likelihood (DHMC_COOP_MMA=1)
-      if (k == K_NUTS) return dense ? (const void*)k_nuts<EPL, FAM, W, true, kPack, true> : (const void*)k_nuts<EPL, FAM, W, false, kPack, true>;
-      if (k == K_SEARCH) return dense ? (const void*)k_search<EPL, FAM, W, true, kPack, true> : (const void*)k_search<EPL, FAM, W, false, kPack, true>;
-    }
-    if (G > 1) {
-      if (k == K_NUTS) return dense ? (const void*)k_nuts<EPL, FAM, W, true, kPack> : (const void*)k_nuts<EPL, FAM, W, false, kPack>;
-      if (k == K_SEARCH) return dense ? (const void*)k_search<EPL, FAM, W, true, kPack> : (const void*)k_search<EPL, FAM, W, false, kPack>;
-    }
-  }
-  if (dense) {
-    if constexpr (dense_layout(W, EPL)) {
-      switch (k) {
-        case K_NUTS: return (const void*)k_nuts<EPL, FAM, W, true>;
-        case K_SEARCH: return (const void*)k_search<EPL, FAM, W, true>;
-        case K_LEAPFROG: return (const void*)k_leapfrog<EPL, FAM, W, true>;
-        case K_PHASE: return (const void*)k_phase<EPL, FAM, W, true>;
-        default: break;
-      }
-    } else {
-      return nullptr;
-    }
-  }
-  switch (k) {
-    case K_NUTS: return (const void*)k_nuts<EPL, FAM, W, false>;
-    case K_SEARCH: return (const void*)k_search<EPL, FAM, W, false>;
-    case K_LEAPFROG: return (const void*)k_leapfrog<EPL, FAM, W, false>;
-    case K_EVAL: return (const void*)k_eval<EPL, FAM, W>;
-    default: return (const void*)k_phase<EPL, FAM, W, false>;
-  }
-}
-
 // rows of N doubles in the logistic scratch: one per CTA of the light kernels, 2·G per CTA
 // (residuals and ll terms of every packed chain) of the persistent kernels
 static size_t lr_rows(const dhmc_handle* h) {
@@ -606,25 +250,18 @@ static int plan(dhmc_handle* h) {
   const size_t xs = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? h->stride : 0;
   const int G = h->G;
   auto heavy_smem = [&](int n_sm) -> size_t {
-    return G > 1 ? (size_t)G * group_smem_bytes(h->W, n_sm, slot_doubles, xs) + coop_smem_bytes(G, h->coop_mma)
+    return G > 1 ? (size_t)G * group_smem_bytes(h->W, n_sm, slot_doubles, xs) + coop_smem_bytes(G, h->coop_mma, (int)h->cfg.dim)
                  : smem_layout(h->W, n_sm, slot_doubles, xs).total;
   };
   struct { size_t total; } L0{heavy_smem(0)};
   h->smem_light = smem_layout(h->W, 0, slot_doubles, xs).total;
   int& reg_ctas = h->reg_ctas[h->dense ? 1 : 0];
   if (reg_ctas == 0) {
-    int rc = dispatch(h->W, h->EPL, h->cfg.family, [&](auto Wc, auto E, auto Fm) -> int {
-      constexpr int WW = decltype(Wc)::value;
-      constexpr int EP = decltype(E)::value;
-      constexpr int FA = decltype(Fm)::value;
-      const void* fn = kernel_ptr<EP, FA, WW>(K_NUTS, h->dense, G, h->coop_mma);
-      if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
-      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L0.total);
-      if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, fn, T * G, L0.total);
-      if (e != cudaSuccess) { h->err = std::string("occupancy query: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
-      return DHMC_OK;
-    });
-    if (rc != DHMC_OK) return rc;
+    const void* fn = lookup_kernel(h->cfg.family, G > 1 ? (h->coop_mma ? 2 : 1) : 0, h->W, h->EPL, K_NUTS, h->dense);
+    if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L0.total);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, fn, T * G, L0.total);
+    if (e != cudaSuccess) { h->err = std::string("occupancy query: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
   }
   if (reg_ctas < 1) { h->err = "kernel does not fit on an SM"; return DHMC_ECUDA; }
   const int ctas = h->cfg.ctas_per_sm > 0 ? std::min(h->cfg.ctas_per_sm, reg_ctas) : reg_ctas;
@@ -662,7 +299,7 @@ static KArgs base_args(dhmc_handle* h) {
   a.chain_begin = 0; a.chain_end = (int)h->cfg.n_chains;
   a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr;
   a.xs_doubles = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? (int)((size_t)h->T * h->EPL) : 0;
-  a.lX = h->lX; a.lXt = h->lXt; a.ly = h->ly; a.lr = h->lr; a.lN = h->lN; a.lLd = h->lLd;
+  a.lX = h->lX; a.lXt = h->lXt; a.ly = h->ly; a.lr = h->lr; a.lN = h->lN; a.lLd = h->lLd; a.lXp = h->lXp;
   return a;
 }
 
@@ -689,21 +326,48 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_st
     if (reset_steps) CK(cudaMemsetAsync(h->total_steps, 0, sizeof(unsigned long long), h->stream));
   }
   if (timing == 1 || timing == 2) CK(cudaEventRecord(h->ev0, h->stream));
-  int rc = dispatch(h->W, h->EPL, h->cfg.family, [&](auto Wc, auto E, auto Fm) -> int {
-    constexpr int WW = decltype(Wc)::value;
-    constexpr int EPL = decltype(E)::value;
-    constexpr int FAM = decltype(Fm)::value;
-    const void* fn = kernel_ptr<EPL, FAM, WW>(k, h->dense, G, h->coop_mma);
+#ifdef DHMC_PROFILE_ROUNDS
+  unsigned long long* prof_buf = nullptr;
+  if (k == K_NUTS && G > 1) {
+    CK(cudaMalloc(&prof_buf, sizeof(unsigned long long) * (size_t)grid * 32 * 16));
+    CK(cudaMemsetAsync(prof_buf, 0, sizeof(unsigned long long) * (size_t)grid * 32 * 16, h->stream));
+    a.prof = prof_buf;
+  }
+#endif
+  {
+    const void* fn = lookup_kernel(h->cfg.family, G > 1 ? (h->coop_mma ? 2 : 1) : 0, h->W, h->EPL, k, h->dense);
     if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
     void* params[] = {(void*)&a};
     e = cudaLaunchKernel(fn, dim3(grid), dim3(h->T * G), params, smem, h->stream);
     if (e != cudaSuccess) { h->err = std::string("cudaLaunchKernel: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
-    return DHMC_OK;
-  });
-  if (rc != DHMC_OK) return rc;
+  }
   h->launches += 1;
+#ifdef DHMC_PROFILE_ROUNDS
+  if (prof_buf) {   // profiling build: dump the per-warp cycle counters of this launch as one JSON line
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<unsigned long long> hp((size_t)grid * 32 * 16);
+    CK(cudaMemcpy(hp.data(), prof_buf, hp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(prof_buf);
+    const char* path = std::getenv("DHMC_PROF_DUMP");
+    if (FILE* f = std::fopen(path ? path : "dhmc_prof.jsonl", "a")) {
+      const int nw = h->T * G / 32;
+      std::fprintf(f, "{\"kernel\": %d, \"grid\": %d, \"warps\": %d, \"dense\": %d, \"sum\": [", (int)k, grid, nw, (int)h->dense);
+      for (int w = 0; w < nw; ++w) {
+        std::fprintf(f, "%s[", w ? ", " : "");
+        for (int i = 0; i < 10; ++i) {
+          unsigned long long sacc = 0;
+          for (int c = 0; c < grid; ++c) sacc += hp[((size_t)c * 32 + w) * 16 + i];
+          std::fprintf(f, "%s%llu", i ? ", " : "", sacc);
+        }
+        std::fprintf(f, "]");
+      }
+      std::fprintf(f, "]}\n");
+      std::fclose(f);
+    }
+  }
+#endif
   if (timing == 1 || timing == 3) CK(cudaEventRecord(h->ev1, h->stream));
   if (timing == 1) return read_timer(h);
   return DHMC_OK;
@@ -758,7 +422,7 @@ int dhmc_destroy(dhmc_handle* h) {
   cudaFree(h->mparams); cudaFree(h->status); cudaFree(h->scratch); cudaFree(h->counter);
   cudaFree(h->total_steps);
   cudaFree(h->minv_dense); cudaFree(h->wt); cudaFree(h->covt); cudaFree(h->dense_tmp);
-  cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr);
+  cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr); cudaFree(h->lXp);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
@@ -790,10 +454,14 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   int pack = 1;
   if (cfg->family == DHMC_FAMILY_LOGISTIC && rt == 0 && cfg->dim <= 32 * kPack) {
     const char* ev = std::getenv("DHMC_PACK");
+    const char* evw = std::getenv("DHMC_PACK_WARPS");     // 1: one warp per chain also for dim 129…256 (8 elements per lane)
+    if (evw && std::atoi(evw) == 1 && cfg->dim > 128) { T = 32; EPL = 8; }
     if (!(ev && std::atoi(ev) == 0) && packed_layout(T / 32, EPL)) pack = kPack;
   }
+  // packed groups evaluate the likelihood on the FP64 tensor cores (coop_core_tma); DHMC_COOP_MMA=0 selects
+  // the FMA formulation (coop_core) — same results bit for bit
   const char* evm = std::getenv("DHMC_COOP_MMA");
-  const bool coop_mma = pack > 1 && evm && std::atoi(evm) == 1 && cfg->dim % 2 == 0;
+  const bool coop_mma = pack > 1 && !(evm && std::atoi(evm) == 0);
   if (T == 0 || EPL == 0) { g_create_err = "dim too large for this build (dim <= 8 * threads_per_chain <= 2048)"; return DHMC_EARG; }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -872,8 +540,8 @@ int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n) {
       const double yv = params[1 + N * D + i];
       if (!(yv >= 0.0 && yv <= 1.0)) { h->err = "dhmc_set_problem: logistic regression needs 0 <= y <= 1"; return DHMC_EARG; }
     }
-    cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr);
-    h->lX = h->lXt = h->ly = h->lr = nullptr;
+    cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr); cudaFree(h->lXp);
+    h->lX = h->lXt = h->ly = h->lr = h->lXp = nullptr;
     const size_t ld = (N + 1) & ~(size_t)1;                 // even leading dimension: 16-byte aligned row segments
     CK(cudaMalloc(&h->lX, sizeof(double) * (N * D + 2)));  // slack for the last 16-byte piece of a tile
     CK(cudaMemsetAsync(h->lX, 0, sizeof(double) * (N * D + 2), h->stream));
@@ -884,6 +552,12 @@ int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n) {
     CK(cudaMemcpyAsync(h->ly, params + 1 + N * D, sizeof(double) * N, cudaMemcpyHostToDevice, h->stream));
     k_transpose<<<1024, 256, 0, h->stream>>>(h->lX, h->lXt, N, D, ld);
     h->launches += 1;
+    if (h->coop_mma) {   // row blocks [32][XS] with zero padding (rows >= N, columns >= D): one bulk copy per block
+      const size_t xs = (size_t)tma_xs((int)D), rows = (N + kTmaRows - 1) / kTmaRows * kTmaRows;
+      CK(cudaMalloc(&h->lXp, sizeof(double) * rows * xs));
+      k_pad_rows<<<1024, 256, 0, h->stream>>>(h->lX, h->lXp, N, D, rows, xs);
+      h->launches += 1;
+    }
     h->lN = (int)N; h->lLd = (int)ld;
     CK(cudaStreamSynchronize(h->stream));
     return DHMC_OK;

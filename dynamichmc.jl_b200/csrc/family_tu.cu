@@ -1,0 +1,14 @@
+// family_tu.cu — instantiates the kernels of ONE log-density family (and one part of it) per
+// translation unit so that the library builds in parallel: nvcc -DDHMC_TU_FAM=<0..3> -DDHMC_TU_PART=<0..2>.
+// The host side (dhmc_b200.cu) reaches the kernels through dhmc_family_kernel_<fam>_<part>().
+#include "kernels.cuh"
+
+#ifndef DHMC_TU_FAM
+#error "compile with -DDHMC_TU_FAM=<family id> -DDHMC_TU_PART=<part>"
+#endif
+#define DHMC_CAT3(a, b, c) a##b##_##c
+#define DHMC_TU_NAME(f, p) DHMC_CAT3(dhmc_family_kernel_, f, p)
+
+const void* DHMC_TU_NAME(DHMC_TU_FAM, DHMC_TU_PART)(int W, int epl, int kernel, int dense) {
+  return dhmc::family_kernel_ptr<DHMC_TU_FAM, DHMC_TU_PART>(W, epl, (dhmc::KernelId)kernel, dense != 0);
+}

@@ -34,7 +34,7 @@
 #endif
 /* heavy transcendental bodies: optionally out of line on the device (code size) */
 #if defined(__CUDACC__) && defined(DHMC_NOINLINE_MATH)
-#define DHMC_HDH __host__ __device__ __noinline__
+#define DHMC_HDH static __host__ __device__ __noinline__
 #else
 #define DHMC_HDH DHMC_HD
 #endif
@@ -206,39 +206,66 @@ static __constant__ double dm_d_logc[128] = DM_TAB_LOGC_INIT;
 #else
 #define DM_TAB(name, i) dm_h_##name[i]
 #endif
-DHMC_HDH double dm_softplus_neg(double d) {
-  if (d != d) return d;
-  if (d == 0.0) return DM_LN2;
-  if (d > 745.2) return 0.0;
-  const double x = -d;
-  const double kd = dm_floor(x * DM_64_INVLN2 + 0.5);
-  const int n = (int)kd;
-  double r = dm_fma(kd, -DM_LN2_64_HI, x);        /* kd * HI is exact */
-  r = dm_fma(kd, -DM_LN2_64_LO, r);               /* |r| <= ln2/128 */
-  const int j = n & 63, k = n >> 6;               /* n = 64 k + j, 0 <= j < 64 */
-  double p = 1.0 / 120.0;
-  p = dm_fma(p, r, 1.0 / 24.0);
-  p = dm_fma(p, r, 1.0 / 6.0);
-  p = dm_fma(p, r, 0.5);
-  p = dm_fma(p * r, r, r);                        /* expm1(r) */
-  const double tj = DM_TAB(exp2, j);
-  const double y = dm_fma(tj, p, tj);             /* 2^(j/64) e^r */
-  const int k1 = k / 2, k2 = k - k1;
-  const double t = (y * dm_pow2i(k1)) * dm_pow2i(k2);   /* exp(-d) */
-  if (d > 36.7368005696771) return t;             /* 1 + t == 1: log1p(t) = t */
-  const double u = 1.0 + t;
-  if (u >= 2.0) return DM_LN2;
-  const int i = (int)((dm_bits(u) >> 45) & 127u);
-  const double ic = DM_TAB(invc, i);
-  const double rr = dm_fma(u, ic, -1.0);          /* |rr| <~ 2^-8 */
-  double q = -1.0 / 6.0;
-  q = dm_fma(q, rr, 1.0 / 5.0);
-  q = dm_fma(q, rr, -1.0 / 4.0);
-  q = dm_fma(q, rr, 1.0 / 3.0);
-  q = dm_fma(q, rr, -0.5);
-  q = dm_fma(q * rr, rr, rr);                     /* log1p(rr) */
-  const double c = t - (u - 1.0);                 /* rounding error of u, exact */
-  return DM_TAB(logc, i) + dm_fma(c, ic, q);
+/* Body shared by the two entry points below: TE(j), TI(i), TL(i) read the exp2 / invc / logc tables;
+ * *t_out receives exp(-d) (it is a by-product: the logistic model's σ(η) reuses it). */
+#define DM_SOFTPLUS_NEG_BODY(TE, TI, TL)                                                        \
+  if (d != d) { *t_out = d; return d; }                                                         \
+  if (d == 0.0) { *t_out = 1.0; return DM_LN2; }                                                \
+  if (d > 745.2) { *t_out = 0.0; return 0.0; }                                                  \
+  const double x = -d;                                                                          \
+  const double kd = dm_floor(x * DM_64_INVLN2 + 0.5);                                           \
+  const int n = (int)kd;                                                                        \
+  double r = dm_fma(kd, -DM_LN2_64_HI, x);        /* kd * HI is exact */                        \
+  r = dm_fma(kd, -DM_LN2_64_LO, r);               /* |r| <= ln2/128 */                          \
+  const int j = n & 63, k = n >> 6;               /* n = 64 k + j, 0 <= j < 64 */               \
+  double p = 1.0 / 120.0;                                                                       \
+  p = dm_fma(p, r, 1.0 / 24.0);                                                                 \
+  p = dm_fma(p, r, 1.0 / 6.0);                                                                  \
+  p = dm_fma(p, r, 0.5);                                                                        \
+  p = dm_fma(p * r, r, r);                        /* expm1(r) */                                \
+  const double tj = TE(j);                                                                      \
+  const double y = dm_fma(tj, p, tj);             /* 2^(j/64) e^r */                            \
+  const int k1 = k / 2, k2 = k - k1;                                                            \
+  const double t = (y * dm_pow2i(k1)) * dm_pow2i(k2);   /* exp(-d) */                           \
+  *t_out = t;                                                                                   \
+  if (d > 36.7368005696771) return t;             /* 1 + t == 1: log1p(t) = t */                \
+  const double u = 1.0 + t;                                                                     \
+  if (u >= 2.0) return DM_LN2;                                                                  \
+  const int i = (int)((dm_bits(u) >> 45) & 127u);                                               \
+  const double ic = TI(i);                                                                      \
+  const double rr = dm_fma(u, ic, -1.0);          /* |rr| <~ 2^-8 */                            \
+  double q = -1.0 / 6.0;                                                                        \
+  q = dm_fma(q, rr, 1.0 / 5.0);                                                                 \
+  q = dm_fma(q, rr, -1.0 / 4.0);                                                                \
+  q = dm_fma(q, rr, 1.0 / 3.0);                                                                 \
+  q = dm_fma(q, rr, -0.5);                                                                      \
+  q = dm_fma(q * rr, rr, rr);                     /* log1p(rr) */                               \
+  const double c = t - (u - 1.0);                 /* rounding error of u, exact */              \
+  return TL(i) + dm_fma(c, ic, q);
+
+#define DM_TE_DEFAULT(j) DM_TAB(exp2, j)
+#define DM_TI_DEFAULT(i) DM_TAB(invc, i)
+#define DM_TL_DEFAULT(i) DM_TAB(logc, i)
+/* softplus(-d) and exp(-d); tables from constant memory on the device (uniform indices: one access) */
+DHMC_HDH double dm_softplus_neg_exp(double d, double* t_out) {
+  DM_SOFTPLUS_NEG_BODY(DM_TE_DEFAULT, DM_TI_DEFAULT, DM_TL_DEFAULT)
+}
+DHMC_HD double dm_softplus_neg(double d) {
+  double t;
+  return dm_softplus_neg_exp(d, &t);
+}
+/* Same arithmetic with the tables behind a pointer, [exp2 (64) | invc (128) | logc (128)] — for code whose
+ * lanes look up DIFFERENT entries (a copy in shared memory avoids the serialised constant-cache accesses). */
+#define DM_TABS_DOUBLES 320
+#define DM_TE_PTR(j) tabs[j]
+#define DM_TI_PTR(i) tabs[64 + (i)]
+#define DM_TL_PTR(i) tabs[192 + (i)]
+DHMC_HD double dm_softplus_neg_exp_tabs(double d, double* t_out, const double* tabs) {
+  DM_SOFTPLUS_NEG_BODY(DM_TE_PTR, DM_TI_PTR, DM_TL_PTR)
+}
+/* the default tables as one array in the layout above (host side: static data; device: constant memory) */
+DHMC_HD double dm_tabs_entry(int i) {
+  return i < 64 ? DM_TAB(exp2, i) : i < 192 ? DM_TAB(invc, i - 64) : DM_TAB(logc, i - 192);
 }
 
 /* log(exp(a)+exp(b)), LogExpFunctions.logaddexp semantics

@@ -14,9 +14,9 @@
  *               l = -v^2/18 - 1/2 e^{-v} sum x_i^2 - (D-1)/2 v
  *   LOGISTIC    logistic regression with a N(0, I) prior, X [N x p], y in {0,1}:
  *               eta = X beta;  l = sum_n [y_n eta_n - log1pexp(eta_n)] - 1/2 |beta|^2
- *               grad = X' (y - sigma(eta)) - beta
- *               params = [N, X row-major (N*p), y (N)];  eta_n and (X' r)_j are sequential fused
- *               multiply-adds over j resp. n, the two scalar sums use the canonical reduction.
+ *               grad = X' (y - sigma(eta)) - beta      (ll term and sigma share one exponential: dhmc_logit_ll_resid)
+ *               params = [N, X row-major (N*p), y (N)];  (X' r)_j is a sequential chain of fused multiply-adds
+ *               over n, eta_n a blocked one over j (dhmc_logit_eta), the two scalar sums use the canonical reduction.
  */
 #ifndef DHMC_MODELS_H
 #define DHMC_MODELS_H
@@ -62,13 +62,43 @@ DHMC_HD double dhmc_funnel_grad(int i, double x, double v, double ev, double S,
 /* --- LOGISTIC */
 /* one multiply-accumulate of η_n = Σ_j X_nj β_j and of (Xᵀr)_j = Σ_n X_nj r_n: fused, as a BLAS would */
 DHMC_HD double dhmc_logit_mac(double acc, double x, double b) { return dm_fma(x, b, acc); }
-DHMC_HD double dhmc_logit_sigma(double eta) { return 1.0 / (1.0 + dm_exp(-eta)); }
-/* y·η − log(1+e^η) with log(1+e^η) = max(η,0) + log(1+e^{−|η|}): one table-driven softplus (absolute
- * accuracy, no division) instead of log1p(exp(η)) */
-DHMC_HD double dhmc_logit_ll(double y, double eta) {
-  return y * eta - ((eta > 0.0 ? eta : 0.0) + dm_softplus_neg(dm_fabs(eta)));
+/* η_n is a blocked dot product (again as a BLAS would): sequential fused multiply-adds within chunks of
+ * DHMC_LOGIT_CHUNK coefficients, the chunk sums added in increasing order:  η = ((s₀ + s₁) + s₂) + …
+ * (dim <= 64: one plain sequential sum).  The chunks are independent accumulation chains, which is what lets
+ * the tensor-core path spread one row tile over several warps. */
+#define DHMC_LOGIT_CHUNK 64
+DHMC_HD double dhmc_logit_eta(const double* xrow, const double* beta, int D) {
+  double eta = 0.0;
+  for (int j0 = 0; j0 < D; j0 += DHMC_LOGIT_CHUNK) {
+    const int j1 = j0 + DHMC_LOGIT_CHUNK < D ? j0 + DHMC_LOGIT_CHUNK : D;
+    double sacc = 0.0;
+    for (int j = j0; j < j1; ++j) sacc = dhmc_logit_mac(sacc, xrow[j], beta[j]);
+    eta = j0 == 0 ? sacc : eta + sacc;
+  }
+  return eta;
 }
-DHMC_HD double dhmc_logit_resid(double y, double eta) { return y - dhmc_logit_sigma(eta); }
+/* ll term y·η − log(1+e^η) and residual y − σ(η) from ONE exponential t = e^{−|η|}:
+ *   log(1+e^η) = max(η,0) + log(1+t)   (table-driven softplus, absolute accuracy, no division)
+ *   σ(η) = 1/(1+t) for η >= 0, t/(1+t) for η < 0   (no cancellation; one correctly rounded division) */
+DHMC_HD void dhmc_logit_finish(double y, double eta, double sp, double t, double* ll, double* resid) {
+  *ll = y * eta - ((eta > 0.0 ? eta : 0.0) + sp);
+  const double u = 1.0 + t;
+  const double s = (eta >= 0.0 ? 1.0 : t) / u;
+  *resid = y - s;
+}
+DHMC_HD void dhmc_logit_ll_resid(double y, double eta, double* ll, double* resid) {
+  double t;
+  const double sp = dm_softplus_neg_exp(dm_fabs(eta), &t);
+  dhmc_logit_finish(y, eta, sp, t, ll, resid);
+}
+/* same values with the math tables behind a pointer (dm_softplus_neg_exp_tabs) */
+DHMC_HD void dhmc_logit_ll_resid_tabs(double y, double eta, double* ll, double* resid, const double* tabs) {
+  double t;
+  const double sp = dm_softplus_neg_exp_tabs(dm_fabs(eta), &t, tabs);
+  dhmc_logit_finish(y, eta, sp, t, ll, resid);
+}
+DHMC_HD double dhmc_logit_ll(double y, double eta) { double l, r; dhmc_logit_ll_resid(y, eta, &l, &r); return l; }
+DHMC_HD double dhmc_logit_resid(double y, double eta) { double l, r; dhmc_logit_ll_resid(y, eta, &l, &r); return r; }
 DHMC_HD double dhmc_logit_lq(double sum_ll, double sum_b2) { return sum_ll - 0.5 * sum_b2; }
 DHMC_HD double dhmc_logit_grad(double xtr, double beta) { return xtr - beta; }
 

@@ -113,9 +113,8 @@ struct HostBackend {
         const double* X = params + 1; const double* y = X + (size_t)N * D;
         vec r(N), ll(N);
         for (int n = 0; n < N; ++n) {
-          double eta = 0.0;
-          for (int j = 0; j < D; ++j) eta = dhmc_logit_mac(eta, X[(size_t)n * D + j], q[j]);
-          ll[n] = dhmc_logit_ll(y[n], eta); r[n] = dhmc_logit_resid(y[n], eta);
+          const double eta = dhmc_logit_eta(X + (size_t)n * D, &q[0], D);
+          dhmc_logit_ll_resid(y[n], eta, &ll[n], &r[n]);
         }
         double sll = canon_sum(T, N, [&](int n) { return ll[n]; });
         double sb = canon_sum(T, D, [&](int i) { return q[i] * q[i]; });

@@ -446,12 +446,14 @@ def test_logistic_packed_groups_equal_one_chain_per_cta(pkg, N, p, K, M):
         r["engine"].close()
 
 
-@pytest.mark.skipif(os.environ.get("DHMC_TEST_EXPERIMENTAL") != "1",
-                    reason="experimental tensor-core likelihood (DHMC_COOP_MMA=1): compiled, not yet validated on hardware")
-@pytest.mark.parametrize("N,p,K", [(300, 20, 21), (1100, 130, 9), (2000, 256, 16)])
-def test_logistic_mma_likelihood_equals_fma_loops(pkg, monkeypatch, N, p, K):
+@pytest.mark.parametrize("N,p,K,warps", [(300, 20, 21, 0), (1100, 130, 9, 0), (2000, 256, 16, 0), (999, 255, 11, 1),
+                                          (1037, 77, 19, 0), (31, 5, 8, 0)])
+def test_logistic_mma_likelihood_equals_fma_loops(pkg, monkeypatch, N, p, K, warps):
     """mma.sync.m8n8k4.f64 accumulates as sequential FMAs (profiles/r01_dmma_order_probe.txt), so the
-    tensor-core version of the cooperative likelihood must reproduce the default path bit for bit."""
+    tensor-core / TMA likelihood (the default of packed chain groups) must reproduce the FMA formulation
+    bit for bit — odd dimensions, ragged last row block, one or two warps per chain."""
+    if warps:
+        monkeypatch.setenv("DHMC_PACK_WARPS", str(warps))
     ℓ, _ = pkg.LogisticRegression.synthetic(N=N, p=p, seed=N + p)
     stages = pkg.default_warmup_stages(M=pkg.Diagonal, init_steps=20, middle_steps=20, doubling_stages=1,
                                        terminating_steps=20)
