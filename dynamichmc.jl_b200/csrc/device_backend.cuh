@@ -347,6 +347,133 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+// One chunk (up to 16 k-steps = four groups of four) of D[8 × 8] += A[8 × 4] · B[4 × 8] for TWO row tiles that share
+// the B fragments: A from shared addresses ap / ap2 (+32 bytes per k-step), B from bp (+32 bytes per k-step).
+// Two fragment sets in ping-pong; every statement is a volatile asm, so the order below is the issue order and the
+// loads run one group ahead of the DMMAs that consume them.
+__device__ __forceinline__ void mma_chunk_2tiles(uint32_t ap, uint32_t ap2, uint32_t bp, int ngr,
+                                                 double& c0, double& c1, double& d0, double& d1) {
+  double fa[2][4], fa2[2][4], fb[2][4];
+#define DHMC_P1_LOAD(set, g)                                                                   \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                              \
+    fa[set][u] = lds64(ap + 128 * (g) + 32 * u); fa2[set][u] = lds64(ap2 + 128 * (g) + 32 * u); \
+    fb[set][u] = lds64(bp + 128 * (g) + 32 * u);                                               \
+  }
+#define DHMC_P1_MMA(set)                                                                       \
+  _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                              \
+    dmma_8x8x4(c0, c1, fa[set][u], fb[set][u]); dmma_8x8x4(d0, d1, fa2[set][u], fb[set][u]);   \
+  }
+  DHMC_P1_LOAD(0, 0)
+  if (ngr > 1) { DHMC_P1_LOAD(1, 1) }
+  DHMC_P1_MMA(0)
+  if (ngr > 2) { DHMC_P1_LOAD(0, 2) }
+  if (ngr > 1) { DHMC_P1_MMA(1) }
+  if (ngr > 3) { DHMC_P1_LOAD(1, 3) }
+  if (ngr > 2) { DHMC_P1_MMA(0) }
+  if (ngr > 3) { DHMC_P1_MMA(1) }
+#undef DHMC_P1_LOAD
+#undef DHMC_P1_MMA
+}
+
+// ---- the Symmetric metric's mat-vec p♯ = M⁻¹p (hamiltonian.jl:110,117) of a packed CTA on the FP64 tensor cores ----
+// Inside the tree all chains of a CTA need M⁻¹·(their own vector) at the same point of the leapfrog step, so the CTA does
+// them one after the other with all its MMA warps: chain c's padded matrix Mp_c [⌈D/32⌉·32][XS] (per-chain metric, as in the
+// reference: this is a GEMV, the MMA's n-dimension carries the same vector eight times) streams through the likelihood's
+// TMA ring in blocks of 32 rows; per block the 8 MMA warps run the P1 scheme (4 row tiles × 4 chunks of 64 columns, the
+// blocked dot product dm_blocked_dot), the chunk sums of all rows are collected in shared memory and added in order when
+// the chain's last block is done.  x is published in the β area [chain][kTmaBS] and y handed back in place.
+// Returns false when no warp of the CTA is active any more.
+template <int G, int W>
+__device__ __noinline__ bool coop_matvec_tma(bool active, long chain, int tid, int grp, int ctid, int D,
+                                             const double* __restrict__ Mp, unsigned char* shared, uint32_t& ring_n) {
+  constexpr int NT = 32 * W * G;
+  constexpr int NW = W * G;
+  constexpr int MW = 8;
+  int* cb_flags = reinterpret_cast<int*>(shared);
+  int* cb_chain = reinterpret_cast<int*>(shared + 32);        // [G] chain index of every group (metric lookup)
+  uint64_t* full = reinterpret_cast<uint64_t*>(shared + 64);
+  uint64_t* empty = full + kTmaStages;
+  const uint32_t sh = smem_u32(shared);
+  const uint32_t beta_a = sh + (uint32_t)tma_beta_off();
+  const uint32_t part_a = sh + (uint32_t)tma_eta_off(G);      // chunk sums [chunk][256 rows] (the idle η / residual tiles)
+  const uint32_t ring_a = sh + (uint32_t)tma_ring_off(G);
+  double* ring = reinterpret_cast<double*>(shared + tma_ring_off(G));
+  const int lane = ctid & 31, wq = ctid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  if (tid == 0) { cb_flags[grp] = active ? 1 : 0; cb_chain[grp] = (int)chain; }
+  __syncthreads();
+  unsigned amask = 0;
+#pragma unroll
+  for (int gg = 0; gg < G; ++gg)
+    if (cb_flags[gg]) amask |= 1u << gg;
+  if (amask == 0) return false;
+  const int XS = tma_xs(D);
+  const int nbc = (D + kTmaRows - 1) / kTmaRows;              // row blocks per chain
+  const int rows_pad = nbc * kTmaRows;
+  const int ng = (D + 15) >> 4, nch = (D + DHMC_DOT_CHUNK - 1) / DHMC_DOT_CHUNK;
+  const int nact = __popc(amask);
+  const int nblk = nact * nbc;
+  const uint32_t stage_bytes = (uint32_t)(sizeof(double) * kTmaRows * XS);
+  const bool producer = (wq == NW - 1) && (lane == 0);
+  const uint32_t n0 = ring_n;
+  auto nth_chain = [&](int ci) { unsigned m = amask; for (int i = 0; i < ci; ++i) m &= m - 1; return __ffs((int)m) - 1; };
+  auto issue = [&](int b) {
+    const uint32_t n = n0 + (uint32_t)b;
+    const int s = (int)(n & 1u);
+    const int c = nth_chain(b / nbc), kb = b % nbc;
+    mbar_wait(empty + s, ((n >> 1) & 1u) ^ 1u);
+    mbar_expect_tx(full + s, stage_bytes);
+    const uint32_t piece = stage_bytes / kTmaPieces;
+    char* dst = reinterpret_cast<char*>(ring + (size_t)s * kTmaRows * XS);
+    const char* src = reinterpret_cast<const char*>(Mp + ((size_t)cb_chain[c] * rows_pad + (size_t)kb * kTmaRows) * XS);
+#pragma unroll
+    for (int pc = 0; pc < kTmaPieces; ++pc) bulk_g2s(dst + (size_t)pc * piece, src + (size_t)pc * piece, piece, full + s);
+  };
+  if (producer) {
+    fence_proxy_async();
+    issue(0);
+    if (nblk > 1) issue(1);
+  }
+  __syncwarp();
+  const int pc1 = wq & 3, mp = (wq >> 2) & 1;
+  const int g0 = 4 * pc1, g1 = (4 * pc1 + 4 < ng) ? 4 * pc1 + 4 : ng;
+  const uint32_t p1_a = (uint32_t)(sizeof(double) * ((16 * mp + fr) * XS + fk)) + 128 * g0;
+  int b = 0;
+  for (int ci = 0; ci < nact; ++ci) {
+    const int c = nth_chain(ci);
+    const uint32_t bp = beta_a + (uint32_t)(sizeof(double) * (c * kTmaBS + fk)) + 128 * g0;    // x_c[k] for every n: broadcast
+    for (int kb = 0; kb < nbc; ++kb, ++b) {
+      const uint32_t n = n0 + (uint32_t)b;
+      const int s = (int)(n & 1u);
+      mbar_wait(full + s, (n >> 1) & 1u);
+      if (wq < MW && g0 < g1) {
+        const uint32_t ap = ring_a + (uint32_t)s * stage_bytes + p1_a;
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        mma_chunk_2tiles(ap, ap + (uint32_t)(sizeof(double) * 8 * XS), bp, g1 - g0, c0, c1, d0, d1);
+        if (fk == 0) {                        // columns n = 0 (all eight columns hold the same dot products)
+          const uint32_t pa = part_a + (uint32_t)(sizeof(double) * (pc1 * 256 + kb * kTmaRows + 16 * mp + fr));
+          sts64(pa, c0);
+          sts64(pa + 64, d0);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+      if (producer && b + 2 < nblk) issue(b + 2);
+      __syncwarp();
+    }
+    __syncthreads();                          // all chunk sums of chain c are in place
+    for (int i = ctid; i < D; i += NT) {
+      const uint32_t pa = part_a + (uint32_t)(sizeof(double) * i);
+      double y = lds64(pa);
+      for (int cc = 1; cc < nch; ++cc) y = y + lds64(pa + (uint32_t)(sizeof(double) * 256 * cc));
+      sts64(beta_a + (uint32_t)(sizeof(double) * (c * kTmaBS + i)), y);     // y_c replaces x_c
+    }
+    __syncthreads();
+  }
+  ring_n = n0 + (uint32_t)nblk;
+  return true;
+}
+
 // optional cycle accounting of the round's phases (build with -DDHMC_PROFILE_ROUNDS; variants/ only)
 #ifdef DHMC_PROFILE_ROUNDS
 #define DHMC_PROF_DECL long long pf_t = clock64(), pf_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -447,31 +574,9 @@ __device__ __noinline__ bool coop_core_tma(double* sll_out, bool active, int tid
     if (wq < MW) {
       const int g0 = 4 * pc1, g1 = (4 * pc1 + 4 < ng) ? 4 * pc1 + 4 : ng;    // k-step groups of this chunk
       if (g0 < g1) {
-        const uint32_t ap = xt + p1_a + 128 * g0, ap2 = ap + (uint32_t)(sizeof(double) * 8 * XS), bp = p1_b + 128 * g0;
+        const uint32_t ap = xt + p1_a + 128 * g0;
         double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
-        // two fragment sets in ping-pong (every statement is a volatile asm: the order below is the issue order,
-        // loads run one group of four k-steps ahead of the DMMAs that consume them)
-        double fa[2][4], fa2[2][4], fb[2][4];
-#define DHMC_P1_LOAD(set, g)                                                                   \
-        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
-          fa[set][u] = lds64(ap + 128 * (g) + 32 * u); fa2[set][u] = lds64(ap2 + 128 * (g) + 32 * u); \
-          fb[set][u] = lds64(bp + 128 * (g) + 32 * u);                                         \
-        }
-#define DHMC_P1_MMA(set)                                                                       \
-        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                        \
-          dmma_8x8x4(c0, c1, fa[set][u], fb[set][u]); dmma_8x8x4(d0, d1, fa2[set][u], fb[set][u]); \
-        }
-        const int ngr = g1 - g0;            // 1 … 4
-        DHMC_P1_LOAD(0, 0)
-        if (ngr > 1) { DHMC_P1_LOAD(1, 1) }
-        DHMC_P1_MMA(0)
-        if (ngr > 2) { DHMC_P1_LOAD(0, 2) }
-        if (ngr > 1) { DHMC_P1_MMA(1) }
-        if (ngr > 3) { DHMC_P1_LOAD(1, 3) }
-        if (ngr > 2) { DHMC_P1_MMA(0) }
-        if (ngr > 3) { DHMC_P1_MMA(1) }
-#undef DHMC_P1_LOAD
-#undef DHMC_P1_MMA
+        mma_chunk_2tiles(ap, ap + (uint32_t)(sizeof(double) * 8 * XS), p1_b + 128 * g0, g1 - g0, c0, c1, d0, d1);
         const uint32_t ea = eta_a + (uint32_t)(sizeof(double) * (pc1 * G * kTmaES + 16 * mp + fr));
         sts64(ea + (uint32_t)(sizeof(double) * (2 * fk) * kTmaES), c0);
         sts64(ea + (uint32_t)(sizeof(double) * (2 * fk + 1) * kTmaES), c1);
@@ -576,6 +681,7 @@ struct DeviceBackend {
   uint32_t ring_n;                          // MMA: blocks of X streamed through the ring so far (uniform over the CTA)
   const double* lXp;                        // MMA: zero-padded row blocks of X, [⌈N/32⌉·32][tma_xs(D)]
   unsigned long long* prof;                 // cycle accounting of this CTA ([warp][16]) in profiling builds, else null
+  const double* Mp;                         // MMA + Symmetric metric: padded M⁻¹ of all chains, [chain][⌈D/32⌉·32][tma_xs(D)]
   double* lll;                              // per-CTA scratch [G][N]: log-likelihood terms (lr holds residuals)
   // geometry: T = 32·WARPS threads per chain, compile-time so that strides fold
   static constexpr int W = WARPS;
@@ -761,8 +867,9 @@ struct DeviceBackend {
     else __syncthreads();
   }
   // y = M⁻¹ x for this chain (Symmetric M⁻¹ * v, hamiltonian.jl:110): x is staged in shared
-  // memory, every thread accumulates its own rows over j = 0..D-1 in increasing j (the
-  // oracle's order); row j of M is read coalesced (M is symmetric).
+  // memory, every thread accumulates its own rows as a blocked dot product over j (dm_blocked_dot:
+  // sequential FMAs within chunks of 64, chunk sums added in order — the oracle's order, and the order of the
+  // tensor-core version coop_matvec_tma); row j of M is read coalesced (M is symmetric).
   __device__ __forceinline__ void matvec(const double (&x)[EPL], double (&y)[EPL]) {
 #pragma unroll
     for (int e = 0; e < EPL; ++e) xs[tid + e * T] = x[e];
@@ -771,11 +878,20 @@ struct DeviceBackend {
 #pragma unroll
     for (int e = 0; e < EPL; ++e) acc[e] = 0.0;
     const double* row = Mrow + tid;
-    for (int j = 0; j < D; ++j, row += D) {
-      const double xj = xs[j];
+    for (int j0 = 0; j0 < D; j0 += DHMC_DOT_CHUNK) {
+      const int j1 = j0 + DHMC_DOT_CHUNK < D ? j0 + DHMC_DOT_CHUNK : D;
+      double sacc[EPL];
 #pragma unroll
-      for (int e = 0; e < EPL; ++e)
-        if (tid + e * T < D) acc[e] = acc[e] + __ldg(row + e * T) * xj;
+      for (int e = 0; e < EPL; ++e) sacc[e] = 0.0;
+#pragma unroll 4
+      for (int j = j0; j < j1; ++j, row += D) {
+        const double xj = xs[j];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e)
+          if (tid + e * T < D) sacc[e] = dm_fma(__ldg(row + e * T), xj, sacc[e]);
+      }
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) acc[e] = j0 == 0 ? sacc[e] : acc[e] + sacc[e];
     }
 #pragma unroll
     for (int e = 0; e < EPL; ++e) y[e] = acc[e];
@@ -921,12 +1037,35 @@ struct DeviceBackend {
     }
     return true;
   }
-  // a warp without further chains keeps attending the CTA's likelihood rounds
+  // packed groups, Symmetric metric, tensor-core build: y = M⁻¹x of all chains of the CTA (coop_matvec_tma)
+  static constexpr bool kCoopMatvec = DENSE && PACK > 1 && MMA;
+  __device__ __forceinline__ void coop_matvec(const double (&x)[EPL], double (&y)[EPL]) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int i = tid + e * T;
+      if (i < D) cb_beta[(size_t)grp * kTmaBS + i] = x[e];
+    }
+    coop_matvec_tma<G, W>(true, chain, tid, grp, ctid, D, Mp, cb_shared, ring_n);
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int i = tid + e * T;
+      y[e] = i < D ? cb_beta[(size_t)grp * kTmaBS + i] : 0.0;
+    }
+  }
+  // a warp without further chains keeps attending the CTA's cooperative calls, in the order a leapfrog step makes
+  // them (M⁻¹pₘ, likelihood, M⁻¹p′ with the cooperative mat-vec; the likelihood alone otherwise)
   __device__ __forceinline__ void coop_finish() {
     if constexpr (PACK > 1) {
       double dummy_ll = 0.0;
       double dummy[EPL];
-      while (coop_round(false, dummy_ll, dummy)) {}
+      if constexpr (kCoopMatvec) {
+        while (coop_matvec_tma<G, W>(false, 0, tid, grp, ctid, D, Mp, cb_shared, ring_n)) {
+          coop_round(false, dummy_ll, dummy);
+          coop_matvec_tma<G, W>(false, 0, tid, grp, ctid, D, Mp, cb_shared, ring_n);
+        }
+      } else {
+        while (coop_round(false, dummy_ll, dummy)) {}
+      }
     }
   }
 
@@ -1122,7 +1261,7 @@ struct DeviceBackend {
       double vel[EPL];
 #pragma unroll
       for (int e = 0; e < EPL; ++e) p[e] = p[e] + h * g[e];       // pₘ                        :277
-      matvec(p, vel);                                             // ∇kinetic_energy = M⁻¹ pₘ  :117
+      if constexpr (kCoopMatvec) coop_matvec(p, vel); else matvec(p, vel);   // ∇kinetic_energy = M⁻¹ pₘ  :117
 #pragma unroll
       for (int e = 0; e < EPL; ++e) {
         q[e] = q[e] + eps * vel[e];                               // q′                        :278
@@ -1130,7 +1269,7 @@ struct DeviceBackend {
       }
       double ksum;
       eval_model(true, h, qbad, &ksum, flags);                    // Q′, p′                    :279-280
-      matvec(p, ps);                                              // p♯′ = M⁻¹ p′ (K and turn statistics)
+      if constexpr (kCoopMatvec) coop_matvec(p, ps); else matvec(p, ps);     // p♯′ = M⁻¹ p′ (K and turn statistics)
       double r[1] = {kinetic_partial()};
       reduce(r);
       return hamiltonian_logdensity(lq, r[0]);

@@ -125,6 +125,14 @@ __global__ void k_broadcast_mat(double* dst, const double* src, size_t dd, size_
     dst[i] = src[i % dd];
 }
 
+// Mp[c][i][j] = M[c][i][j] for i, j < D, zero elsewhere ([B][rows][xs])
+__global__ void k_pad_metric(const double* M, double* Mp, size_t D, size_t rows, size_t xs, size_t B) {
+  const size_t per = rows * xs, tot = per * B;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t c = t / per, r = t % per, i = r / xs, j = r % xs;
+    Mp[t] = (i < D && j < D) ? M[c * D * D + i * D + j] : 0.0;
+  }
+}
 // Xp[n][j] = X[n][j] for n < N, j < D, zero elsewhere (rows x xs)
 __global__ void k_pad_rows(const double* X, double* Xp, size_t N, size_t D, size_t rows, size_t xs) {
   const size_t tot = rows * xs;
@@ -215,6 +223,7 @@ struct dhmc_handle {
   bool has_position = false, has_eps = false;
   bool dense = false;               // κ is a Symmetric (dense) metric
   double *minv_dense = nullptr, *wt = nullptr, *covt = nullptr, *dense_tmp = nullptr;
+  double* minv_pad = nullptr;       // packed groups on the tensor cores: zero-padded row blocks of every chain's M⁻¹
   double *lX = nullptr, *lXt = nullptr, *ly = nullptr, *lr = nullptr;   // logistic regression
   double* lXp = nullptr;            // … zero-padded row blocks of X for the tensor-core likelihood
   int lN = 0, lLd = 0;
@@ -297,7 +306,7 @@ static KArgs base_args(dhmc_handle* h) {
   a.n_sm = h->n_sm; a.n_slots = h->n_slots; a.stride = h->stride * (h->dense ? 2 : 1);
   a.counter = h->counter; a.total_steps = h->total_steps;
   a.chain_begin = 0; a.chain_end = (int)h->cfg.n_chains;
-  a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr;
+  a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr; a.minv_pad = h->minv_pad;
   a.xs_doubles = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? (int)((size_t)h->T * h->EPL) : 0;
   a.lX = h->lX; a.lXt = h->lXt; a.ly = h->ly; a.lr = h->lr; a.lN = h->lN; a.lLd = h->lLd; a.lXp = h->lXp;
   return a;
@@ -421,7 +430,7 @@ int dhmc_destroy(dhmc_handle* h) {
   cudaFree(h->q); cudaFree(h->g); cudaFree(h->lq); cudaFree(h->p); cudaFree(h->minv); cudaFree(h->eps);
   cudaFree(h->mparams); cudaFree(h->status); cudaFree(h->scratch); cudaFree(h->counter);
   cudaFree(h->total_steps);
-  cudaFree(h->minv_dense); cudaFree(h->wt); cudaFree(h->covt); cudaFree(h->dense_tmp);
+  cudaFree(h->minv_dense); cudaFree(h->wt); cudaFree(h->covt); cudaFree(h->dense_tmp); cudaFree(h->minv_pad);
   cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr); cudaFree(h->lXp);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -454,8 +463,10 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   int pack = 1;
   if (cfg->family == DHMC_FAMILY_LOGISTIC && rt == 0 && cfg->dim <= 32 * kPack) {
     const char* ev = std::getenv("DHMC_PACK");
-    const char* evw = std::getenv("DHMC_PACK_WARPS");     // 1: one warp per chain also for dim 129…256 (8 elements per lane)
-    if (evw && std::atoi(evw) == 1 && cfg->dim > 128) { T = 32; EPL = 8; }
+    // one warp per chain (8 elements per lane above dim 128): eight warps at 255 registers — the tensor-core rounds
+    // need only two warps per sub-partition, and the state machine does not spill; DHMC_PACK_WARPS=2: two warps per chain
+    const char* evw = std::getenv("DHMC_PACK_WARPS");
+    if (!(evw && std::atoi(evw) == 2) && cfg->dim > 128) { T = 32; EPL = 8; }
     if (!(ev && std::atoi(ev) == 0) && packed_layout(T / 32, EPL)) pack = kPack;
   }
   // packed groups evaluate the likelihood on the FP64 tensor cores (coop_core_tma); DHMC_COOP_MMA=0 selects
@@ -601,6 +612,10 @@ static int ensure_dense(dhmc_handle* h) {
   const int fgrid = (int)std::min<size_t>((size_t)h->sm_count * 4, B);
   CK(cudaMalloc(&h->dense_tmp, sizeof(double) * 3 * dd * (size_t)fgrid));
   CK(cudaMemsetAsync(h->wt, 0, sizeof(double) * B * dd, h->stream));
+  if (h->G > 1 && h->coop_mma) {   // [B][⌈D/32⌉·32][XS]: one bulk copy per 32-row block (coop_matvec_tma)
+    const size_t rows = ((size_t)h->cfg.dim + kTmaRows - 1) / kTmaRows * kTmaRows;
+    CK(cudaMalloc(&h->minv_pad, sizeof(double) * B * rows * (size_t)tma_xs((int)h->cfg.dim)));
+  }
   return plan(h);   // the shared-memory layout now carries the mat-vec staging vector
 }
 // κ = GaussianKineticEnergy(Symmetric M⁻¹): W = cholesky(inv(M⁻¹)).L on device, then switch
@@ -611,6 +626,11 @@ static int factor_and_switch(dhmc_handle* h) {
   CK(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));
   k_dense_factor<<<fgrid, 128, 0, h->stream>>>(h->minv_dense, h->wt, h->dense_tmp, h->status, (int)h->cfg.dim, (int)B);
   h->launches += 1;
+  if (h->minv_pad) {
+    const size_t rows = ((size_t)h->cfg.dim + kTmaRows - 1) / kTmaRows * kTmaRows;
+    k_pad_metric<<<2048, 256, 0, h->stream>>>(h->minv_dense, h->minv_pad, (size_t)h->cfg.dim, rows, (size_t)tma_xs((int)h->cfg.dim), B);
+    h->launches += 1;
+  }
   CK(cudaGetLastError());
   const bool was = h->dense;
   h->dense = true;

@@ -58,6 +58,7 @@ struct KArgs {
   double* lr;                   // logistic scratch: [grid][lN] residuals, or per CTA of packed groups [lN][G] residuals + [G][lN] ll terms
   int lN, lLd;                  // observations, leading dimension of Xᵀ (even)
   const double* lXp;            // tensor-core likelihood: zero-padded row blocks of X
+  const double* minv_pad;       // tensor-core mat-vec: padded M⁻¹ [B][⌈D/32⌉·32][tma_xs(D)]
   unsigned long long* prof;     // profiling builds (-DDHMC_PROFILE_ROUNDS): [grid][32 warps][16] cycle counters
 };
 
@@ -92,7 +93,7 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G, 
   b.lX = a.lX; b.lXt = a.lXt; b.ly = a.ly; b.lN = a.lN; b.lLd = a.lLd;
   b.lr = a.lr ? a.lr + (size_t)blockIdx.x * a.lN : nullptr;
   b.lll = nullptr; b.cb_flags = nullptr; b.cb_beta = b.cb_grad = b.cb_stage = nullptr;
-  b.cb_shared = nullptr; b.ring_n = 0; b.lXp = nullptr;
+  b.cb_shared = nullptr; b.ring_n = 0; b.lXp = nullptr; b.Mp = a.minv_pad;
   b.prof = a.prof ? a.prof + (size_t)blockIdx.x * 32 * 16 : nullptr;
   size_t group = blockIdx.x;
   if constexpr (G > 1) {

@@ -100,6 +100,23 @@ DHMC_HD double dm_pow2i(int k) {
   return dm_from_bits((uint64_t)(k + 1023) << 52);
 }
 
+/* Blocked dot product Σ_j a[j·sa]·b[j] (what a BLAS does, with a FIXED blocking): sequential fused
+ * multiply-adds within chunks of DHMC_DOT_CHUNK elements, the chunk sums added in increasing order,
+ * ((s₀ + s₁) + s₂) + …; n <= 64 is one plain sequential chain.  The chunks are independent accumulation
+ * chains — the unit the tensor-core paths (mma.sync.m8n8k4.f64 = four sequential FMAs) spread over warps.
+ * Used for η = Xβ of the logistic model and for the Symmetric metric's M⁻¹p (hamiltonian.jl:110). */
+#define DHMC_DOT_CHUNK 64
+DHMC_HD double dm_blocked_dot(const double* a, size_t sa, const double* b, int n) {
+  double tot = 0.0;
+  for (int j0 = 0; j0 < n; j0 += DHMC_DOT_CHUNK) {
+    const int j1 = j0 + DHMC_DOT_CHUNK < n ? j0 + DHMC_DOT_CHUNK : n;
+    double sacc = 0.0;
+    for (int j = j0; j < j1; ++j) sacc = dm_fma(a[(size_t)j * sa], b[j], sacc);
+    tot = j0 == 0 ? sacc : tot + sacc;
+  }
+  return tot;
+}
+
 /* ------------------------------------------------------------------- exp */
 #define DM_LN2_HI 6.93147180369123816490e-01 /* 0x3FE62E42FEE00000 */
 #define DM_LN2_LO 1.90821492927058770002e-10 /* 0x3DEA39EF35793C76 */

@@ -66,17 +66,8 @@ DHMC_HD double dhmc_logit_mac(double acc, double x, double b) { return dm_fma(x,
  * DHMC_LOGIT_CHUNK coefficients, the chunk sums added in increasing order:  η = ((s₀ + s₁) + s₂) + …
  * (dim <= 64: one plain sequential sum).  The chunks are independent accumulation chains, which is what lets
  * the tensor-core path spread one row tile over several warps. */
-#define DHMC_LOGIT_CHUNK 64
-DHMC_HD double dhmc_logit_eta(const double* xrow, const double* beta, int D) {
-  double eta = 0.0;
-  for (int j0 = 0; j0 < D; j0 += DHMC_LOGIT_CHUNK) {
-    const int j1 = j0 + DHMC_LOGIT_CHUNK < D ? j0 + DHMC_LOGIT_CHUNK : D;
-    double sacc = 0.0;
-    for (int j = j0; j < j1; ++j) sacc = dhmc_logit_mac(sacc, xrow[j], beta[j]);
-    eta = j0 == 0 ? sacc : eta + sacc;
-  }
-  return eta;
-}
+#define DHMC_LOGIT_CHUNK DHMC_DOT_CHUNK
+DHMC_HD double dhmc_logit_eta(const double* xrow, const double* beta, int D) { return dm_blocked_dot(xrow, 1, beta, D); }
 /* ll term y·η − log(1+e^η) and residual y − σ(η) from ONE exponential t = e^{−|η|}:
  *   log(1+e^η) = max(η,0) + log(1+t)   (table-driven softplus, absolute accuracy, no division)
  *   σ(η) = 1/(1+t) for η >= 0, t/(1+t) for η < 0   (no cancellation; one correctly rounded division) */

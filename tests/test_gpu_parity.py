@@ -446,16 +446,19 @@ def test_logistic_packed_groups_equal_one_chain_per_cta(pkg, N, p, K, M):
         r["engine"].close()
 
 
-@pytest.mark.parametrize("N,p,K,warps", [(300, 20, 21, 0), (1100, 130, 9, 0), (2000, 256, 16, 0), (999, 255, 11, 1),
-                                          (1037, 77, 19, 0), (31, 5, 8, 0)])
-def test_logistic_mma_likelihood_equals_fma_loops(pkg, monkeypatch, N, p, K, warps):
+@pytest.mark.parametrize("N,p,K,warps,M", [(300, 20, 21, 0, "Diagonal"), (1100, 130, 9, 0, "Diagonal"),
+                                            (2000, 256, 16, 0, "Diagonal"), (999, 255, 11, 2, "Diagonal"),
+                                            (1037, 77, 19, 0, "Symmetric"), (31, 5, 8, 0, "Symmetric"),
+                                            (700, 200, 10, 0, "Symmetric"), (640, 256, 9, 2, "Symmetric")])
+def test_logistic_mma_likelihood_equals_fma_loops(pkg, monkeypatch, N, p, K, warps, M):
     """mma.sync.m8n8k4.f64 accumulates as sequential FMAs (profiles/r01_dmma_order_probe.txt), so the
-    tensor-core / TMA likelihood (the default of packed chain groups) must reproduce the FMA formulation
-    bit for bit — odd dimensions, ragged last row block, one or two warps per chain."""
+    tensor-core / TMA formulation (the default of packed chain groups: likelihood rounds and, with a Symmetric
+    metric, the cooperative M⁻¹p) must reproduce the FMA formulation bit for bit — odd dimensions, ragged last
+    row block, one or two warps per chain, chains that run out early."""
     if warps:
         monkeypatch.setenv("DHMC_PACK_WARPS", str(warps))
     ℓ, _ = pkg.LogisticRegression.synthetic(N=N, p=p, seed=N + p)
-    stages = pkg.default_warmup_stages(M=pkg.Diagonal, init_steps=20, middle_steps=20, doubling_stages=1,
+    stages = pkg.default_warmup_stages(M=getattr(pkg, M), init_steps=20, middle_steps=20, doubling_stages=1,
                                        terminating_steps=20)
     out = []
     for mma in ("0", "1"):
@@ -464,10 +467,38 @@ def test_logistic_mma_likelihood_equals_fma_loops(pkg, monkeypatch, N, p, K, war
     for k in range(K):
         a, b = out[0]["inference"][k], out[1]["inference"][k]
         assert a["ϵ"] == b["ϵ"] and np.array_equal(a["posterior_matrix"], b["posterior_matrix"])
+        assert np.array_equal(a["κ"].minv, b["κ"].minv)
         for f in INT_FIELDS:
             assert np.array_equal(a["tree_statistics"][f], b["tree_statistics"][f])
     for r in out:
         r["engine"].close()
+
+
+def test_c4_shape_matches_oracle(pkg, po):
+    """BASELINE.json configs[3] at its exact shape — logistic regression N = 10 000, p = 256, per-chain dense
+    (Symmetric) metric — against the oracle: warm-up with a Symmetric stage (so M⁻¹, W and ϵ are the adapted ones),
+    then draws; chains 0, 5 and the last one of a handle whose chain count is not a multiple of the CTA's 8.
+    Integers bit-exact, positions / metric / step size bit-equal (tolerance bar: 1e-10 relative)."""
+    ℓ, _ = pkg.LogisticRegression.synthetic(N=10000, p=256, seed=7)
+    K, N, seed = 13, 3, 2026
+    stages = (pkg.InitialStepsizeSearch(), pkg.TuningNUTS(20, pkg.DualAveraging()),
+              pkg.TuningNUTS(20, pkg.DualAveraging(), pkg.Symmetric), pkg.TuningNUTS(20, pkg.DualAveraging()))
+    r = pkg.mcmc_keep_warmup(seed, ℓ, N, chains=K, warmup_stages=stages)
+    T, _ = r["engine"].layout()
+    params = po.logistic_params(ℓ.X, ℓ.y)
+    ostages = po.default_warmup_stages(init_steps=20, middle_steps=20, doubling_stages=1, terminating_steps=20,
+                                       M=po.METRIC_SYMMETRIC)
+    for k in (0, 5, K - 1):
+        o = po.mcmc_with_warmup(po.FAMILY_LOGISTIC, 256, N, seed, k, stages=ostages, params=params, T=T, welford=True)
+        res = r["inference"][k]
+        assert res["κ"].dense
+        np.testing.assert_allclose(res["κ"].minv, o["minv"], rtol=RTOL, atol=0)
+        np.testing.assert_allclose(res["posterior_matrix"].T, o["posterior_matrix"], rtol=RTOL, atol=0)
+        assert np.array_equal(res["κ"].minv, o["minv"]) and res["ϵ"] == o["eps"]
+        assert np.array_equal(res["posterior_matrix"].T, o["posterior_matrix"])
+        for f in INT_FIELDS:
+            assert np.array_equal(res["tree_statistics"][f], o["tree_statistics"][f])
+    r["engine"].close()
 
 
 # --------------------------------------------------------------- trajectory diagnostics (diagnostics.jl:139-216)
