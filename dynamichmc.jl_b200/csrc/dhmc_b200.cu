@@ -15,9 +15,15 @@
 // There is NO CPU fallback: without a CUDA device dhmc_create fails with
 // DHMC_ECUDA and nothing else can be called.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>      // types and prototypes only: the library is bound at run time (nccl_api below)
+
+#include <pthread.h>
+#include <sched.h>
 
 #include <cmath>
 #include <cstdio>
+#include <fstream>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -208,6 +214,7 @@ struct dhmc_handle {
   cudaEvent_t h2d_ev[16] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t chunk_ev[16] = {};
+  std::vector<void*> registered;    // caller buffers page-locked on the fly (direct host writes of draws that exceed HBM)
   void* stage[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only device staging for host outputs
   size_t stage_bytes[4] = {0, 0, 0, 0};
   double *q = nullptr, *g = nullptr, *lq = nullptr, *p = nullptr, *minv = nullptr, *eps = nullptr;
@@ -229,6 +236,10 @@ struct dhmc_handle {
   int lN = 0, lLd = 0;
   int reg_ctas[2] = {0, 0};         // occupancy of k_nuts (diag, dense)
   size_t smem_sm = 0, smem_cta_max = 0;
+  ncclComm_t comm = nullptr;        // multi-GPU: one communicator per handle (dhmc_comm_init)
+  int comm_nranks = 1, comm_rank = 0;
+  double last_comm_ms = 0;
+  size_t l2_persist_max = 0, l2_window_max = 0;   // persisting-L2 carve-out and largest access-policy window of the device
   std::string err;
 };
 
@@ -242,6 +253,8 @@ static std::string g_create_err;
       return e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA;              \
     }                                                                                 \
   } while (0)
+
+static void set_l2_window(dhmc_handle* h, const void* ptr, size_t bytes);
 
 // rows of N doubles in the logistic scratch: one per CTA of the light kernels, 2·G per CTA
 // (residuals and ll terms of every packed chain) of the persistent kernels
@@ -286,11 +299,28 @@ static int plan(dhmc_handle* h) {
   h->scratch_per_cta = (size_t)(h->n_slots - h->n_sm) * slot_doubles;
   cudaFree(h->scratch); h->scratch = nullptr;
   CK(cudaMalloc(&h->scratch, sizeof(double) * h->scratch_per_cta * (size_t)h->grid * (size_t)G));
+  // (an access-policy window over the slot arena was measured and rejected: 1.10e8 vs 1.17e8 leapfrog-steps/s at C2)
   if (h->lN) {   // residual scratch of the logistic family follows the grid
     cudaFree(h->lr); h->lr = nullptr;
     CK(cudaMalloc(&h->lr, sizeof(double) * (size_t)h->lN * lr_rows(h)));
   }
   return DHMC_OK;
+}
+
+// Keep a re-read working set resident in L2 (access-policy window on the compute stream): the design matrix of the
+// logistic family (every SM sweeps it once per gradient; evicted by the metric / co-moment streams otherwise), else the
+// slot arena of the persistent kernels (its dirty lines were written back and re-fetched between tree levels).
+static void set_l2_window(dhmc_handle* h, const void* ptr, size_t bytes) {
+  if (!ptr || !bytes || h->l2_persist_max == 0) return;
+  cudaStreamAttrValue v;
+  std::memset(&v, 0, sizeof v);
+  const size_t win = std::min(bytes, h->l2_window_max);
+  v.accessPolicyWindow.base_ptr = const_cast<void*>(ptr);
+  v.accessPolicyWindow.num_bytes = win;
+  v.accessPolicyWindow.hitRatio = (float)std::min(1.0, 0.9 * (double)h->l2_persist_max / (double)win);
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
 }
 
 static KArgs base_args(dhmc_handle* h) {
@@ -423,6 +453,7 @@ static void choose_layout(int64_t D, int req_T, int* T, int* EPL) {
 extern "C" {
 
 const char* dhmc_last_error(dhmc_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+int dhmc_comm_destroy(dhmc_handle* h);
 
 int dhmc_destroy(dhmc_handle* h) {
   if (!h) return DHMC_OK;
@@ -432,6 +463,8 @@ int dhmc_destroy(dhmc_handle* h) {
   cudaFree(h->total_steps);
   cudaFree(h->minv_dense); cudaFree(h->wt); cudaFree(h->covt); cudaFree(h->dense_tmp); cudaFree(h->minv_pad);
   cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr); cudaFree(h->lXp);
+  for (void* r : h->registered) cudaHostUnregister(r);
+  if (h->comm) dhmc_comm_destroy(h);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
@@ -519,6 +552,14 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   k_fill<<<1024, 256, 0, h->stream>>>(h->minv, 1.0, B * D);   // κ = GaussianKineticEnergy(D), mcmc.jl:130
   h->launches += 1;
 
+  if (!(std::getenv("DHMC_NO_L2_WINDOW"))) {
+    h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    if (h->l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max) != cudaSuccess) {
+      cudaGetLastError();
+      h->l2_persist_max = 0;
+    }
+  }
   h->smem_sm = (size_t)prop.sharedMemPerMultiprocessor;          // 228 KB
   h->smem_cta_max = (size_t)prop.sharedMemPerBlockOptin;         // 227 KB
   {
@@ -568,6 +609,7 @@ int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n) {
       CK(cudaMalloc(&h->lXp, sizeof(double) * rows * xs));
       k_pad_rows<<<1024, 256, 0, h->stream>>>(h->lX, h->lXp, N, D, rows, xs);
       h->launches += 1;
+      set_l2_window(h, h->lXp, sizeof(double) * rows * xs);
     }
     h->lN = (int)N; h->lLd = (int)ld;
     CK(cudaStreamSynchronize(h->stream));
@@ -799,13 +841,22 @@ static int ensure_stage(dhmc_handle* h, int i, size_t bytes) {
   h->stage_bytes[i] = bytes;
   return DHMC_OK;
 }
+// Is `p` page-locked host memory that the device can address (cudaHostAlloc / cudaHostRegister)?  Then *dev is its device alias.
+static bool host_mapped(const void* p, void** dev) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+  *dev = at.devicePointer;
+  return true;
+}
 static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda, const double* p_over_host,
                     const uint32_t* dir_over_host, double* posterior, dhmc_tree_stats* stats,
                     double* eps_used, double* logdens, bool outputs_on_device, bool advance_t,
-                    const double* q_host = nullptr) {
+                    const double* q_host = nullptr, int thin = 1) {
   if ((!h->has_position && !q_host) || !h->has_eps) { h->err = "set position and step size (or run the initial search) first"; return DHMC_EARG; }
   CK(cudaSetDevice(h->cfg.device));
-  const size_t B = (size_t)h->cfg.n_chains, D = (size_t)h->cfg.dim, n = (size_t)N;
+  if (thin < 1 || N % thin != 0) { h->err = "thin >= 1 and N a multiple of thin"; return DHMC_EARG; }
+  const size_t B = (size_t)h->cfg.n_chains, D = (size_t)h->cfg.dim, n = (size_t)(N / thin);   // n: kept draws per chain
   double *d_post = nullptr, *d_eps = nullptr, *d_ld = nullptr, *d_p = nullptr;
   dhmc_tree_stats* d_stats = nullptr;
   unsigned* d_dir = nullptr;
@@ -813,13 +864,45 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   auto cleanup = [&] { cudaFree(d_p); cudaFree(d_dir); };
 #define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA; } } while (0)
 #define CKS(call) do { int r_ = (call); if (r_ != DHMC_OK) { cleanup(); return r_; } } while (0)
+  // Host outputs.  Page-locked (pinned) buffers are written by the kernel itself through their device alias — no staging
+  // copy in HBM, no second hop, the PCIe writes overlap the sampling at cache-line granularity and N is not bounded by
+  // device memory.  Pageable buffers are staged in HBM and copied chunk by chunk; if the draws would not fit, the buffer
+  // is page-locked on the fly (cudaHostRegister) and written directly.
+  bool direct[4] = {false, false, false, false};
   if (outputs_on_device) {
     d_post = posterior; d_stats = stats; d_eps = eps_used; d_ld = logdens;
   } else {
-    if (posterior) { CKS(ensure_stage(h, 0, sizeof(double) * B * n * D)); d_post = (double*)h->stage[0]; }
-    if (stats) { CKS(ensure_stage(h, 1, sizeof(dhmc_tree_stats) * B * n)); d_stats = (dhmc_tree_stats*)h->stage[1]; }
-    if (eps_used) { CKS(ensure_stage(h, 2, sizeof(double) * B * n)); d_eps = (double*)h->stage[2]; }
-    if (logdens) { CKS(ensure_stage(h, 3, sizeof(double) * B * n)); d_ld = (double*)h->stage[3]; }
+    void* dv = nullptr;
+    if (posterior) {
+      const size_t bytes = sizeof(double) * B * n * D;
+      bool ok = host_mapped(posterior, &dv);
+      if (!ok) {
+        size_t fr = 0, tot = 0;
+        cudaMemGetInfo(&fr, &tot);
+        if (bytes > h->stage_bytes[0] && bytes + ((size_t)1 << 30) > fr) {       // would not fit in HBM: page-lock the caller's buffer
+          if (cudaHostRegister(posterior, bytes, cudaHostRegisterMapped) == cudaSuccess) {
+            h->registered.push_back(posterior);
+            ok = host_mapped(posterior, &dv);
+          } else {
+            cudaGetLastError();
+          }
+        }
+      }
+      if (ok) { d_post = (double*)dv; direct[0] = true; }
+      else { CKS(ensure_stage(h, 0, bytes)); d_post = (double*)h->stage[0]; }
+    }
+    if (stats) {
+      if (host_mapped(stats, &dv)) { d_stats = (dhmc_tree_stats*)dv; direct[1] = true; }
+      else { CKS(ensure_stage(h, 1, sizeof(dhmc_tree_stats) * B * n)); d_stats = (dhmc_tree_stats*)h->stage[1]; }
+    }
+    if (eps_used) {
+      if (host_mapped(eps_used, &dv)) { d_eps = (double*)dv; direct[2] = true; }
+      else { CKS(ensure_stage(h, 2, sizeof(double) * B * n)); d_eps = (double*)h->stage[2]; }
+    }
+    if (logdens) {
+      if (host_mapped(logdens, &dv)) { d_ld = (double*)dv; direct[3] = true; }
+      else { CKS(ensure_stage(h, 3, sizeof(double) * B * n)); d_ld = (double*)h->stage[3]; }
+    }
   }
   if (p_over_host) {
     CKR(cudaMalloc(&d_p, sizeof(double) * B * D));
@@ -830,12 +913,15 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
     CKR(cudaMemcpyAsync(d_dir, dir_over_host, sizeof(unsigned) * B, cudaMemcpyHostToDevice, h->stream));
   }
   KArgs a = base_args(h);
-  a.N = N; a.cfg = cfg; a.p_override = d_p; a.dir_override = d_dir;
+  a.N = N; a.thin = thin; a.N_keep = (int)n; a.cfg = cfg; a.p_override = d_p; a.dir_override = d_dir;
   a.out_q = d_post; a.out_stats = d_stats; a.out_eps = d_eps; a.out_lq = d_ld;
   if (cfg.metric == DHMC_METRIC_SYMMETRIC) a.covt = h->covt;
   const size_t out_bytes = posterior ? sizeof(double) * B * n * D : 0;
   // chunks must stay many waves long, or the ragged tail of every chunk idles the SMs
-  int nchunks = (!outputs_on_device && B >= 4096 && out_bytes >= ((size_t)32 << 20)) ? 8 : 1;
+  // chunks overlap the staged downloads (and the upload of q_host) with the sampling of the next chunk; with direct
+  // host writes only an upload is left to overlap
+  const bool staged_big = posterior && !direct[0] && out_bytes >= ((size_t)32 << 20);
+  int nchunks = (!outputs_on_device && B >= 4096 && (staged_big || q_host)) ? 8 : 1;
   while (nchunks > 1 && B / (size_t)nchunks < (size_t)16 * (size_t)h->grid) nchunks /= 2;
   CKR(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));   // status words describe the current call
   for (int ci = 0; ci < nchunks; ++ci) {
@@ -863,10 +949,10 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
     if (!outputs_on_device) {
       CKR(cudaEventRecord(h->chunk_ev[ci], h->stream));
       CKR(cudaStreamWaitEvent(h->copy_stream, h->chunk_ev[ci], 0));
-      if (posterior) CKR(cudaMemcpyAsync(posterior + c0 * n * D, d_post + c0 * n * D, sizeof(double) * nc * n * D, cudaMemcpyDeviceToHost, h->copy_stream));
-      if (stats) CKR(cudaMemcpyAsync(stats + c0 * n, d_stats + c0 * n, sizeof(dhmc_tree_stats) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
-      if (eps_used) CKR(cudaMemcpyAsync(eps_used + c0 * n, d_eps + c0 * n, sizeof(double) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
-      if (logdens) CKR(cudaMemcpyAsync(logdens + c0 * n, d_ld + c0 * n, sizeof(double) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
+      if (posterior && !direct[0]) CKR(cudaMemcpyAsync(posterior + c0 * n * D, d_post + c0 * n * D, sizeof(double) * nc * n * D, cudaMemcpyDeviceToHost, h->copy_stream));
+      if (stats && !direct[1]) CKR(cudaMemcpyAsync(stats + c0 * n, d_stats + c0 * n, sizeof(dhmc_tree_stats) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
+      if (eps_used && !direct[2]) CKR(cudaMemcpyAsync(eps_used + c0 * n, d_eps + c0 * n, sizeof(double) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
+      if (logdens && !direct[3]) CKR(cudaMemcpyAsync(logdens + c0 * n, d_ld + c0 * n, sizeof(double) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
     }
   }
   unsigned long long steps = 0;
@@ -938,6 +1024,60 @@ int dhmc_mcmc_from(dhmc_handle* h, const double* q, int32_t N, double* posterior
   AdaptConfig cfg{};
   return run_nuts(h, N, cfg, 0.0, nullptr, nullptr, posterior, stats, nullptr, logdens, false, true, q);
 }
+int dhmc_mcmc_thinned(dhmc_handle* h, const double* q, int32_t N, int32_t thin, double* posterior,
+                      dhmc_tree_stats* stats, double* logdens) {
+  if (!h || N < 1 || thin < 1) return DHMC_EARG;
+  AdaptConfig cfg{};
+  return run_nuts(h, N, cfg, 0.0, nullptr, nullptr, posterior, stats, nullptr, logdens, false, true, q, thin);
+}
+// Page-locked host memory on the NUMA node of the handle's GPU: the calling thread is moved to that node's CPUs while the
+// pages are allocated and pinned (first touch), so that the kernel's direct writes / the DMA engines cross one PCIe root
+// complex and no inter-socket link.  *node receives the NUMA node (or -1 when unknown).
+int dhmc_host_alloc(dhmc_handle* h, size_t bytes, void** out, int32_t* node) {
+  if (!h || !out || bytes == 0) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  int numa = -1;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof bus, h->cfg.device) == cudaSuccess) {
+    for (char* c = bus; *c; ++c) *c = (char)std::tolower(*c);
+    std::ifstream f(std::string("/sys/bus/pci/devices/") + bus + "/numa_node");
+    if (f) f >> numa;
+  } else {
+    cudaGetLastError();
+  }
+  cpu_set_t old_set, node_set;
+  bool moved = false;
+  if (numa >= 0 && sched_getaffinity(0, sizeof old_set, &old_set) == 0) {
+    std::ifstream f("/sys/devices/system/node/node" + std::to_string(numa) + "/cpulist");
+    std::string list;
+    if (f && std::getline(f, list)) {
+      CPU_ZERO(&node_set);
+      size_t pos = 0;
+      while (pos < list.size()) {            // "0-31,64-95"
+        size_t end = list.find(',', pos);
+        if (end == std::string::npos) end = list.size();
+        const std::string tok = list.substr(pos, end - pos);
+        const size_t dash = tok.find('-');
+        const int a = std::atoi(tok.c_str()), b = dash == std::string::npos ? a : std::atoi(tok.c_str() + dash + 1);
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) if (CPU_ISSET(c, &old_set)) CPU_SET(c, &node_set);
+        pos = end + 1;
+      }
+      if (CPU_COUNT(&node_set) > 0 && sched_setaffinity(0, sizeof node_set, &node_set) == 0) moved = true;
+    }
+  }
+  void* p = nullptr;
+  const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocMapped | cudaHostAllocPortable);
+  if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+  if (e != cudaSuccess) { h->err = std::string("cudaHostAlloc: ") + cudaGetErrorString(e); return DHMC_ENOMEM; }
+  *out = p;
+  if (node) *node = numa;
+  return DHMC_OK;
+}
+int dhmc_host_free(dhmc_handle* h, void* p) {
+  if (!h) return DHMC_EARG;
+  if (p && cudaFreeHost(p) != cudaSuccess) { h->err = "cudaFreeHost failed"; cudaGetLastError(); return DHMC_ECUDA; }
+  return DHMC_OK;
+}
 int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats, double* logdens) {
   if (!h || N < 0) return DHMC_EARG;
   if (N == 0) return DHMC_OK;
@@ -976,5 +1116,90 @@ int dhmc_tree_summary_dev(dhmc_handle* h, const dhmc_tree_stats* stats_dev, int3
 int dhmc_last_total_steps(dhmc_handle* h, int64_t* steps) { if (!h || !steps) return DHMC_EARG; *steps = h->last_steps; return DHMC_OK; }
 int dhmc_last_kernel_ms(dhmc_handle* h, double* ms) { if (!h || !ms) return DHMC_EARG; *ms = h->last_ms; return DHMC_OK; }
 int dhmc_kernel_launches(dhmc_handle* h, int64_t* n) { if (!h || !n) return DHMC_EARG; *n = h->launches; return DHMC_OK; }
+
+// ---- multi-GPU: chains are sharded over ranks with no data-path collective; the one exchange is the
+// all-gather of (thinned) draws / final positions at the end.  One process per GPU; rank 0 creates the id, the host
+// program (Julia: MPI / Distributed; Python: torch.distributed) carries its 128 bytes to the other ranks.
+// NCCL is bound with dlopen("libnccl.so.2") at the first dhmc_comm_* call instead of a DT_NEEDED entry: a host process
+// that already carries an NCCL (e.g. the copy bundled with PyTorch) must end up with ONE libnccl, and a process that never
+// shards pays nothing.  The soname lookup returns the copy that is already loaded, else the system library.
+struct nccl_api {
+  decltype(&::ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&::ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&::ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&::ncclAllGather) AllGather = nullptr;
+  decltype(&::ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&::ncclGetVersion) GetVersion = nullptr;
+  bool ok = false;
+  std::string why;
+};
+static nccl_api& nccl() {
+  static nccl_api api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { api.why = std::string("dlopen(libnccl.so.2): ") + dlerror(); return api; }
+#define DHMC_NCCL_SYM(name) api.name = reinterpret_cast<decltype(api.name)>(dlsym(lib, "nccl" #name)); if (!api.name) { api.why = "libnccl lacks nccl" #name; return api; }
+    DHMC_NCCL_SYM(GetUniqueId) DHMC_NCCL_SYM(CommInitRank) DHMC_NCCL_SYM(CommDestroy) DHMC_NCCL_SYM(AllGather)
+    DHMC_NCCL_SYM(GetErrorString) DHMC_NCCL_SYM(GetVersion)
+#undef DHMC_NCCL_SYM
+    api.ok = true;
+  }
+  return api;
+}
+int dhmc_comm_unique_id(void* id128) {
+  if (!id128) return DHMC_EARG;
+  static_assert(sizeof(ncclUniqueId) == DHMC_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  if (!nccl().ok) { g_create_err = nccl().why; return DHMC_ENCCL; }
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) { g_create_err = "ncclGetUniqueId failed"; return DHMC_ENCCL; }
+  std::memcpy(id128, &id, sizeof id);
+  return DHMC_OK;
+}
+#define CKN(call)                                                                     \
+  do {                                                                                \
+    if (!nccl().ok) { h->err = nccl().why; return DHMC_ENCCL; }                       \
+    ncclResult_t r_ = (call);                                                         \
+    if (r_ != ncclSuccess) { h->err = std::string(#call) + ": " + nccl().GetErrorString(r_); return DHMC_ENCCL; } \
+  } while (0)
+int dhmc_comm_init(dhmc_handle* h, int32_t nranks, int32_t rank, const void* id128) {
+  if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return DHMC_EARG;
+  if (h->comm) { h->err = "communicator already initialised"; return DHMC_EARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof id);
+  CKN(nccl().CommInitRank(&h->comm, nranks, id, rank));
+  h->comm_nranks = nranks; h->comm_rank = rank;
+  return DHMC_OK;
+}
+int dhmc_comm_destroy(dhmc_handle* h) {
+  if (!h) return DHMC_EARG;
+  if (h->comm) { nccl().CommDestroy(h->comm); h->comm = nullptr; h->comm_nranks = 1; h->comm_rank = 0; }
+  return DHMC_OK;
+}
+// ncclAllGather of `count` doubles per rank, DEVICE pointers (e.g. the draws buffer of dhmc_mcmc_dev): recv is
+// [nranks][count]; rank order = global chain order, so recv is the [D, N, B·nranks] column-major draws array.
+int dhmc_allgather_dev(dhmc_handle* h, const double* send_dev, double* recv_dev, size_t count) {
+  if (!h || !send_dev || !recv_dev) return DHMC_EARG;
+  if (!h->comm) { h->err = "dhmc_comm_init first"; return DHMC_EARG; }
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  CKN(nccl().AllGather(send_dev, recv_dev, count, ncclDouble, h->comm, h->stream));
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaEventSynchronize(h->ev1));
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+  h->last_comm_ms = ms;
+  return DHMC_OK;
+}
+// The current position of every chain of every rank: recv_dev [D, B·nranks] (DEVICE), one all-gather of D·B doubles per rank.
+int dhmc_allgather_positions_dev(dhmc_handle* h, double* recv_dev) {
+  if (!h || !recv_dev) return DHMC_EARG;
+  return dhmc_allgather_dev(h, h->q, recv_dev, (size_t)h->cfg.n_chains * (size_t)h->cfg.dim);
+}
+int dhmc_last_comm_ms(dhmc_handle* h, double* ms) { if (!h || !ms) return DHMC_EARG; *ms = h->last_comm_ms; return DHMC_OK; }
+#undef CKN
 
 }  // extern "C"

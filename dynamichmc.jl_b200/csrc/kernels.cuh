@@ -58,6 +58,7 @@ struct KArgs {
   double* lr;                   // logistic scratch: [grid][lN] residuals, or per CTA of packed groups [lN][G] residuals + [G][lN] ll terms
   int lN, lLd;                  // observations, leading dimension of Xᵀ (even)
   const double* lXp;            // tensor-core likelihood: zero-padded row blocks of X
+  int thin, N_keep;             // draws: every thin-th transition is kept (N_keep = N / thin rows per chain)
   const double* minv_pad;       // tensor-core mat-vec: padded M⁻¹ [B][⌈D/32⌉·32][tma_xs(D)]
   unsigned long long* prof;     // profiling builds (-DDHMC_PROFILE_ROUNDS): [grid][32 warps][16] cycle counters
 };
@@ -210,8 +211,18 @@ struct DrawSink {
   const KArgs& a;
   long c;
   __device__ __forceinline__ void operator()(int n, const dhmc_tree_stats& ts, double e) {
-    const size_t row = (size_t)c * a.N + n;
-    if (a.out_q) store_vec(b, a.out_q, b.q, row * a.D, a.D);
+    if (a.thin > 1) {                     // thinning: transition n is kept when (n + 1) is a multiple of thin
+      if ((n + 1) % a.thin != 0) return;
+      n = (n + 1) / a.thin - 1;
+    }
+    const size_t row = (size_t)c * a.N_keep + n;
+    if (a.out_q) {                       // draws are written once and never re-read on the device: streaming stores
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const int i = b.tid + e * b.T;
+        if (i < a.D) __stcs(a.out_q + row * a.D + i, b.q[e]);
+      }
+    }
     if (b.tid == 0) {
       if (a.out_stats) a.out_stats[row] = ts;
       if (a.out_lq) a.out_lq[row] = b.lq;

@@ -35,7 +35,8 @@ enum {
   DHMC_ENUMERIC = 2, /* -> DynamicHMCError (hamiltonian.jl:203,213,215;
                         stepsize.jl:58,78) for at least one chain */
   DHMC_ECUDA = 3,
-  DHMC_ENOMEM = 4
+  DHMC_ENOMEM = 4,
+  DHMC_ENCCL = 5
 };
 
 /* per-chain status bits (dhmc_chain_status) */
@@ -156,6 +157,16 @@ int dhmc_mcmc(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* sta
  * mcmc.jl:335-351.  Upload, evaluation, sampling and download are pipelined by chain chunks. */
 int dhmc_mcmc_from(dhmc_handle* h, const double* q, int32_t N, double* posterior,
                    dhmc_tree_stats* stats, double* logdens);
+/* mcmc with a thinned output (§8f-3): N transitions, every thin-th one is kept, outputs are [D, N/thin, B] resp.
+ * [N/thin, B].  q == NULL continues from the resident positions, else as dhmc_mcmc_from.
+ * All host-output calls write PAGE-LOCKED buffers (cudaHostAlloc / cudaHostRegister / dhmc_host_alloc) directly from
+ * the sampling kernel — no staging copy in HBM, so N is not bounded by device memory; pageable buffers are staged in HBM
+ * and copied chunk by chunk, or page-locked on the fly when the draws would not fit. */
+int dhmc_mcmc_thinned(dhmc_handle* h, const double* q, int32_t N, int32_t thin, double* posterior,
+                      dhmc_tree_stats* stats, double* logdens);
+/* Page-locked, device-mapped host memory on the NUMA node of the handle's GPU (for the output buffers above). */
+int dhmc_host_alloc(dhmc_handle* h, size_t bytes, void** out, int32_t* numa_node);
+int dhmc_host_free(dhmc_handle* h, void* p);
 /* Same with DEVICE output pointers (draws stay in HBM for an NCCL all-gather). */
 int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats,
                   double* logdens);
@@ -168,6 +179,26 @@ int dhmc_mcmc_dev(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats*
 int dhmc_tree_summary_dev(dhmc_handle* h, const dhmc_tree_stats* stats_dev, int32_t N,
                           int64_t* depth_counts, int64_t* termination_counts,
                           double* acceptance_sum, int64_t* steps_sum, double* ebfmi);
+
+/* ---- multi-GPU: chains sharded over ranks, ONE all-gather of draws at the end ------------
+ * One process (rank) per GPU; a handle owns the chains [chain_offset, chain_offset + n_chains) and the RNG keys use
+ * the global chain id, so results do not depend on the number of ranks.  Nothing is exchanged while sampling.
+ * The reference has no counterpart (multi-chain = the user runs mcmc_with_warmup K times,
+ * docs/src/worked_example.md:97-103); these entry points replace the user's own gather of the per-chain results
+ * (stack_posterior_matrices / pool_posterior_matrices, mcmc.jl:602-617, over all ranks). */
+#define DHMC_COMM_ID_BYTES 128
+/* rank 0: a fresh ncclUniqueId (128 bytes), to be carried to the other ranks by the host program */
+int dhmc_comm_unique_id(void* id128);
+/* every rank: ncclCommInitRank on the handle's device */
+int dhmc_comm_init(dhmc_handle* h, int32_t nranks, int32_t rank, const void* id128);
+int dhmc_comm_destroy(dhmc_handle* h);
+/* ncclAllGather of `count` doubles per rank between DEVICE buffers (recv: [nranks][count]); with the draws buffer of
+ * dhmc_mcmc_dev as `send`, recv is the [D, N, B·nranks] column-major array of all ranks' draws. */
+int dhmc_allgather_dev(dhmc_handle* h, const double* send_dev, double* recv_dev, size_t count);
+/* the current position of every chain of every rank, recv_dev: [D, B·nranks] (DEVICE) */
+int dhmc_allgather_positions_dev(dhmc_handle* h, double* recv_dev);
+/* device time of the last all-gather (CUDA events on the handle's stream) */
+int dhmc_last_comm_ms(dhmc_handle* h, double* ms);
 
 /* ---- measurement hooks ------------------------------------------------- */
 /* Σ tree_statistics.steps over all chains and draws of the last sampling call. */
