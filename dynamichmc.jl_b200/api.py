@@ -274,6 +274,7 @@ class Engine:
 
     def close(self):
         if getattr(self, "_h", None):
+            self.host_free_all()
             self._lib.dhmc_destroy(self._h)
             self._h = None
 
@@ -438,6 +439,68 @@ class Engine:
         ld = np.empty((K, N)) if ld is None else ld
         self._ck(self._lib.dhmc_mcmc_from(self._h, L.ptr(q), C.c_int32(N), L.ptr(post), L.ptr(stats), L.ptr(ld)))
         return dict(posterior_matrix=post, tree_statistics=stats, logdensities=ld)
+
+    def mcmc_thinned(self, N, thin=1, q=None, out=None):
+        """N transitions, every `thin`-th kept (dhmc_mcmc_thinned).  `out` may hold preallocated arrays; page-locked
+        ones (host_alloc) are written by the sampling kernel directly, so the kept draws need not fit in HBM."""
+        _argcheck(thin >= 1 and N % thin == 0, "thin ≥ 1 and N a multiple of thin")
+        K, D, n = self.K, self.D, N // thin
+        out = out or {}
+        post = out.get("posterior_matrix", None)
+        post = np.empty((K, n, D)) if post is None else post
+        stats = out.get("tree_statistics", None)
+        stats = np.zeros((K, n), dtype=L.tree_stats_dtype) if stats is None else stats
+        ld = out.get("logdensities", None)
+        ld = np.empty((K, n)) if ld is None else ld
+        qq = None if q is None else self._kd(q, "q")
+        self._ck(self._lib.dhmc_mcmc_thinned(self._h, L.ptr(qq), C.c_int32(N), C.c_int32(thin), L.ptr(post),
+                                             L.ptr(stats), L.ptr(ld)))
+        return dict(posterior_matrix=post, tree_statistics=stats, logdensities=ld)
+
+    def host_alloc(self, shape, dtype=np.float64):
+        """Page-locked, device-mapped numpy array on the NUMA node of this engine's GPU (dhmc_host_alloc).
+        Freed with the engine (or host_free)."""
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        p, node = C.c_void_p(), C.c_int32(-1)
+        self._ck(self._lib.dhmc_host_alloc(self._h, C.c_size_t(max(nbytes, 1)), C.byref(p), C.byref(node)))
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+        self._host_allocs = getattr(self, "_host_allocs", [])
+        self._host_allocs.append(p.value)
+        self.numa_node = node.value
+        return a
+
+    def host_free_all(self):
+        for p in getattr(self, "_host_allocs", []):
+            self._lib.dhmc_host_free(self._h, C.c_void_p(p))
+        self._host_allocs = []
+
+    # -- multi-GPU (include/dhmc.h, "multi-GPU"): one all-gather of draws at the end
+    @staticmethod
+    def comm_unique_id():
+        lib = L.lib()
+        buf = (C.c_char * L.COMM_ID_BYTES)()
+        rc = lib.dhmc_comm_unique_id(buf)
+        if rc != L.DHMC_OK:
+            raise RuntimeError(f"dhmc_comm_unique_id failed [{rc}]: {lib.dhmc_last_error(None).decode()}")
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        _argcheck(len(unique_id) == L.COMM_ID_BYTES, "128-byte ncclUniqueId")
+        self._ck(self._lib.dhmc_comm_init(self._h, C.c_int32(nranks), C.c_int32(rank), C.c_char_p(unique_id)))
+
+    def allgather_dev(self, send_ptr, recv_ptr, count):
+        self._ck(self._lib.dhmc_allgather_dev(self._h, C.c_void_p(send_ptr), C.c_void_p(recv_ptr), C.c_size_t(count)))
+        v = C.c_double()
+        self._ck(self._lib.dhmc_last_comm_ms(self._h, C.byref(v)))
+        return v.value
+
+    def allgather_positions_dev(self, recv_ptr):
+        self._ck(self._lib.dhmc_allgather_positions_dev(self._h, C.c_void_p(recv_ptr)))
+        v = C.c_double()
+        self._ck(self._lib.dhmc_last_comm_ms(self._h, C.byref(v)))
+        return v.value
 
     def mcmc_dev(self, N, posterior_ptr=0, stats_ptr=0, logdens_ptr=0):
         """Device-pointer variant: draws stay in HBM (e.g. torch tensors' data_ptr())."""

@@ -21,6 +21,7 @@
 #include <pthread.h>
 #include <sched.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -214,6 +215,8 @@ struct dhmc_handle {
   cudaEvent_t h2d_ev[16] = {};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t chunk_ev[16] = {};
+  cudaEvent_t copy_ev[16] = {};
+  bool trace = false;
   std::vector<void*> registered;    // caller buffers page-locked on the fly (direct host writes of draws that exceed HBM)
   void* stage[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only device staging for host outputs
   size_t stage_bytes[4] = {0, 0, 0, 0};
@@ -468,6 +471,7 @@ int dhmc_destroy(dhmc_handle* h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (auto& e : h->chunk_ev) if (e) cudaEventDestroy(e);
+  for (auto& e : h->copy_ev) if (e) cudaEventDestroy(e);
   for (auto& b : h->stage) cudaFree(b);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   for (auto& e : h->h2d_ev) if (e) cudaEventDestroy(e);
@@ -527,8 +531,11 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   CKC(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
   CKC(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
-  for (auto& e : h->h2d_ev) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-  for (auto& e : h->chunk_ev) CKC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  const bool trace = std::getenv("DHMC_TRACE") != nullptr;      // DHMC_TRACE=1: timeline of the chunk pipeline on stderr
+  for (auto& e : h->h2d_ev) CKC(cudaEventCreateWithFlags(&e, trace ? cudaEventDefault : cudaEventDisableTiming));
+  for (auto& e : h->chunk_ev) CKC(cudaEventCreateWithFlags(&e, trace ? cudaEventDefault : cudaEventDisableTiming));
+  for (auto& e : h->copy_ev) CKC(cudaEventCreateWithFlags(&e, trace ? cudaEventDefault : cudaEventDisableTiming));
+  h->trace = trace;
   CKC(cudaEventCreate(&h->ev0));
   CKC(cudaEventCreate(&h->ev1));
   const size_t B = (size_t)cfg->n_chains, D = (size_t)cfg->dim;
@@ -552,7 +559,10 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   k_fill<<<1024, 256, 0, h->stream>>>(h->minv, 1.0, B * D);   // κ = GaussianKineticEnergy(D), mcmc.jl:130
   h->launches += 1;
 
-  if (!(std::getenv("DHMC_NO_L2_WINDOW"))) {
+  // Opt-in (DHMC_L2_WINDOW=1): persisting-L2 window over the logistic design matrix.  Measured on the B200: no gain for C4
+  // (the matrix stays L2-resident anyway), and the carve-out costs the other kernels L2 capacity (C2: 1.17e8 -> 1.09e8
+  // leapfrog-steps/s, streaming leapfrog 0.96 -> 0.42 of the HBM peak), hence off by default.
+  if (std::getenv("DHMC_L2_WINDOW") && std::atoi(std::getenv("DHMC_L2_WINDOW")) == 1) {
     h->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     h->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     if (h->l2_persist_max && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, h->l2_persist_max) != cudaSuccess) {
@@ -843,6 +853,8 @@ static int ensure_stage(dhmc_handle* h, int i, size_t bytes) {
 }
 // Is `p` page-locked host memory that the device can address (cudaHostAlloc / cudaHostRegister)?  Then *dev is its device alias.
 static bool host_mapped(const void* p, void** dev) {
+  static const bool off = std::getenv("DHMC_NO_DIRECT") && std::atoi(std::getenv("DHMC_NO_DIRECT")) == 1;   // A/B switch: always stage
+  if (off) return false;
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
   if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
@@ -854,6 +866,9 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
                     double* eps_used, double* logdens, bool outputs_on_device, bool advance_t,
                     const double* q_host = nullptr, int thin = 1) {
   if ((!h->has_position && !q_host) || !h->has_eps) { h->err = "set position and step size (or run the initial search) first"; return DHMC_EARG; }
+  const auto tr0 = std::chrono::steady_clock::now();
+  auto tr_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count(); };
+  double tr_pt[6] = {0, 0, 0, 0, 0, 0};
   CK(cudaSetDevice(h->cfg.device));
   if (thin < 1 || N % thin != 0) { h->err = "thin >= 1 and N a multiple of thin"; return DHMC_EARG; }
   const size_t B = (size_t)h->cfg.n_chains, D = (size_t)h->cfg.dim, n = (size_t)(N / thin);   // n: kept draws per chain
@@ -912,6 +927,7 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
     CKR(cudaMalloc(&d_dir, sizeof(unsigned) * B));
     CKR(cudaMemcpyAsync(d_dir, dir_over_host, sizeof(unsigned) * B, cudaMemcpyHostToDevice, h->stream));
   }
+  tr_pt[0] = tr_ms();
   KArgs a = base_args(h);
   a.N = N; a.thin = thin; a.N_keep = (int)n; a.cfg = cfg; a.p_override = d_p; a.dir_override = d_dir;
   a.out_q = d_post; a.out_stats = d_stats; a.out_eps = d_eps; a.out_lq = d_ld;
@@ -923,6 +939,7 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   const bool staged_big = posterior && !direct[0] && out_bytes >= ((size_t)32 << 20);
   int nchunks = (!outputs_on_device && B >= 4096 && (staged_big || q_host)) ? 8 : 1;
   while (nchunks > 1 && B / (size_t)nchunks < (size_t)16 * (size_t)h->grid) nchunks /= 2;
+  if (const char* ev = std::getenv("DHMC_E2E_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16 && !outputs_on_device) nchunks = v; }
   CKR(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));   // status words describe the current call
   for (int ci = 0; ci < nchunks; ++ci) {
     const size_t c0 = B * ci / nchunks, c1 = B * (ci + 1) / nchunks, nc = c1 - c0;
@@ -953,22 +970,43 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
       if (stats && !direct[1]) CKR(cudaMemcpyAsync(stats + c0 * n, d_stats + c0 * n, sizeof(dhmc_tree_stats) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
       if (eps_used && !direct[2]) CKR(cudaMemcpyAsync(eps_used + c0 * n, d_eps + c0 * n, sizeof(double) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
       if (logdens && !direct[3]) CKR(cudaMemcpyAsync(logdens + c0 * n, d_ld + c0 * n, sizeof(double) * nc * n, cudaMemcpyDeviceToHost, h->copy_stream));
+      if (h->trace) CKR(cudaEventRecord(h->copy_ev[ci], h->copy_stream));
     }
   }
+  tr_pt[1] = tr_ms();
   unsigned long long steps = 0;
   CKR(cudaMemcpyAsync(&steps, h->total_steps, sizeof steps, cudaMemcpyDeviceToHost, h->stream));
   CKR(cudaStreamSynchronize(h->stream));
+  tr_pt[2] = tr_ms();
   CKR(cudaStreamSynchronize(h->copy_stream));
+  tr_pt[3] = tr_ms();
   CKS(read_timer(h));
+  if (h->trace && nchunks > 1) {
+    float t;
+    std::fprintf(stderr, "[dhmc trace] chunks %d:", nchunks);
+    for (int ci = 0; ci < nchunks; ++ci) {
+      float a = -1, b2 = -1, c = -1;
+      if (q_host) cudaEventElapsedTime(&a, h->ev0, h->h2d_ev[ci]);
+      cudaEventElapsedTime(&b2, h->ev0, h->chunk_ev[ci]);
+      if (!outputs_on_device) cudaEventElapsedTime(&c, h->ev0, h->copy_ev[ci]);
+      std::fprintf(stderr, " [h2d %.2f kern %.2f d2h %.2f]", a, b2, c);
+    }
+    cudaEventElapsedTime(&t, h->ev0, h->ev1);
+    std::fprintf(stderr, " total kernels %.2f ms | host: setup %.2f, enqueued %.2f, compute stream done %.2f, copy stream done %.2f\n", t,
+                 tr_pt[0], tr_pt[1], tr_pt[2], tr_pt[3]);
+    cudaGetLastError();
+  }
 #undef CKR
 #undef CKS
   cleanup();
   h->last_steps = (int64_t)steps;
   if (advance_t) h->t += (uint32_t)N;
   if (q_host) h->has_position = true;
+  if (h->trace) std::fprintf(stderr, "[dhmc trace] host: before status check %.2f ms\n", tr_ms());
   rc = sync_and_check_status(h, DHMC_CHAIN_NONFINITE_Q | DHMC_CHAIN_BAD_ACCEPTANCE | DHMC_CHAIN_BAD_STEPSIZE | (q_host ? DHMC_CHAIN_BAD_INITIAL : 0),
                              q_host ? "invalid initial position, or non-finite position / acceptance rate / step size while sampling"
                                     : "sampling: non-finite position, acceptance rate or step size");
+  if (h->trace) std::fprintf(stderr, "[dhmc trace] host: after status check %.2f ms\n", tr_ms());
   if (rc != DHMC_OK) return rc;
   if (cfg.metric == DHMC_METRIC_DIAGONAL && h->dense) {   // κ ← Diagonal: back to the diagonal kernels
     h->dense = false;

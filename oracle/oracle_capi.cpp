@@ -357,6 +357,7 @@ int orc_bench_mcmc(int family, int D, const double* params, int T, int max_depth
   mallopt(M_TRIM_THRESHOLD, 1 << 30);
   mallopt(M_TOP_PAD, 64 << 20);
   mallopt(M_MMAP_THRESHOLD, 1 << 30);
+  const int nparams = nparams_of(family, D);   // on the calling thread: the logistic N is thread-local state
   std::atomic<int> next{0};
   std::atomic<int64_t> steps{0};
   std::atomic<int> failed{0};
@@ -380,7 +381,7 @@ int orc_bench_mcmc(int family, int D, const double* params, int T, int max_depth
       int c = next.fetch_add(1);
       if (c >= n_chains) break;
       try {
-        Sampler S; S.l = make_model(family, D, params, nparams_of(family, D), T, 0);
+        Sampler S; S.l = make_model(family, D, params, nparams, T, 0);
         S.alg = NUTS{max_depth, min_delta}; S.key = dm_make_key(seed, (uint64_t)c);
         vec mv; if (minv0) mv.assign(minv0, minv0 + D);
         auto r = mcmc_with_warmup(S, N, stages, nullptr, minv0 ? &mv : nullptr, eps0);
