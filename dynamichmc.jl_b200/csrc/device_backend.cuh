@@ -333,6 +333,22 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// the same with an L2 eviction policy: the design matrix is re-read by every SM for every gradient (evict_last keeps it
+// resident while the per-chain metrics stream past), a chain's metric block is read once per mat-vec (evict_first)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
 __device__ __forceinline__ double lds64(uint32_t addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
@@ -416,6 +432,7 @@ __device__ __noinline__ bool coop_matvec_tma(bool active, long chain, int tid, i
   const uint32_t stage_bytes = (uint32_t)(sizeof(double) * kTmaRows * XS);
   const bool producer = (wq == NW - 1) && (lane == 0);
   const uint32_t n0 = ring_n;
+  const uint64_t pol = l2_policy_evict_first();
   auto nth_chain = [&](int ci) { unsigned m = amask; for (int i = 0; i < ci; ++i) m &= m - 1; return __ffs((int)m) - 1; };
   auto issue = [&](int b) {
     const uint32_t n = n0 + (uint32_t)b;
@@ -427,7 +444,7 @@ __device__ __noinline__ bool coop_matvec_tma(bool active, long chain, int tid, i
     char* dst = reinterpret_cast<char*>(ring + (size_t)s * kTmaRows * XS);
     const char* src = reinterpret_cast<const char*>(Mp + ((size_t)cb_chain[c] * rows_pad + (size_t)kb * kTmaRows) * XS);
 #pragma unroll
-    for (int pc = 0; pc < kTmaPieces; ++pc) bulk_g2s(dst + (size_t)pc * piece, src + (size_t)pc * piece, piece, full + s);
+    for (int pc = 0; pc < kTmaPieces; ++pc) bulk_g2s_hint(dst + (size_t)pc * piece, src + (size_t)pc * piece, piece, full + s, pol);
   };
   if (producer) {
     fence_proxy_async();
@@ -529,6 +546,7 @@ __device__ __noinline__ bool coop_core_tma(double* sll_out, bool active, int tid
   const uint32_t stage_bytes = (uint32_t)(sizeof(double) * kTmaRows * XS);
   const bool producer = (wq == NW - 1) && (lane == 0);
   const uint32_t n0 = ring_n;
+  const uint64_t pol = l2_policy_evict_last();
   auto issue = [&](int b) {                 // block b of this round -> stage (n0 + b) % 2
     const uint32_t n = n0 + (uint32_t)b;
     const int s = (int)(n & 1u);
@@ -540,7 +558,7 @@ __device__ __noinline__ bool coop_core_tma(double* sll_out, bool active, int tid
     const double* src = lXp + (size_t)b * kTmaRows * XS;
 #pragma unroll
     for (int pc = 0; pc < kTmaPieces; ++pc)
-      bulk_g2s(reinterpret_cast<char*>(dst) + (size_t)pc * piece, reinterpret_cast<const char*>(src) + (size_t)pc * piece, piece, full + s);
+      bulk_g2s_hint(reinterpret_cast<char*>(dst) + (size_t)pc * piece, reinterpret_cast<const char*>(src) + (size_t)pc * piece, piece, full + s, pol);
   };
   if (producer) {
     fence_proxy_async();                    // generic writes to the ring (Xᵀr hand-back) precede the async writes
