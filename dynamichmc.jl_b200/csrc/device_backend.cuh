@@ -31,29 +31,32 @@ constexpr int kMaxWarps = 8;   // T <= 256
 
 struct SmemLayout {
   int red_off;    // doubles: [2][kMaxWarps][kRedWidth]
-  int ctl_off;    // bytes from base: Entry[W][kMaxLevels+1]
+  int ctl_off;    // bytes from base: Entry[W][levels]
   int misc_off;   // bytes: int[4]
   int top_off;    // bytes: TopState[W] (transition-level scalars, one copy per warp)
-  int tab_off;    // bytes: double*[64] base address of every slot (shared or global)
+  int tab_off;    // bytes: double*[ntab] base address of every slot (shared or global)
   int xs_off;     // bytes: staging vector for the dense mat-vec (dense metric only)
   int slots_off;  // bytes
   size_t total;   // bytes
 };
 // stride = doubles per slot (a slot of the dense metric holds a (p, p♯) pair), xs = doubles of staging
-__host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride, size_t xs = 0) {
+// levels = stack entries per warp (max_depth + 1), ntab = entries of the slot-address table (>= n_slots); kernels for
+// max_depth <= 12 use the compile-time standard values
+constexpr int kStdLevels = 13, kStdTab = 64;
+__host__ __device__ inline SmemLayout smem_layout(int W, int n_sm, size_t stride, size_t xs = 0, int levels = kStdLevels, int ntab = kStdTab) {
   SmemLayout L;
   size_t off = 0;
   L.red_off = 0;
   off += sizeof(double) * 2 * kMaxWarps * kRedWidth;
   L.ctl_off = (int)off;
-  off += sizeof(Entry) * (size_t)W * (kMaxLevels + 1);
+  off += sizeof(Entry) * (size_t)W * (size_t)levels;
   off = (off + 15) & ~(size_t)15;
   L.misc_off = (int)off;
   off += 16;
   L.top_off = (int)off;
   off += ((sizeof(TopState) + 15) & ~(size_t)15) * (size_t)W;
   L.tab_off = (int)off;
-  off += sizeof(double*) * 64;
+  off += sizeof(double*) * (size_t)ntab;
   L.xs_off = (int)off;
   off += sizeof(double) * xs;
   L.slots_off = (int)off;
@@ -688,8 +691,9 @@ __device__ __noinline__ bool coop_core_tma(double* sll_out, bool active, int tid
 // (coop_round), so every element of X is read once per PACK gradients instead of once per
 // gradient — the family is bound by L2 traffic on X otherwise.  The per-chain arithmetic
 // and its order are unchanged (η_n sequential in j, (Xᵀr)_j sequential in n, Σ ll lane-strided).
-template <int EPL, int FAM, int WARPS, bool DENSE = false, int PACK = 1, bool MMA = false>
+template <int EPL, int FAM, int WARPS, bool DENSE = false, int PACK = 1, bool MMA = false, bool DEEP = false>
 struct DeviceBackend {
+  static constexpr bool kDeep = DEEP;     // max_depth > 12: the slot pool spills past its register word (nuts_machine.cuh)
   static constexpr bool kMma = MMA;      // likelihood rounds on the FP64 tensor cores, X streamed by TMA (packed groups only)
   static_assert(PACK == 1 || (WARPS <= 2 && FAM == DHMC_FAMILY_LOGISTIC), "packed groups: one or two warps per chain, logistic family");
   static constexpr int G = PACK;
@@ -729,9 +733,9 @@ struct DeviceBackend {
   __device__ __forceinline__ bool valid(int e) const { return tid + e * T < D; }
   // slot base addresses are tabulated once per CTA in shared memory: one LDS.64 instead of a
   // 64-bit select + multiply-add at every access
-  double** slot_tab;
+  double** slot_tab; int n_tab;
   __device__ __forceinline__ void build_slot_table() {
-    for (int s = tid; s < 64; s += T)
+    for (int s = tid; s < n_tab; s += T)
       slot_tab[s] = s < n_sm ? sm_slots + (size_t)s * stride : gl_slots + (size_t)(s - n_sm) * stride;
     group_sync();
   }
@@ -819,9 +823,7 @@ struct DeviceBackend {
   // ---- interface used by NutsMachine ----
   __device__ __forceinline__ TopState& top() const { return *tops; }
   __device__ __forceinline__ void top_sync() const { __syncwarp(); }
-  __device__ __forceinline__ uint64_t reserved_mask() const {
-    return (1ull << (n_slots - 1)) | (1ull << (n_slots - 2));   // Welford mean / M2
-  }
+  __device__ __forceinline__ int reserved_first() const { return n_slots - 2; }   // the two highest slots: Welford mean / M2
   __device__ __forceinline__ double cur_lq() const { return lq; }
   __device__ __forceinline__ void set_cur_lq(double v) { lq = v; }
 

@@ -39,8 +39,10 @@ using namespace dhmc;
 // kernel lookup, one function per (family, part) translation unit (family_tu.cu)
 #define DHMC_DECL_TU(f, p) const void* dhmc_family_kernel_##f##_##p(int W, int epl, int kernel, int dense);
 DHMC_DECL_TU(0, 0) DHMC_DECL_TU(1, 0) DHMC_DECL_TU(2, 0) DHMC_DECL_TU(3, 0) DHMC_DECL_TU(3, 1) DHMC_DECL_TU(3, 2)
+DHMC_DECL_TU(0, 3) DHMC_DECL_TU(1, 3) DHMC_DECL_TU(2, 3) DHMC_DECL_TU(3, 3)
 #undef DHMC_DECL_TU
-// part: 0 = one chain per CTA, 1 = packed chain groups with the FMA likelihood, 2 = packed groups on the tensor cores
+// part: 0 = one chain per CTA, 1 = packed chain groups with the FMA likelihood, 2 = packed groups on the tensor cores,
+// 3 = one chain per CTA with max_depth > 12 (persistent kernels only)
 static const void* lookup_kernel(int fam, int part, int W, int epl, KernelId k, bool dense) {
   switch (fam * 4 + part) {
     case 0: return dhmc_family_kernel_0_0(W, epl, k, dense);
@@ -49,6 +51,10 @@ static const void* lookup_kernel(int fam, int part, int W, int epl, KernelId k, 
     case 12: return dhmc_family_kernel_3_0(W, epl, k, dense);
     case 13: return dhmc_family_kernel_3_1(W, epl, k, dense);
     case 14: return dhmc_family_kernel_3_2(W, epl, k, dense);
+    case 3: return dhmc_family_kernel_0_3(W, epl, k, dense);
+    case 7: return dhmc_family_kernel_1_3(W, epl, k, dense);
+    case 11: return dhmc_family_kernel_2_3(W, epl, k, dense);
+    case 15: return dhmc_family_kernel_3_3(W, epl, k, dense);
   }
   return nullptr;
 }
@@ -206,9 +212,11 @@ struct dhmc_handle {
   dhmc_config cfg;
   int T = 0, W = 0, EPL = 0;
   int G = 1;                        // chains per CTA of the persistent kernels (packed chain groups)
+  bool deep = false;                // max_depth > 12: kernels whose slot pool spills past 64 slots (part 3), one chain per CTA
   bool coop_mma = false;            // packed groups: likelihood rounds on the FP64 tensor cores, X streamed by TMA
   size_t stride = 0;
   int n_slots = 0, n_sm = 0, grid = 0, sm_count = 0, light_grid = 0;
+  int levels = 13, ntab = 64;       // stack entries per warp (max_depth + 1), slot-table entries (>= n_slots)
   size_t smem_bytes = 0, smem_light = 0;
   size_t scratch_per_cta = 0;
   cudaStream_t stream = nullptr, copy_stream = nullptr, h2d_stream = nullptr;
@@ -258,6 +266,7 @@ static std::string g_create_err;
   } while (0)
 
 static void set_l2_window(dhmc_handle* h, const void* ptr, size_t bytes);
+static int kernel_part(const dhmc_handle* h, KernelId k, int G);
 
 // rows of N doubles in the logistic scratch: one per CTA of the light kernels, 2·G per CTA
 // (residuals and ll terms of every packed chain) of the persistent kernels
@@ -275,14 +284,14 @@ static int plan(dhmc_handle* h) {
   const size_t xs = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? h->stride : 0;
   const int G = h->G;
   auto heavy_smem = [&](int n_sm) -> size_t {
-    return G > 1 ? (size_t)G * group_smem_bytes(h->W, n_sm, slot_doubles, xs) + coop_smem_bytes(G, h->coop_mma, (int)h->cfg.dim)
-                 : smem_layout(h->W, n_sm, slot_doubles, xs).total;
+    return G > 1 ? (size_t)G * group_smem_bytes(h->W, n_sm, slot_doubles, xs, h->levels, h->ntab) + coop_smem_bytes(G, h->coop_mma, (int)h->cfg.dim)
+                 : smem_layout(h->W, n_sm, slot_doubles, xs, h->levels, h->ntab).total;
   };
   struct { size_t total; } L0{heavy_smem(0)};
-  h->smem_light = smem_layout(h->W, 0, slot_doubles, xs).total;
+  h->smem_light = smem_layout(h->W, 0, slot_doubles, xs).total;      // light kernels: standard layout
   int& reg_ctas = h->reg_ctas[h->dense ? 1 : 0];
   if (reg_ctas == 0) {
-    const void* fn = lookup_kernel(h->cfg.family, G > 1 ? (h->coop_mma ? 2 : 1) : 0, h->W, h->EPL, K_NUTS, h->dense);
+    const void* fn = lookup_kernel(h->cfg.family, kernel_part(h, K_NUTS, G), h->W, h->EPL, K_NUTS, h->dense);
     if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L0.total);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, fn, T * G, L0.total);
@@ -326,6 +335,12 @@ static void set_l2_window(dhmc_handle* h, const void* ptr, size_t bytes) {
   if (cudaStreamSetAttribute(h->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
 }
 
+static int kernel_part(const dhmc_handle* h, KernelId k, int G) {
+  const bool heavy = (k == K_NUTS || k == K_SEARCH);
+  if (heavy && h->deep) return 3;
+  return G > 1 ? (h->coop_mma ? 2 : 1) : 0;
+}
+
 static KArgs base_args(dhmc_handle* h) {
   KArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -337,6 +352,7 @@ static KArgs base_args(dhmc_handle* h) {
   a.t0 = h->t;
   a.scratch = h->scratch; a.scratch_per_cta = h->scratch_per_cta;
   a.n_sm = h->n_sm; a.n_slots = h->n_slots; a.stride = h->stride * (h->dense ? 2 : 1);
+  a.levels = h->levels; a.ntab = h->ntab;
   a.counter = h->counter; a.total_steps = h->total_steps;
   a.chain_begin = 0; a.chain_end = (int)h->cfg.n_chains;
   a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr; a.minv_pad = h->minv_pad;
@@ -377,7 +393,7 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_st
   }
 #endif
   {
-    const void* fn = lookup_kernel(h->cfg.family, G > 1 ? (h->coop_mma ? 2 : 1) : 0, h->W, h->EPL, k, h->dense);
+    const void* fn = lookup_kernel(h->cfg.family, kernel_part(h, k, G), h->W, h->EPL, k, h->dense);
     if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
@@ -485,7 +501,7 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   if (!cfg || !out) { g_create_err = "null argument"; return DHMC_EARG; }
   *out = nullptr;
   // @argcheck sites: NUTS.jl:190-191
-  if (!(cfg->max_depth > 0 && cfg->max_depth <= kMaxLevels)) { g_create_err = "0 < max_depth <= 12 (this build)"; return DHMC_EARG; }
+  if (!(cfg->max_depth > 0 && cfg->max_depth <= kMaxLevels)) { g_create_err = "0 < max_depth <= MAX_DIRECTIONS_DEPTH (32)"; return DHMC_EARG; }   // NUTS.jl:190, trees.jl:10
   if (!(cfg->min_delta < 0)) { g_create_err = "min_delta < 0"; return DHMC_EARG; }
   if (cfg->dim < 1 || cfg->n_chains < 1 || cfg->n_chains > (1ll << 30)) { g_create_err = "dim >= 1, 1 <= n_chains <= 2^30"; return DHMC_EARG; }
   if (cfg->family < 0 || cfg->family >= DHMC_FAMILY_COUNT) { g_create_err = "unknown family"; return DHMC_EARG; }
@@ -498,7 +514,8 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   // above) sharing every pass over X (packed chain groups); an explicit threads_per_chain keeps
   // one chain per CTA
   int pack = 1;
-  if (cfg->family == DHMC_FAMILY_LOGISTIC && rt == 0 && cfg->dim <= 32 * kPack) {
+  const bool deep = cfg->max_depth > 12;
+  if (cfg->family == DHMC_FAMILY_LOGISTIC && rt == 0 && cfg->dim <= 32 * kPack && !deep) {
     const char* ev = std::getenv("DHMC_PACK");
     // one warp per chain (8 elements per lane above dim 128): eight warps at 255 registers — the tensor-core rounds
     // need only two warps per sub-partition, and the state machine does not spill; DHMC_PACK_WARPS=2: two warps per chain
@@ -520,8 +537,10 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   }
   if (cfg->device < 0 || cfg->device >= ndev) { g_create_err = "bad device ordinal"; return DHMC_EARG; }
   dhmc_handle* h = new dhmc_handle();
-  h->cfg = *cfg; h->T = T; h->W = T / 32; h->EPL = EPL; h->stride = (size_t)T * EPL; h->G = pack; h->coop_mma = coop_mma;
+  h->cfg = *cfg; h->T = T; h->W = T / 32; h->EPL = EPL; h->stride = (size_t)T * EPL; h->G = pack; h->coop_mma = coop_mma; h->deep = deep;
   h->n_slots = slots_needed(cfg->max_depth);
+  h->levels = deep ? cfg->max_depth + 1 : kStdLevels;        // deep persistent kernels size their stack / slot table at run time
+  h->ntab = deep ? std::max(kStdTab, (h->n_slots + 7) & ~7) : kStdTab;
   auto fail = [&](int rc) { g_create_err = h->err; dhmc_destroy(h); return rc; };
 #define CKC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); return fail(e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA); } } while (0)
   CKC(cudaSetDevice(cfg->device));

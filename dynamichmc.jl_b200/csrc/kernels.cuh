@@ -58,6 +58,8 @@ struct KArgs {
   double* lr;                   // logistic scratch: [grid][lN] residuals, or per CTA of packed groups [lN][G] residuals + [G][lN] ll terms
   int lN, lLd;                  // observations, leading dimension of Xᵀ (even)
   const double* lXp;            // tensor-core likelihood: zero-padded row blocks of X
+  int levels, ntab;             // deep kernels (max_depth > 12) only: stack entries per warp (max_depth + 1), slot-table entries;
+                                // all other kernels use the compile-time kStdLevels / kStdTab so that the offsets fold into immediates
   int thin, N_keep;             // draws: every thin-th transition is kept (N_keep = N / thin rows per chain)
   const double* minv_pad;       // tensor-core mat-vec: padded M⁻¹ [B][⌈D/32⌉·32][tma_xs(D)]
   unsigned long long* prof;     // profiling builds (-DDHMC_PROFILE_ROUNDS): [grid][32 warps][16] cycle counters
@@ -80,17 +82,17 @@ __host__ __device__ constexpr size_t coop_ring_doubles(int G) { return (size_t)k
 __host__ __device__ inline size_t coop_smem_bytes(int G, bool mma, int D) {
   return mma ? tma_smem_bytes(G, D) : 64 + sizeof(double) * (coop_beta_doubles(G) + coop_ring_doubles(G));
 }
-__host__ __device__ inline size_t group_smem_bytes(int W, int n_sm, size_t stride, size_t xs) {
-  return (smem_layout(W, n_sm, stride, xs).total + 127) & ~(size_t)127;   // the CTA-shared area behind the groups stays 128-byte aligned
+__host__ __device__ inline size_t group_smem_bytes(int W, int n_sm, size_t stride, size_t xs, int levels, int ntab) {
+  return (smem_layout(W, n_sm, stride, xs, levels, ntab).total + 127) & ~(size_t)127;   // the CTA-shared area behind the groups stays 128-byte aligned
 }
 
-template <int EPL, int FAM, int W, bool DN, int G, bool MM>
-__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G, MM>& b, const KArgs& a,
+template <int EPL, int FAM, int W, bool DN, int G, bool MM, bool DP>
+__device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G, MM, DP>& b, const KArgs& a,
                                               unsigned char* smem) {
   b.ctid = threadIdx.x; b.grp = 0;
   b.tid = threadIdx.x; b.lane = threadIdx.x & 31; b.warp = threadIdx.x >> 5;
   b.D = a.D;
-  const SmemLayout L = smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles);
+  const SmemLayout L = smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles, DP ? a.levels : kStdLevels, DP ? a.ntab : kStdTab);
   b.lX = a.lX; b.lXt = a.lXt; b.ly = a.ly; b.lN = a.lN; b.lLd = a.lLd;
   b.lr = a.lr ? a.lr + (size_t)blockIdx.x * a.lN : nullptr;
   b.lll = nullptr; b.cb_flags = nullptr; b.cb_beta = b.cb_grad = b.cb_stage = nullptr;
@@ -100,7 +102,7 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G, 
   if constexpr (G > 1) {
     b.grp = threadIdx.x / (32 * W); b.tid = threadIdx.x % (32 * W); b.warp = b.tid >> 5;
     group = (size_t)blockIdx.x * G + b.grp;
-    const size_t per = group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles);
+    const size_t per = group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles, DP ? a.levels : kStdLevels, DP ? a.ntab : kStdTab);
     unsigned char* shared = smem + per * G;            // the area after the G per-group blocks (128-byte aligned)
     b.cb_shared = shared;
     b.cb_flags = reinterpret_cast<int*>(shared);
@@ -138,12 +140,12 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G, 
   b.red = reinterpret_cast<double*>(smem + L.red_off);
   b.red_buf = 0;
   b.rexp_cache = 0.0; b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;
-  b.ctl = reinterpret_cast<Entry*>(smem + L.ctl_off) + b.warp * (kMaxLevels + 1);
+  b.ctl = reinterpret_cast<Entry*>(smem + L.ctl_off) + b.warp * (DP ? a.levels : kStdLevels);
   b.tops = reinterpret_cast<TopState*>(smem + L.top_off + b.warp * ((sizeof(TopState) + 15) & ~(size_t)15));
   b.sm_slots = reinterpret_cast<double*>(smem + L.slots_off);
   b.gl_slots = a.scratch + group * a.scratch_per_cta;
   b.n_sm = a.n_sm; b.n_slots = a.n_slots;
-  b.slot_tab = reinterpret_cast<double**>(smem + L.tab_off);
+  b.slot_tab = reinterpret_cast<double**>(smem + L.tab_off); b.n_tab = DP ? a.ntab : kStdTab;
   b.build_slot_table();
   b.mparams = a.mparams;
 }
@@ -169,8 +171,8 @@ __device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc, int be
   return s_misc[0];
 }
 
-template <int EPL, int FAM, int W, bool DN, int G, bool MM>
-__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN, G, MM>& b, const KArgs& a, long c,
+template <int EPL, int FAM, int W, bool DN, int G, bool MM, bool DP>
+__device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN, G, MM, DP>& b, const KArgs& a, long c,
                                            bool with_p) {
   b.chain = c;
   b.rexp_base = 0xffffffffu; b.rexp_t = 0xffffffffu;   // the randexp batch belongs to one chain
@@ -194,8 +196,8 @@ __device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN, G, MM>
     if (with_p) b.matvec(b.p, b.ps);
   }
 }
-template <int EPL, int FAM, int W, bool DN, int G, bool MM>
-__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN, G, MM>& b, double* dst,
+template <int EPL, int FAM, int W, bool DN, int G, bool MM, bool DP>
+__device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN, G, MM, DP>& b, double* dst,
                                           const double (&v)[EPL], size_t base, int D) {
 #pragma unroll
   for (int e = 0; e < EPL; ++e) {
@@ -205,9 +207,9 @@ __device__ __forceinline__ void store_vec(const DeviceBackend<EPL, FAM, W, DN, G
 }
 
 // ------------------------------------------------------------------ k_nuts
-template <int EPL, int FAM, int W, bool DN, int G, bool MM>
+template <int EPL, int FAM, int W, bool DN, int G, bool MM, bool DP>
 struct DrawSink {
-  DeviceBackend<EPL, FAM, W, DN, G, MM>& b;
+  DeviceBackend<EPL, FAM, W, DN, G, MM, DP>& b;
   const KArgs& a;
   long c;
   __device__ __forceinline__ void operator()(int n, const dhmc_tree_stats& ts, double e) {
@@ -231,25 +233,25 @@ struct DrawSink {
   }
 };
 
-template <int EPL, int FAM, int W, bool DN, int G = 1, bool MM = false>
+template <int EPL, int FAM, int W, bool DN, int G = 1, bool MM = false, bool DP = false>
 __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nuts(const KArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN, G, MM> b;
+  DeviceBackend<EPL, FAM, W, DN, G, MM, DP> b;
 #ifdef DHMC_PROFILE_ROUNDS
   const long long pf_kernel_t0 = clock64();
 #endif
   setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles) : 0) +
-                                       smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
+  int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles, DP ? a.levels : kStdLevels, DP ? a.ntab : kStdTab) : 0) +
+                                       smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles, DP ? a.levels : kStdLevels, DP ? a.ntab : kStdTab).misc_off);
   for (;;) {
     int c;
     if constexpr (G > 1) c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
     else c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM, DP>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
-    DrawSink<EPL, FAM, W, DN, G, MM> sink{b, a, c};
+    DrawSink<EPL, FAM, W, DN, G, MM, DP> sink{b, a, c};
     const double eps_next = m.run(a.t0, a.N, a.eps[c], a.cfg, a.p_override,
                                   a.dir_override ? a.dir_override + c : nullptr, sink);
     const size_t base = (size_t)c * a.D;
@@ -270,20 +272,20 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nu
 }
 
 // ------------------------------------------------------------------ k_search
-template <int EPL, int FAM, int W, bool DN, int G = 1, bool MM = false>
+template <int EPL, int FAM, int W, bool DN, int G = 1, bool MM = false, bool DP = false>
 __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_search(const KArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  DeviceBackend<EPL, FAM, W, DN, G, MM> b;
+  DeviceBackend<EPL, FAM, W, DN, G, MM, DP> b;
   setup_backend(b, a, smem);
-  int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles) : 0) +
-                                       smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles).misc_off);
+  int* s_misc = reinterpret_cast<int*>(smem + (G > 1 ? b.grp * group_smem_bytes(W, a.n_sm, b.stride, (size_t)a.xs_doubles, DP ? a.levels : kStdLevels, DP ? a.ntab : kStdTab) : 0) +
+                                       smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles, DP ? a.levels : kStdLevels, DP ? a.ntab : kStdTab).misc_off);
   for (;;) {
     int c;
     if constexpr (G > 1) c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
     else c = next_chain(a.counter, s_misc, a.chain_begin);
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
-    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
+    NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM, DP>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
                                            a.max_depth, a.min_delta, a.n_slots);
     const double eps = m.find_initial_stepsize(a.s_init, a.s_thresh, a.s_maxiter, a.p_override);
     if (b.tid == 0) {
@@ -383,10 +385,22 @@ constexpr int kPack = 8;            // packed chain groups: chains per CTA (logi
 constexpr bool packed_layout(int W, int EPL) { return (W == 1) || (W == 2 && EPL == 4); }
 
 // which subset of a family's kernels a translation unit instantiates (build parallelism):
-//   PART 0: one chain per CTA;  PART 1: packed groups, FMA likelihood;  PART 2: packed groups, tensor-core likelihood
+//   PART 0: one chain per CTA;  PART 1: packed groups, FMA likelihood;  PART 2: packed groups, tensor-core likelihood;
+//   PART 3: one chain per CTA, max_depth > 12 (k_nuts / k_search only)
 template <int EPL, int FAM, int W, int PART>
 const void* kernel_ptr(KernelId k, bool dense) {
-  if constexpr (PART > 0) {
+  if constexpr (PART == 3) {        // max_depth > 12: one chain per CTA, slot pool with spill words
+    if (dense) {
+      if constexpr (dense_layout(W, EPL)) {
+        if (k == K_NUTS) return (const void*)k_nuts<EPL, FAM, W, true, 1, false, true>;
+        if (k == K_SEARCH) return (const void*)k_search<EPL, FAM, W, true, 1, false, true>;
+      }
+      return nullptr;
+    }
+    if (k == K_NUTS) return (const void*)k_nuts<EPL, FAM, W, false, 1, false, true>;
+    if (k == K_SEARCH) return (const void*)k_search<EPL, FAM, W, false, 1, false, true>;
+    return nullptr;
+  } else if constexpr (PART > 0) {
     if constexpr (FAM == DHMC_FAMILY_LOGISTIC && packed_layout(W, EPL)) {
       constexpr bool MM = PART == 2;
       if (k == K_NUTS) return dense ? (const void*)k_nuts<EPL, FAM, W, true, kPack, MM> : (const void*)k_nuts<EPL, FAM, W, false, kPack, MM>;

@@ -40,13 +40,16 @@
 
 #if defined(__CUDACC__)
 #define DHMC_M __device__ __forceinline__
+#define DHMC_COLD __device__ __noinline__      // rarely taken paths: kept out of line so that they cost the hot loop no registers
 #else
 #define DHMC_M inline
+#define DHMC_COLD inline
 #endif
 
 namespace dhmc {
 
-constexpr int kMaxLevels = 12;   // max_depth <= 12 in this build
+constexpr int kMaxLevels = 32;   // max_depth <= MAX_DIRECTIONS_DEPTH = 32 (trees.jl:10, NUTS.jl:190)
+constexpr int kMaskWords = 3;    // slot free-list: 64 slots in a register word + two spill words (max_depth > 12 needs up to 164 slots)
 constexpr int kFixedSlots = 7;   // OTHER(q,p,g) NEARP RHOT ZT(q,g)
 constexpr int kWelfordSlots = 2; // running mean / M2 of the metric window
 
@@ -87,6 +90,7 @@ struct TopState {
   int i_near, i_far, depth, regs_fwd;
   uint32_t flags, dirs;
   int s_oq, s_og, s_zq, s_zg, s_op, s_near, s_rhot;
+  uint64_t free_hi[kMaskWords - 1];   // slots 64…: touched only when max_depth > 12
 };
 
 template <class B>
@@ -104,30 +108,109 @@ struct NutsMachine {
   DHMC_M NutsMachine(B& b_, dm_rng_key k, int md, double mind, int nslots)
       : b(b_), key(k), max_depth(md), min_delta(mind), n_slots(nslots) {}
 
-  // ---- slot pool (bit set = free).  Low indices are the on-chip slots. ----
-  DHMC_M int alloc_lo() {
-    uint64_t m = freemask;
+  // ---- slot pool (bit set = free).  Low indices are the on-chip slots.  Slots 0…63 live in the register word
+  // `freemask`; deeper trees (max_depth > 12: up to 164 slots) spill to TopState::free_hi, which the common
+  // configurations never touch; the spill paths exist only in backends with kDeep (separate kernel instantiations), so the
+  // max_depth <= 12 kernels are exactly the single-word code. ----
+  DHMC_M static int ffs64(uint64_t m) {        // index of the lowest set bit (m != 0)
 #if defined(__CUDA_ARCH__)
-    int s = m ? __ffsll((long long)m) - 1 : 63;
+    return __ffsll((long long)m) - 1;
 #else
     int s = 0;
-    while (s < 63 && !((m >> s) & 1ull)) ++s;  // pool is sized so that a free slot exists
+    while (!((m >> s) & 1ull)) ++s;
+    return s;
 #endif
+  }
+  DHMC_M static int fls64(uint64_t m) {        // index of the highest set bit (m != 0)
+#if defined(__CUDA_ARCH__)
+    return 63 - __clzll((long long)m);
+#else
+    int s = 63;
+    while (!((m >> s) & 1ull)) --s;
+    return s;
+#endif
+  }
+  DHMC_M void init_pool() {
+    const int r0 = b.reserved_first();           // slots r0, r0 + 1 are reserved (window statistics)
+    freemask = n_slots >= 64 ? ~0ull : ((1ull << n_slots) - 1ull);
+    if (r0 < 64) freemask &= ~(1ull << r0);
+    if (r0 + 1 < 64) freemask &= ~(1ull << (r0 + 1));
+    if constexpr (B::kDeep) { if (n_slots > 64) init_pool_hi(r0); }
+  }
+  DHMC_COLD void init_pool_hi(int r0) {
+    TopState& S = b.top();
+    for (int w = 1; w < kMaskWords; ++w) {
+      const int lo = 64 * w;
+      uint64_t m = n_slots >= lo + 64 ? ~0ull : (n_slots > lo ? ((1ull << (n_slots - lo)) - 1ull) : 0ull);
+      if (r0 >= lo && r0 < lo + 64) m &= ~(1ull << (r0 - lo));
+      if (r0 + 1 >= lo && r0 + 1 < lo + 64) m &= ~(1ull << (r0 + 1 - lo));
+      S.free_hi[w - 1] = m;
+    }
+    b.top_sync();
+  }
+  DHMC_M int alloc_lo() {
+    const uint64_t m = freemask;
+    if constexpr (B::kDeep) {
+      if (!m && n_slots > 64) return alloc_lo_hi();
+    }
+    const int s = m ? ffs64(m) : 63;             // (n_slots <= 64: the pool is sized so that a free slot exists)
     freemask = m & ~(1ull << s);
     return s;
+  }
+  DHMC_COLD int alloc_lo_hi() {
+    TopState& S = b.top();
+    for (int w = 0; w < kMaskWords - 1; ++w) {
+      const uint64_t mh = S.free_hi[w];
+      if (mh) {
+        const int s = ffs64(mh);
+        b.top_sync();
+        S.free_hi[w] = mh & ~(1ull << s);
+        b.top_sync();
+        return 64 * (w + 1) + s;
+      }
+    }
+    return 63;
   }
   DHMC_M int alloc_hi() {
-    uint64_t m = freemask;
-#if defined(__CUDA_ARCH__)
-    int s = m ? 63 - __clzll((long long)m) : 0;
-#else
-    int s = n_slots - 1;
-    while (s > 0 && !((m >> s) & 1ull)) --s;
-#endif
+    if constexpr (B::kDeep) {
+      if (n_slots > 64) {
+        const int s = alloc_hi_hi();
+        if (s >= 0) return s;
+      }
+    }
+    const uint64_t m = freemask;
+    const int s = m ? fls64(m) : 0;
     freemask = m & ~(1ull << s);
     return s;
   }
-  DHMC_M void release(int s) { freemask |= (1ull << s); }
+  DHMC_COLD int alloc_hi_hi() {
+    TopState& S = b.top();
+    for (int w = kMaskWords - 2; w >= 0; --w) {
+      const uint64_t mh = S.free_hi[w];
+      if (mh) {
+        const int s = fls64(mh);
+        b.top_sync();
+        S.free_hi[w] = mh & ~(1ull << s);
+        b.top_sync();
+        return 64 * (w + 1) + s;
+      }
+    }
+    return -1;
+  }
+  DHMC_M void release(int s) {
+    if constexpr (B::kDeep) {
+      if (s < 64) freemask |= (1ull << s);
+      else release_hi(s);
+    } else {
+      freemask |= (1ull << s);
+    }
+  }
+  DHMC_COLD void release_hi(int s) {
+    TopState& S = b.top();
+    b.top_sync();
+    S.free_hi[(s >> 6) - 1] |= 1ull << (s & 63);
+    b.top_sync();
+  }
 
   // rand_bool_logprob — NUTS.jl:43-45 (no draw when logprob ≥ 0)
   DHMC_M bool rand_bool_logprob(double logprob) {
@@ -152,7 +235,7 @@ struct NutsMachine {
     const double pi0 = b.phase_logdensity();  // logdensity(H, z), NUTS.jl:236
 
     // ---- initial leaf (trees.jl:285, NUTS.jl:148-159 with is_initial) ----
-    freemask = (n_slots >= 64 ? ~0ull : ((1ull << n_slots) - 1ull)) & ~b.reserved_mask();
+    init_pool();
     S.s_oq = alloc_hi(); S.s_og = alloc_hi();         // other edge q, ∇ℓ (rarely touched)
     S.s_zq = alloc_hi(); S.s_zg = alloc_hi();         // proposal ζ of the whole tree
     S.s_op = alloc_lo();                              // other edge p  (= far-edge momentum)
@@ -402,7 +485,7 @@ struct NutsMachine {
     b.draw_search_momentum(key, p_override);
     const double l0 = b.phase_logdensity();
     if (!dm_isfinite(l0)) { status |= DHMC_CHAIN_SEARCH_FAILED; return dm_nan(); }
-    freemask = (n_slots >= 64 ? ~0ull : ((1ull << n_slots) - 1ull)) & ~b.reserved_mask();
+    init_pool();
     const int sq = alloc_lo(), sp = alloc_lo(), sg = alloc_lo();
     b.st_q(sq); b.st_p(sp); b.st_g(sg);
     const double lq0 = b.cur_lq();

@@ -51,7 +51,8 @@ struct HostBackend {
   TopState top_;
   TopState& top() { return top_; }
   void top_sync() {}
-  uint64_t reserved_mask() const { return 0; }
+  static constexpr bool kDeep = true;              // exercise the spill words of the slot pool on the host as well
+  int reserved_first() const { return 1 << 20; }   // no reserved slots in the host simulation
   double cur_lq() const { return lq; }
   void set_cur_lq(double v) { lq = v; }
   void st_q(int s) { slots[s] = q; }
@@ -204,7 +205,8 @@ struct DummyBackend {
   explicit DummyBackend(int nslots) : slots(nslots, 0) {}
   TopState& top() { return top_; }
   void top_sync() {}
-  uint64_t reserved_mask() const { return 0; }
+  static constexpr bool kDeep = true;              // exercise the spill words of the slot pool on the host as well
+  int reserved_first() const { return 1 << 20; }   // no reserved slots in the host simulation
   double cur_lq() const { return 0.0; }
   void set_cur_lq(double) {}
   void st_q(int s) { slots[s] = z; }

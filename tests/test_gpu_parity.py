@@ -501,6 +501,35 @@ def test_c4_shape_matches_oracle(pkg, po):
     r["engine"].close()
 
 
+@pytest.mark.parametrize("D,max_depth,eps_lo,eps_hi", [(3, 15, 2e-4, 4e-4), (2, 20, 4e-4, 3e-3), (40, 32, 2e-4, 6e-4)])
+def test_deep_trees_match_oracle(pkg, po, D, max_depth, eps_lo, eps_hi):
+    """max_depth beyond 12 (reference limit: 0 < max_depth ≤ 32, NUTS.jl:190, trees.jl:10): the slot pool spills past its
+    64-slot register word.  Tiny step sizes make the trees 11-15 doublings deep — some end at max_depth, some by a U-turn
+    deep in the tree — and every integer and the new position must still equal the recursive oracle's."""
+    rng = np.random.default_rng(max_depth)
+    K = 6
+    ℓ = pkg.StandardNormal(D)
+    eng = _engine(pkg, ℓ, K, seed=31, algorithm=pkg.NUTS(max_depth=max_depth))
+    T, _ = eng.layout()
+    q = rng.normal(size=(K, D))
+    eps = np.exp(rng.uniform(np.log(eps_lo), np.log(eps_hi), K))
+    eng.set_position(q); eng.set_stepsize(eps)
+    depths = []
+    for t in range(2):
+        stats = eng.sample_tree()
+        st = eng.get_state(("q", "grad"))
+        for k in range(K):
+            o = po.sample_tree(po.FAMILY_STD_NORMAL, q[k], eps[k], 31, k, t, T=T, max_depth=max_depth)
+            for f in INT_FIELDS:
+                assert o["stats"][f] == stats[k][f], (f, k, t, o["stats"], stats[k])
+            assert o["stats"]["pi"] == stats[k]["pi"] and o["stats"]["acceptance_rate"] == stats[k]["acceptance_rate"]
+            assert np.array_equal(st["q"][k], o["q"]) and np.array_equal(st["grad"][k], o["g"])
+            depths.append(int(stats[k]["depth"]))
+        q = st["q"]
+    assert max(depths) >= min(13, max_depth)        # the spill words of the slot pool were really used
+    eng.close()
+
+
 # --------------------------------------------------------------- trajectory diagnostics (diagnostics.jl:139-216)
 def test_trajectory_diagnostics_match_oracle(pkg, po):
     D = 37
