@@ -146,3 +146,19 @@ def test_julia_shim_ccall_signatures_match_the_header():
         assert len(parts) - 2 == ntypes, f"{m.group(1)}: {len(parts) - 2} arguments for {ntypes} types"
         n += 1
     assert n >= 10
+
+
+def test_julia_shim_passes_the_chain_count_to_chain_status():
+    """Round-1 defect: `_throw` called chain_status(ptr) with a default K = 0, so failed_chains was always empty.
+    Every call (and the definition) must carry the chain count, and the error path must forward it."""
+    jl = open(os.path.join(ROOT, "julia", "B200HMC.jl")).read()
+    jl = re.sub(r"#[^\n]*", "", jl)
+    calls = re.findall(r"chain_status\(([^()]*)\)", jl)
+    assert len(calls) >= 2
+    for c in calls:
+        assert len(_split_top_level(c)) == 2, f"chain_status({c}): expected (ptr, K)"
+    assert "K = 0" not in jl and re.search(r"_ck\(h::Handle, rc\).*h\.K", jl)
+    # the dense metric is returned as Symmetric(M⁻¹) when the handle is dense, the reference API surface is present
+    for needle in ("dhmc_metric_is_dense", "dhmc_get_metric_dense", "Symmetric(M", "function mcmc_keep_warmup", "mcmc_steps(",
+                   "function mcmc_next_step", "reporter"):
+        assert needle in jl, needle

@@ -29,6 +29,29 @@ def test_oracle_reproduces_golden_vectors(po):
         assert np.array_equal(ql, _f(c["leapfrog2"]["q"])) and np.array_equal(pl, _f(c["leapfrog2"]["p"]))
 
 
+JULIA_FIXTURES = sorted(f for f in os.listdir(os.path.join(HERE, "golden")) if f.startswith("julia_") and f.endswith(".json"))
+FAMILY_IDS = {"std_normal": 0, "diag_normal": 1, "funnel": 2, "logistic": 3}
+
+
+@pytest.mark.skipif(not JULIA_FIXTURES, reason="no tests/golden/julia_*.json: julia/parity.jl has not been run (no Julia in the build image)")
+@pytest.mark.parametrize("fname", JULIA_FIXTURES or ["-"])
+def test_julia_fixtures_when_present(po, fname):
+    """Vectors written by julia/parity.jl from the REAL DynamicHMC.jl (momenta and direction words injected through
+    sample_tree's p= / directions= keywords, randexp from the engine's Philox stream): the oracle must reproduce every
+    integer of TreeStatisticsNUTS exactly and the new position within 1e-10 relative (BASELINE.json north_star)."""
+    fx = json.load(open(os.path.join(HERE, "golden", fname)))
+    fam = FAMILY_IDS[fx["family"]]
+    params = np.array(fx["params"], float) if fx["params"] else None
+    for c in fx["cases"]:
+        r = po.sample_tree(fam, np.array(c["q"], float), c["eps"], fx["seed"], c["chain"], c["t"], params=params,
+                           p=np.array(c["p"], float), directions=c["directions"], T=32)
+        for f in ("depth", "left", "right", "steps", "directions"):
+            assert int(r["stats"][f]) == int(c["stats"][f]), (fname, c["chain"], c["t"], f)
+        np.testing.assert_allclose(r["q"], np.array(c["q_new"], float), rtol=1e-10, atol=0)
+        np.testing.assert_allclose(r["stats"]["pi"], c["stats"]["pi"], rtol=1e-10)
+        np.testing.assert_allclose(r["stats"]["acceptance_rate"], c["stats"]["acceptance_rate"], rtol=1e-10, atol=1e-300)
+
+
 @pytest.mark.gpu
 def test_cuda_reproduces_golden_vectors(pkg, po):
     for c in CASES:

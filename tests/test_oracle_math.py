@@ -108,3 +108,28 @@ def test_canonical_reduction_width(po):
             off //= 2
     part[0] = part[0] + part[32]
     assert po.canon_dot(T, a, b) == part[0]
+
+
+def test_logaddexp_at_logexpfunctions_branch_points(po):
+    """LogExpFunctions.logaddexp(x, y) = max + log1pexp(-|x - y|), and its Float64 log1pexp switches formulas at
+    x0 ≈ -745.13 (exp underflows), x1 ≈ -36.74 (log1p(e) == e), x2 ≈ 18.02 and x3 ≈ 33.23.  The package is
+    not vendored with the reference, so these are pinned against an 80-digit evaluation: the engine's table-driven
+    logaddexp must agree with the true value to a few ulp ON BOTH SIDES of every branch point (any branch of the Julia
+    implementation is itself accurate to ~1 ulp there, so this bounds the engine-vs-Julia difference)."""
+    import mpmath
+    mpmath.mp.dps = 80
+    pts = []
+    for c in (-745.1332191019412, -36.7368005696771, 18.021826694558577, 33.23111882352963, 0.0, -1e-300, -0.6931471805599453):
+        for k in (-3, -1, 0, 1, 3):
+            pts.append(float(np.nextafter(c, np.inf)) if k > 0 else float(np.nextafter(c, -np.inf)) if k < 0 else c)
+            pts.append(c + k * 1e-9)
+    pts = np.array(sorted(set(pts)))
+    for base in (0.0, 3.5, -120.25, 1e6):
+        a = np.full(pts.size, base); b = base + pts          # b - a = the branch-point argument
+        got = po.math("logaddexp", a, b)
+        for ai, bi, gi in zip(a, b, got):
+            true = mpmath.log(mpmath.exp(mpmath.mpf(ai)) + mpmath.exp(mpmath.mpf(bi))) if max(ai, bi) < 700 else \
+                mpmath.mpf(max(ai, bi)) + mpmath.log1p(mpmath.exp(-abs(mpmath.mpf(ai) - mpmath.mpf(bi))))
+            err = abs(mpmath.mpf(float(gi)) - true)
+            ulp = np.spacing(abs(float(true))) if float(true) != 0 else 5e-324
+            assert err <= 4 * ulp + mpmath.mpf(2.3e-16), (ai, bi, gi, float(true))
