@@ -169,6 +169,97 @@ def test_full_warmup_matches_oracle(pkg, po, fam, D):
     r["engine"].close()
 
 
+def _c5_model(pkg, D=1000):
+    """BASELINE.json configs[4]: MvNormal with σᵢ² = 10^{4(i−1)/(D−1)} (κ = 10⁴), SURVEY.md §8d."""
+    return pkg.DiagNormal(np.zeros(D), 10.0 ** (4.0 * np.arange(D) / (D - 1)))
+
+
+def test_c5_shape_full_default_warmup_matches_oracle(pkg, po):
+    """C5 at its exact shape: D = 1000, κ = 10⁴, the FULL default warm-up (search + 75 + 25…400 with diagonal metric
+    windows + 50 = 900 transitions, mcmc.jl:415-425) and draws; the chains are the LAST ones of a 65 536-chain shard
+    (global ids 65 512 … 65 535 through chain_offset, i.e. the same RNG keys): warm-up statistics, step sizes, adapted
+    metric and draws must equal the oracle's."""
+    ℓ = _c5_model(pkg)
+    K, N, seed, off = 24, 10, 2026, 65536 - 24
+    r = pkg.mcmc_keep_warmup(seed, ℓ, N, chains=K, chain_offset=off)
+    T, _ = r["engine"].layout()
+    params = ℓ.params()
+    for k in (0, 11, K - 1):
+        o = po.mcmc_with_warmup(po.FAMILY_DIAG_NORMAL, 1000, N, seed, off + k, params=params, T=T, welford=True, keep_warmup=True)
+        w = np.concatenate([s["results"]["tree_statistics"][k] for s in r["warmup"] if s["results"]])
+        assert w.size == 900
+        for f in INT_FIELDS:
+            assert np.array_equal(w[f], o["warmup_stats"][f]), f
+        weps = np.concatenate([s["results"]["ϵs"][k] for s in r["warmup"] if s["results"]])
+        assert np.array_equal(weps, o["warmup_eps"])
+        res = r["inference"][k]
+        assert res["ϵ"] == o["eps"] and np.array_equal(res["κ"].minv, o["minv"])
+        np.testing.assert_allclose(res["posterior_matrix"].T, o["posterior_matrix"], rtol=RTOL, atol=0)
+        assert np.array_equal(res["posterior_matrix"].T, o["posterior_matrix"])
+        for f in INT_FIELDS:
+            assert np.array_equal(res["tree_statistics"][f], o["tree_statistics"][f])
+    r["engine"].close()
+
+
+def test_c5_last_chain_of_a_65536_chain_handle(pkg, po):
+    """The same model on a full-size handle (65 536 chains, 2.1 GB of state): the last chain (index arithmetic at scale)
+    after the step-size search, a dual-averaging stage and a diagonal metric window equals the oracle."""
+    ℓ = _c5_model(pkg)
+    K, N, seed = 65536, 4, 77
+    stages = (pkg.InitialStepsizeSearch(), pkg.TuningNUTS(20, pkg.DualAveraging()),
+              pkg.TuningNUTS(20, pkg.DualAveraging(), pkg.Diagonal), pkg.TuningNUTS(20, pkg.DualAveraging()))
+    r = pkg.mcmc_keep_warmup(seed, ℓ, N, chains=K, warmup_stages=stages, keep_warmup=False)
+    T, _ = r["engine"].layout()
+    ostages = po.default_warmup_stages(init_steps=20, middle_steps=20, doubling_stages=1, terminating_steps=20)
+    for k in (0, 40000, K - 1):
+        o = po.mcmc_with_warmup(po.FAMILY_DIAG_NORMAL, 1000, N, seed, k, stages=ostages, params=ℓ.params(), T=T, welford=True)
+        res = r["inference"][k]
+        assert res["ϵ"] == o["eps"] and np.array_equal(res["κ"].minv, o["minv"])
+        assert np.array_equal(res["posterior_matrix"].T, o["posterior_matrix"])
+        for f in INT_FIELDS:
+            assert np.array_equal(res["tree_statistics"][f], o["tree_statistics"][f])
+    r["engine"].close()
+
+
+def test_c3_shape_funnel_262144_chains(pkg, po):
+    """C3 at its exact shape: Neal's funnel D = 10 on a 262 144-chain handle (ragged tree depths, one warp per chain).
+    Sampled chain ids against the oracle, and the device-side depth histogram / termination counts
+    (dhmc_tree_summary_dev) against the host-side counts of the very same statistics."""
+    import ctypes as C
+    ℓ = pkg.Funnel(10)
+    K, N, seed = 262144, 6, 9
+    eng = pkg.Engine(ℓ, chains=K, seed=seed)
+    T, _ = eng.layout()
+    eng.random_position(); eng.find_initial_stepsize()
+    eng.warmup_stage(pkg.TuningNUTS(30, pkg.DualAveraging()))
+    eng.warmup_stage(pkg.TuningNUTS(25, pkg.DualAveraging(), pkg.Diagonal))
+    eng.warmup_stage(pkg.TuningNUTS(20, pkg.DualAveraging()))
+    out = eng.mcmc(N)
+    st = eng.get_state(("minv", "eps"))
+    ostages = [(po.STAGE_SEARCH, 0, po.METRIC_NOTHING, 0), (po.STAGE_TUNING, 30, po.METRIC_NOTHING, 1),
+               (po.STAGE_TUNING, 25, po.METRIC_DIAGONAL, 1), (po.STAGE_TUNING, 20, po.METRIC_NOTHING, 1)]
+    for k in (0, 1, 31, 4097, 131071, 200003, K - 1):
+        o = po.mcmc_with_warmup(po.FAMILY_FUNNEL, 10, N, seed, k, stages=ostages, T=T, welford=True)
+        assert st["eps"][k] == o["eps"] and np.array_equal(st["minv"][k], o["minv"])
+        assert np.array_equal(out["posterior_matrix"][k], o["posterior_matrix"])
+        for f in INT_FIELDS:
+            assert np.array_equal(out["tree_statistics"][k][f], o["tree_statistics"][f])
+    # device-side summary of a device-resident statistics buffer == host-side counts of the same records
+    import torch
+    dstats = torch.empty((K, N, 56), dtype=torch.uint8, device="cuda")
+    eng.mcmc_dev(N, 0, dstats.data_ptr(), 0)
+    host = dstats.cpu().numpy().view(pkg._lib.tree_stats_dtype).reshape(K, N)
+    summ = eng.tree_summary_dev(dstats.data_ptr(), N, ebfmi=False)
+    depth_counts = np.bincount(host["depth"].ravel(), minlength=len(summ["depth_counts"]))
+    assert depth_counts.tolist()[:len(summ["depth_counts"])] == summ["depth_counts"] and depth_counts.sum() == K * N
+    div = int(np.sum(host["left"] == host["right"]))
+    mx = int(np.sum((host["left"] == 1) & (host["right"] == 0)))
+    assert summ["termination_counts"] == dict(max_depth=mx, divergence=div, turning=K * N - div - mx)
+    assert summ["steps"] == int(host["steps"].sum())
+    assert len(summ["depth_counts"]) >= 5                      # ragged: several depths occur
+    eng.close()
+
+
 def test_initial_stepsize_search(pkg, po):
     D, K = 30, 64
     rng = np.random.default_rng(12)
