@@ -25,7 +25,7 @@ EXPORTS = [
     "dhmc_set_transition_count", "dhmc_leapfrog", "dhmc_phase_logdensity", "dhmc_sample_tree",
     "dhmc_find_initial_stepsize", "dhmc_warmup_stage", "dhmc_mcmc", "dhmc_mcmc_from", "dhmc_mcmc_dev",
     "dhmc_tree_summary_dev", "dhmc_last_total_steps", "dhmc_last_kernel_ms", "dhmc_kernel_launches",
-    "dhmc_mcmc_thinned", "dhmc_host_alloc", "dhmc_host_free",
+    "dhmc_ess_rhat_dev", "dhmc_acceptance_quantiles_dev", "dhmc_mcmc_thinned", "dhmc_host_alloc", "dhmc_host_free",
     "dhmc_comm_unique_id", "dhmc_comm_init", "dhmc_comm_destroy", "dhmc_allgather_dev",
     "dhmc_allgather_positions_dev", "dhmc_last_comm_ms",
 ]

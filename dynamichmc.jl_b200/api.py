@@ -520,6 +520,21 @@ class Engine:
                     termination_counts=dict(max_depth=int(term[0]), divergence=int(term[1]), turning=int(term[2])),
                     depth_counts=depth[: nz[-1] + 1].tolist() if nz.size else [], EBFMI=eb)
 
+    def ess_rhat_dev(self, draws_ptr, N, max_lag=0):
+        """split-R̂ and ESS per parameter from a DEVICE draws buffer [K, N, D] (dhmc_ess_rhat_dev)."""
+        rhat, ess = np.empty(self.D), np.empty(self.D)
+        self._ck(self._lib.dhmc_ess_rhat_dev(self._h, C.c_void_p(draws_ptr), C.c_int32(N), C.c_int32(max_lag),
+                                             L.ptr(rhat), L.ptr(ess)))
+        return dict(rhat=rhat, ess=ess)
+
+    def acceptance_quantiles_dev(self, stats_ptr, N, probs=(0.05, 0.25, 0.5, 0.75, 0.95)):
+        """a_quantiles of summarize_tree_statistics (diagnostics.jl:35) from a DEVICE statistics buffer."""
+        pr = np.ascontiguousarray(probs, float)
+        out = np.empty(pr.size)
+        self._ck(self._lib.dhmc_acceptance_quantiles_dev(self._h, C.c_void_p(stats_ptr), C.c_int32(N), L.ptr(pr),
+                                                         C.c_int32(pr.size), L.ptr(out)))
+        return out
+
     # -- measurement hooks
     def last_total_steps(self):
         v = C.c_int64()

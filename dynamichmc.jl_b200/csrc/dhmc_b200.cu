@@ -196,6 +196,53 @@ __global__ void k_tree_summary(const dhmc_tree_stats* stats, int N, int B, unsig
   }
 }
 
+// ---- cross-chain convergence diagnostics on device-resident draws [B][N][D] (§8f-2; the reference's tests use
+// MCMCDiagnosticTools.ess_rhat on the same quantities, sample-correctness_utilities.jl:40-43).  Every chain is split in
+// two halves of n = N/2 draws (m = 2B sequences).  One warp = 32 consecutive parameters of one sequence: mean, then the
+// biased autocovariances at lags 0…L; the per-parameter sums over sequences are accumulated with atomics:
+//   acc[d][0] = Σ (μ − pilot_d), [1] = Σ (μ − pilot_d)², [2 + t] = Σ acov(t)        (pilot_d = mean of sequence 0: a shift
+//   that keeps the variance of the means free of cancellation).  The host finishes R̂ and the Geyer sum (tiny).
+__global__ void k_pilot_mean(const double* draws, int n, int N, int D, double* pilot) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += draws[(size_t)i * D + d];
+  pilot[d] = s / n;
+}
+__global__ void k_ess_rhat(const double* draws, int N, int n, int D, int B, int L, const double* pilot, double* acc) {
+  const int lane = threadIdx.x & 31;
+  const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+  const int tiles = (D + 31) / 32;
+  const long work = (long)2 * B * tiles;                    // (sequence, parameter tile)
+  for (long w = warp; w < work; w += nwarps) {
+    const long seq = w / tiles;
+    const int d = (int)(w % tiles) * 32 + lane;
+    if (d >= D) continue;
+    const double* x = draws + ((size_t)(seq >> 1) * N + (size_t)(seq & 1) * n) * D + d;
+    double mu = 0.0;
+    for (int i = 0; i < n; ++i) mu += x[(size_t)i * D];
+    mu /= n;
+    double* a = acc + (size_t)d * (L + 3);
+    const double dm = mu - pilot[d];
+    atomicAdd(a, dm);
+    atomicAdd(a + 1, dm * dm);
+    for (int t = 0; t <= L; ++t) {
+      double c = 0.0;
+      for (int i = 0; i + t < n; ++i) c += (x[(size_t)i * D] - mu) * (x[(size_t)(i + t) * D] - mu);
+      atomicAdd(a + 2 + t, c / n);
+    }
+  }
+}
+// histogram of the acceptance rates (4096 bins on [0, 1]) of a device statistics buffer
+__global__ void k_acceptance_hist(const dhmc_tree_stats* stats, size_t n, unsigned long long* hist, int bins) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double a = stats[i].acceptance_rate;
+    int b = a >= 1.0 ? bins - 1 : a <= 0.0 ? 0 : (int)(a * bins);
+    if (!(a == a)) b = bins;                                  // NaN bucket
+    atomicAdd(hist + b, 1ull);
+  }
+}
+
 // broadcast a D-vector (or scalar when D == 1) to all chains
 __global__ void k_broadcast(double* dst, const double* src, size_t D, size_t B) {
   const size_t n = D * B;
@@ -1167,6 +1214,86 @@ int dhmc_tree_summary_dev(dhmc_handle* h, const dhmc_tree_stats* stats_dev, int3
   if (termination_counts) for (int i = 0; i < 3; ++i) termination_counts[i] = (int64_t)cnt[33 + i];
   if (steps_sum) *steps_sum = (int64_t)cnt[36];
   if (acceptance_sum) *acceptance_sum = acc;
+  return DHMC_OK;
+}
+
+int dhmc_ess_rhat_dev(dhmc_handle* h, const double* draws_dev, int32_t N, int32_t max_lag, double* rhat, double* ess) {
+  if (!h || !draws_dev || N < 4 || (!rhat && !ess)) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  const int D = (int)h->cfg.dim, B = (int)h->cfg.n_chains, n = N / 2;
+  int L = max_lag > 0 ? max_lag : 64;
+  if (L > n - 2) L = n - 2;
+  if (L < 1) L = 1;
+  double *d_pilot = nullptr, *d_acc = nullptr;
+  CK(cudaMalloc(&d_pilot, sizeof(double) * D));
+  CK(cudaMalloc(&d_acc, sizeof(double) * (size_t)D * (L + 3)));
+  CK(cudaMemsetAsync(d_acc, 0, sizeof(double) * (size_t)D * (L + 3), h->stream));
+  k_pilot_mean<<<(D + 127) / 128, 128, 0, h->stream>>>(draws_dev, n, N, D, d_pilot);
+  k_ess_rhat<<<h->sm_count * 8, 256, 0, h->stream>>>(draws_dev, N, n, D, B, L, d_pilot, d_acc);
+  h->launches += 2;
+  std::vector<double> acc((size_t)D * (L + 3));
+  cudaError_t e = cudaMemcpyAsync(acc.data(), d_acc, sizeof(double) * acc.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_pilot); cudaFree(d_acc);
+  if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return DHMC_ECUDA; }
+  const double m = 2.0 * B, dn = (double)n;
+  for (int d = 0; d < D; ++d) {
+    const double* a = &acc[(size_t)d * (L + 3)];
+    const double mean_var = a[2] / m * dn / (dn - 1.0);                    // W: mean within-sequence variance (n − 1)
+    const double var_means = m > 1 ? (a[1] - a[0] * a[0] / m) / (m - 1.0) : 0.0;
+    const double var_plus = mean_var * (dn - 1.0) / dn + var_means;        // (n−1)/n·W + B/n
+    if (rhat) rhat[d] = std::sqrt(var_plus / mean_var);
+    if (ess) {
+      // Geyer's initial monotone sequence on ρ̂_t = 1 − (W − mean acov_t) / var⁺, pairs (ρ̂_2k + ρ̂_2k+1)
+      double tau = 0.0, prev = 1e300;
+      for (int t = 0; t + 1 <= L; t += 2) {
+        const double r0 = 1.0 - (mean_var - a[2 + t] / m) / var_plus, r1 = 1.0 - (mean_var - a[3 + t] / m) / var_plus;
+        double pair = r0 + r1;
+        if (!(pair > 0.0)) break;
+        if (pair > prev) pair = prev;
+        prev = pair;
+        tau += 2.0 * pair;
+      }
+      tau -= 1.0;
+      if (tau < 1.0 / std::log10(m * dn)) tau = 1.0 / std::log10(m * dn);   // cap of the super-efficient case (Stan: ESS ≤ S·log10 S)
+      ess[d] = m * dn / tau;
+    }
+  }
+  return DHMC_OK;
+}
+int dhmc_acceptance_quantiles_dev(dhmc_handle* h, const dhmc_tree_stats* stats_dev, int32_t N, const double* probs,
+                                  int32_t nprobs, double* out) {
+  if (!h || !stats_dev || N < 1 || !probs || nprobs < 1 || !out) return DHMC_EARG;
+  CK(cudaSetDevice(h->cfg.device));
+  constexpr int BINS = 4096;
+  unsigned long long* d_hist = nullptr;
+  CK(cudaMalloc(&d_hist, sizeof(unsigned long long) * (BINS + 1)));
+  CK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * (BINS + 1), h->stream));
+  const size_t n = (size_t)N * (size_t)h->cfg.n_chains;
+  k_acceptance_hist<<<h->sm_count * 8, 256, 0, h->stream>>>(stats_dev, n, d_hist, BINS);
+  h->launches += 1;
+  std::vector<unsigned long long> hist(BINS + 1);
+  cudaError_t e = cudaMemcpyAsync(hist.data(), d_hist, sizeof(unsigned long long) * hist.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(d_hist);
+  if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return DHMC_ECUDA; }
+  const unsigned long long tot = n - hist[BINS];
+  for (int k = 0; k < nprobs; ++k) {
+    if (!(probs[k] >= 0.0 && probs[k] <= 1.0)) { h->err = "0 ≤ p ≤ 1"; return DHMC_EARG; }
+    if (tot == 0) { out[k] = dm_nan(); continue; }
+    const double target = probs[k] * (double)(tot - 1);             // Julia's quantile (type 7): position in the sorted sample
+    unsigned long long cum = 0;
+    double q = 1.0;
+    for (int b = 0; b < BINS; ++b) {
+      if ((double)(cum + hist[b]) > target) {                       // the order statistic lies in bin b: interpolate inside it
+        const double frac = hist[b] ? (target - (double)cum + 0.5) / (double)hist[b] : 0.5;
+        q = ((double)b + std::min(1.0, std::max(0.0, frac))) / BINS;
+        break;
+      }
+      cum += hist[b];
+    }
+    out[k] = q;
+  }
   return DHMC_OK;
 }
 

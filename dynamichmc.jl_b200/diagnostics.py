@@ -122,3 +122,40 @@ def leapfrog_trajectory(ℓ, q, ϵ, positions, κ=None, p=None, seed=0, device=0
     finally:
         eng.close()
     return [out[i] for i in sorted(out)]
+
+
+def ess_rhat(draws, max_lag=0):
+    """Numpy mirror of dhmc_ess_rhat_dev (include/dhmc.h): split-R̂ and ESS per parameter of `draws` [chains, N, D].
+    Every chain is split in two halves (m = 2·chains sequences of n = N // 2 draws); W = mean within-sequence variance,
+    var⁺ = (n−1)/n·W + var(sequence means); ρ̂_t = 1 − (W − mean_c acov_c(t)) / var⁺ with the biased autocovariance;
+    τ = −1 + 2 Σ (ρ̂_2k + ρ̂_2k+1) over Geyer's initial monotone sequence; ESS = m·n / τ.  The quantities the reference's
+    correctness tests take from MCMCDiagnosticTools.ess_rhat (test/sample-correctness_utilities.jl:40-43)."""
+    x = np.asarray(draws, float)
+    K, N, D = x.shape
+    n = N // 2
+    L = max_lag if max_lag > 0 else 64
+    L = max(1, min(L, n - 2))
+    seq = np.concatenate([x[:, :n], x[:, n:2 * n]], axis=1).reshape(2 * K, n, D) if False else \
+        np.stack([x[:, :n], x[:, n:2 * n]], axis=1).reshape(2 * K, n, D)
+    m = 2 * K
+    mu = seq.mean(axis=1)                                      # [m, D]
+    xc = seq - mu[:, None, :]
+    acov = np.stack([(xc[:, : n - t] * xc[:, t:]).sum(axis=1) / n for t in range(L + 1)])   # [L+1, m, D]
+    mean_var = acov[0].mean(axis=0) * n / (n - 1.0)
+    var_plus = mean_var * (n - 1.0) / n + (mu.var(axis=0, ddof=1) if m > 1 else 0.0)
+    rhat = np.sqrt(var_plus / mean_var)
+    rho = 1.0 - (mean_var[None] - acov.mean(axis=1)) / var_plus[None]                      # [L+1, D]
+    ess = np.empty(D)
+    for d in range(D):
+        tau, prev = 0.0, np.inf
+        for t in range(0, L, 2):
+            pair = rho[t, d] + rho[t + 1, d]
+            if not pair > 0:
+                break
+            pair = min(pair, prev)
+            prev = pair
+            tau += 2 * pair
+        tau -= 1.0
+        tau = max(tau, 1.0 / np.log10(m * n))
+        ess[d] = m * n / tau
+    return dict(rhat=rhat, ess=ess)

@@ -180,6 +180,17 @@ int dhmc_tree_summary_dev(dhmc_handle* h, const dhmc_tree_stats* stats_dev, int3
                           int64_t* depth_counts, int64_t* termination_counts,
                           double* acceptance_sum, int64_t* steps_sum, double* ebfmi);
 
+/* Cross-chain convergence diagnostics reduced on the GPU over device-resident draws [D, N, B] (the posterior buffer of
+ * dhmc_mcmc_dev): per parameter the split-R̂ and the effective sample size of the pooled sequences (every chain split in two
+ * halves; autocorrelations up to max_lag ≤ N/2 − 2, 0 = 64; Geyer's initial monotone sequence) — what the reference's
+ * correctness tests compute with MCMCDiagnosticTools.ess_rhat (test/sample-correctness_utilities.jl:40-43).
+ * rhat, ess: host [D], either may be NULL. */
+int dhmc_ess_rhat_dev(dhmc_handle* h, const double* draws_dev, int32_t N, int32_t max_lag, double* rhat, double* ess);
+/* Quantiles of the acceptance rates (Diagnostics.summarize_tree_statistics: a_quantiles at 0.05 … 0.95,
+ * diagnostics.jl:35,100-106) of a device statistics buffer [N, B], from a 4096-bin histogram (resolution 2.4e-4). */
+int dhmc_acceptance_quantiles_dev(dhmc_handle* h, const dhmc_tree_stats* stats_dev, int32_t N, const double* probs,
+                                  int32_t nprobs, double* out);
+
 /* ---- multi-GPU: chains sharded over ranks, ONE all-gather of draws at the end ------------
  * One process (rank) per GPU; a handle owns the chains [chain_offset, chain_offset + n_chains) and the RNG keys use
  * the global chain id, so results do not depend on the number of ranks.  Nothing is exchanged while sampling.

@@ -166,3 +166,21 @@ def test_reference_kat_leapfrog_trajectory(pkg_with_oracle_engine):
     for t, (qq, pp) in zip(traj, zs):
         np.testing.assert_allclose(t["z"]["q"], qq, rtol=1e-8, atol=1e-12)
         np.testing.assert_allclose(t["z"]["p"], pp, rtol=1e-8, atol=1e-12)
+
+
+def test_ess_rhat_mirror_on_ar1_chains(pkg):
+    """The numpy mirror of the device diagnostic on AR(1) chains with a known answer: ESS/N = (1 − φ)/(1 + φ); R̂ ≈ 1 for
+    chains from the same distribution and clearly above 1 when half of the chains are shifted."""
+    rng = np.random.default_rng(5)
+    K, N, D = 64, 400, 3
+    phis = np.array([0.0, 0.5, 0.8])
+    x = np.empty((K, N, D))
+    x[:, 0] = rng.normal(size=(K, D))
+    for i in range(1, N):
+        x[:, i] = phis * x[:, i - 1] + np.sqrt(1 - phis ** 2) * rng.normal(size=(K, D))
+    r = pkg.diagnostics.ess_rhat(x, max_lag=60)
+    assert np.all(np.abs(r["rhat"] - 1) < 0.03)
+    expect = K * (N // 2 * 2) * (1 - phis) / (1 + phis)
+    assert np.all(np.abs(r["ess"] / expect - 1) < 0.15), (r["ess"], expect)
+    x[: K // 2] += 1.0
+    assert np.all(pkg.diagnostics.ess_rhat(x, max_lag=60)["rhat"] > 1.1)

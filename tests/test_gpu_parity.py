@@ -621,6 +621,30 @@ def test_deep_trees_match_oracle(pkg, po, D, max_depth, eps_lo, eps_hi):
     eng.close()
 
 
+def test_device_ess_rhat_and_acceptance_quantiles(pkg):
+    """§8f-2: split-R̂ / ESS across chains and the acceptance-rate quantiles reduced on the GPU from device-resident draws
+    and statistics, against the numpy mirror (diagnostics.ess_rhat) resp. numpy quantiles of the same records."""
+    import torch
+    D, K, N = 37, 512, 120
+    rng = np.random.default_rng(3)
+    ℓ = pkg.DiagNormal(rng.normal(size=D), rng.uniform(0.3, 4, D))
+    eng = pkg.Engine(ℓ, chains=K, seed=17)
+    eng.random_position(); eng.find_initial_stepsize()
+    eng.warmup_stage(pkg.TuningNUTS(60, pkg.DualAveraging()))
+    draws = torch.empty((K, N, D), dtype=torch.float64, device="cuda")
+    stats = torch.empty((K, N, 56), dtype=torch.uint8, device="cuda")
+    eng.mcmc_dev(N, draws.data_ptr(), stats.data_ptr(), 0)
+    dev = eng.ess_rhat_dev(draws.data_ptr(), N, max_lag=40)
+    ref = pkg.diagnostics.ess_rhat(draws.cpu().numpy(), max_lag=40)
+    np.testing.assert_allclose(dev["rhat"], ref["rhat"], rtol=1e-9)
+    np.testing.assert_allclose(dev["ess"], ref["ess"], rtol=1e-7)
+    assert np.all(dev["rhat"] < 1.02) and np.all(dev["ess"] > 0.2 * K * N)        # the bar of sample-correctness_utilities.jl:107-110
+    a = stats.cpu().numpy().view(pkg._lib.tree_stats_dtype).reshape(K, N)["acceptance_rate"].ravel()
+    q = eng.acceptance_quantiles_dev(stats.data_ptr(), N)
+    np.testing.assert_allclose(q, np.quantile(a, pkg.diagnostics.ACCEPTANCE_QUANTILES), atol=5e-4)
+    eng.close()
+
+
 # --------------------------------------------------------------- trajectory diagnostics (diagnostics.jl:139-216)
 def test_trajectory_diagnostics_match_oracle(pkg, po):
     D = 37
