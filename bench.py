@@ -424,15 +424,18 @@ def main():
         if wl["flops_per_lf"]:
             peak_tf = DMMA_FMA_PER_CLK_SM * 2 * 148 * sm_max_mhz * 1e6 / 1e12
             ach = steps_per_launch * wl["flops_per_lf"] / (ms_per_launch * 1e-3) / 1e12
-            traffic = None
-            try:
+            traffic, traffic_src = None, None
+            try:   # the ncu capture ran a smaller batch; the traffic is the per-chain metric stream, i.e. proportional to the steps
                 tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["c4"]
-                if (tr["chains"], tr["draws_per_step"]) == (K, n):
-                    traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                per_ms = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["duration_ms"]
+                traffic = per_ms * ms_per_launch
+                traffic_src = ("scaled by launch duration from the committed ncu --set full capture at %d chains (profiles/r02_traffic.json: "
+                               "%.0f GB in %.0f ms = %.2f TB/s, the per-chain dense metrics), not measured in this run"
+                               % (tr["chains"], (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / 1e9, tr["duration_ms"], per_ms / 1e9))
             except Exception:
                 pass
             roof = {"bound": "tensor", "kernel": kernel, "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": ach / peak_tf, "traffic": traffic,
+                    "frac": ach / peak_tf, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_kind": "FP64 DMMA rate measured by benchmarks/c4_probes.cu (64 FMA/clk/SM = the DFMA rate) x 148 SMs x "
                                  "%.0f MHz; MEASURED_PEAKS.json holds no FP64 figure" % sm_max_mhz,
                     "algorithmic_flops_per_launch": steps_per_launch * wl["flops_per_lf"],
@@ -441,10 +444,10 @@ def main():
             ach = steps_per_launch * wl["bytes_per_lf"] / (ms_per_launch * 1e-3) / 1e9
             traffic, traffic_src = None, None
             try:   # DRAM bytes per launch from the committed ncu --set full capture of this same command
-                tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["k_nuts"]
+                tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["k_nuts"]
                 if args.config == "C2" and (tr["dim"], tr["chains"], tr["draws_per_step"]) == (D, K, n):
                     traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
-                    traffic_src = "committed ncu --set full capture (profiles/r01_traffic.json), not measured in this run"
+                    traffic_src = "committed ncu --set full capture of this same command (profiles/r02_traffic.json), not measured in this run"
             except Exception:
                 pass
             roof = {"bound": "hbm", "kernel": kernel, "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
