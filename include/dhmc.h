@@ -159,9 +159,10 @@ int dhmc_mcmc_from(dhmc_handle* h, const double* q, int32_t N, double* posterior
                    dhmc_tree_stats* stats, double* logdens);
 /* mcmc with a thinned output (§8f-3): N transitions, every thin-th one is kept, outputs are [D, N/thin, B] resp.
  * [N/thin, B].  q == NULL continues from the resident positions, else as dhmc_mcmc_from.
- * All host-output calls write PAGE-LOCKED buffers (cudaHostAlloc / cudaHostRegister / dhmc_host_alloc) directly from
- * the sampling kernel — no staging copy in HBM, so N is not bounded by device memory; pageable buffers are staged in HBM
- * and copied chunk by chunk, or page-locked on the fly when the draws would not fit. */
+ * All host-output calls: while the kept draws fit in HBM they are staged there and copied chunk by chunk, overlapped with the
+ * sampling of the next chunk (page-locked buffers — cudaHostAlloc / cudaHostRegister / dhmc_host_alloc — make the copies
+ * asynchronous); when they do not fit, the sampling kernel writes the (page-locked, if need be on the fly) host buffer
+ * directly, so N is not bounded by device memory. */
 int dhmc_mcmc_thinned(dhmc_handle* h, const double* q, int32_t N, int32_t thin, double* posterior,
                       dhmc_tree_stats* stats, double* logdens);
 /* Page-locked, device-mapped host memory on the NUMA node of the handle's GPU (for the output buffers above). */

@@ -621,6 +621,36 @@ def test_deep_trees_match_oracle(pkg, po, D, max_depth, eps_lo, eps_hi):
     eng.close()
 
 
+@pytest.mark.parametrize("direct", ["0", "1"])
+def test_thinned_draws_into_page_locked_buffers(pkg, monkeypatch, direct):
+    """§8f-3: dhmc_mcmc_thinned keeps every thin-th transition; with page-locked output buffers (dhmc_host_alloc) the
+    draws are either staged and copied (default while they fit in HBM) or written by the sampling kernel straight into
+    the host buffer (DHMC_DIRECT=1 — the route taken when they do not fit).  Both must equal the plain mcmc call."""
+    monkeypatch.setenv("DHMC_DIRECT", direct)
+    D, K, N, thin = 130, 200, 12, 3
+    rng = np.random.default_rng(8)
+    ℓ = pkg.DiagNormal(rng.normal(size=D), rng.uniform(0.5, 2, D))
+    outs = []
+    for mode in ("plain", "thinned"):
+        eng = pkg.Engine(ℓ, chains=K, seed=99)
+        eng.random_position(); eng.find_initial_stepsize()
+        eng.warmup_stage(pkg.TuningNUTS(30, pkg.DualAveraging()))
+        if mode == "plain":
+            outs.append(eng.mcmc(N))
+        else:
+            bufs = dict(posterior_matrix=eng.host_alloc((K, N // thin, D)),
+                        tree_statistics=eng.host_alloc((K, N // thin), dtype=pkg._lib.tree_stats_dtype),
+                        logdensities=eng.host_alloc((K, N // thin)))
+            r = eng.mcmc_thinned(N, thin, out=bufs)
+            outs.append({k: np.array(v) for k, v in r.items()})
+        eng.close()
+    a, b = outs
+    assert np.array_equal(a["posterior_matrix"][:, thin - 1::thin], b["posterior_matrix"])
+    assert np.array_equal(a["logdensities"][:, thin - 1::thin], b["logdensities"])
+    for f in INT_FIELDS:
+        assert np.array_equal(a["tree_statistics"][f][:, thin - 1::thin], b["tree_statistics"][f])
+
+
 def test_device_ess_rhat_and_acceptance_quantiles(pkg):
     """§8f-2: split-R̂ / ESS across chains and the acceptance-rate quantiles reduced on the GPU from device-resident draws
     and statistics, against the numpy mirror (diagnostics.ess_rhat) resp. numpy quantiles of the same records."""
