@@ -488,9 +488,9 @@ def main():
         if e2e:
             line["e2e"] = {"value": sm[6].item() / mx[5].item(), "unit": UNIT,
                            "h2d_bytes_per_step": e2e[2], "d2h_bytes_per_step": e2e[3],
-                           "how": "dhmc_mcmc_from: positions uploaded from page-locked host memory in chain chunks, draws / statistics "
-                                  "/ log densities written by the sampling kernel straight into page-locked host buffers "
-                                  "(NUMA node %s)" % numa}
+                           "how": "dhmc_mcmc_from with page-locked NUMA-local host buffers (node %s): positions uploaded, draws / statistics / "
+                                  "log densities downloaded, both pipelined by chain chunks against the sampling of the next chunk (draws "
+                                  "that do not fit in HBM would be written by the kernel directly)" % numa}
         if gather:
             bw = K * D * 8 * (world - 1) / (mx[7].item() * 1e-3) / 1e9
             line["allgather"] = {"ms": mx[7].item(), "first_call_ms": gather[0], "bytes_per_rank": K * D * 8,

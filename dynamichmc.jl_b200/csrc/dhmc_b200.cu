@@ -1011,7 +1011,7 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   // host writes only an upload is left to overlap
   const bool staged_big = posterior && !direct[0] && out_bytes >= ((size_t)32 << 20);
   int nchunks = (!outputs_on_device && B >= 4096 && (staged_big || q_host)) ? 16 : 1;
-  while (nchunks > 1 && B / (size_t)nchunks < (size_t)8 * (size_t)h->grid) nchunks /= 2;
+  while (nchunks > 1 && B / (size_t)nchunks < (size_t)8 * (size_t)h->grid * (size_t)h->G) nchunks /= 2;   // >= 8 waves of chain slots per chunk
   if (const char* ev = std::getenv("DHMC_E2E_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16 && !outputs_on_device) nchunks = v; }
   CKR(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));   // status words describe the current call
   for (int ci = 0; ci < nchunks; ++ci) {
