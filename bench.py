@@ -440,6 +440,16 @@ def main():
                                  "%.0f MHz; MEASURED_PEAKS.json holds no FP64 figure" % sm_max_mhz,
                     "algorithmic_flops_per_launch": steps_per_launch * wl["flops_per_lf"],
                     "flops_per_leapfrog": wl["flops_per_lf"]}
+            # the per-chain dense metric is a GEMV stream from HBM: 2 mat-vecs per leapfrog, each over the chain's padded
+            # [D'][XS] matrix (D' = 32·⌈D/32⌉, XS = the bank-conflict-free pitch): report it against the HBM peak too
+            xs_pad = ((D + 7) // 8) * 8
+            while xs_pad % 16 != 4:
+                xs_pad += 1
+            gemv_bytes = 2 * ((D + 31) // 32 * 32) * xs_pad * 8
+            gbs = steps_per_launch * gemv_bytes / (ms_per_launch * 1e-3) / 1e9
+            roof["metric_gemv_stream"] = {"bytes_per_leapfrog": gemv_bytes, "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak,
+                                          "what": "M^-1 p with the reference's PER-CHAIN metric: a GEMV per chain on DMMA.8x8x4 (the MMA's "
+                                                  "n-dimension carries one vector); DHMC_METRIC_SYMMETRIC_POOLED turns it into a GEMM"}
         else:
             ach = steps_per_launch * wl["bytes_per_lf"] / (ms_per_launch * 1e-3) / 1e9
             traffic, traffic_src = None, None

@@ -187,6 +187,7 @@ class InitialStepsizeSearch:
 
 Diagonal = "Diagonal"
 Symmetric = "Symmetric"
+SymmetricPooled = "SymmetricPooled"      # NOT in the reference: one dense metric per group of 8 chains (dhmc.h, DHMC_METRIC_SYMMETRIC_POOLED)
 
 
 @dataclass
@@ -202,7 +203,7 @@ class TuningNUTS:
         if self.λ is None:
             self.λ = 5.0 / self.N
         _argcheck(self.λ >= 0, "λ ≥ 0")
-        _argcheck(self.M in (None, Diagonal, Symmetric), "M <: Union{Nothing,Diagonal,Symmetric}")
+        _argcheck(self.M in (None, Diagonal, Symmetric, SymmetricPooled), "M <: Union{Nothing,Diagonal,Symmetric}")
 
 
 def default_warmup_stages(stepsize_search=InitialStepsizeSearch(), M=Diagonal,
@@ -408,7 +409,8 @@ class Engine:
         if isinstance(stage.stepsize_adaptation, DualAveraging):
             a = stage.stepsize_adaptation
             da = C.byref(L.DualAveragingC(a.δ, a.γ, a.κ, a.t0, 0))
-        metric = {Diagonal: L.METRIC_DIAGONAL, Symmetric: L.METRIC_SYMMETRIC}.get(stage.M, L.METRIC_NOTHING)
+        metric = {Diagonal: L.METRIC_DIAGONAL, Symmetric: L.METRIC_SYMMETRIC,
+                  SymmetricPooled: L.METRIC_SYMMETRIC_POOLED}.get(stage.M, L.METRIC_NOTHING)
         self._ck(self._lib.dhmc_warmup_stage(self._h, C.c_int32(N), C.c_int32(metric), da,
                                              C.c_double(stage.λ), L.ptr(post), L.ptr(stats),
                                              L.ptr(eps), L.ptr(ld)))

@@ -313,7 +313,8 @@ constexpr int kTmaChunks = 256 / DHMC_LOGIT_CHUNK;     // η chunk sums per row 
 // η area: kTmaChunks partial tiles [chain][kTmaES], then the residual tile; after the round the first G·64 doubles
 // hand the per-thread Σ ll partials back
 __host__ __device__ inline size_t tma_tabs_off(int G) { return tma_eta_off(G) + sizeof(double) * (kTmaChunks + 1) * (size_t)G * kTmaES; }   // math tables, DM_TABS_DOUBLES
-__host__ __device__ inline size_t tma_ring_off(int G) { return (tma_tabs_off(G) + sizeof(double) * DM_TABS_DOUBLES + 127) & ~(size_t)127; }
+__host__ __device__ inline size_t tma_y_off(int G) { return tma_tabs_off(G) + sizeof(double) * DM_TABS_DOUBLES; }             // pooled-metric GEMM: M⁻¹·[8 vectors] result [chain][kTmaBS]
+__host__ __device__ inline size_t tma_ring_off(int G) { return (tma_y_off(G) + sizeof(double) * (size_t)G * kTmaBS + 127) & ~(size_t)127; }
 __host__ __device__ inline size_t tma_smem_bytes(int G, int D) { return tma_ring_off(G) + sizeof(double) * kTmaStages * tma_stage_doubles(D); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -489,6 +490,98 @@ __device__ __noinline__ bool coop_matvec_tma(bool active, long chain, int tid, i
       sts64(beta_a + (uint32_t)(sizeof(double) * (c * kTmaBS + i)), y);     // y_c replaces x_c
     }
     __syncthreads();
+  }
+  ring_n = n0 + (uint32_t)nblk;
+  return true;
+}
+
+// ---- the same product when the eight chains of the CTA SHARE their metric (DHMC_METRIC_SYMMETRIC_POOLED, not reference
+// semantics): M⁻¹·[x₀ … x₇] is a true GEMM — the metric streams through the ring ONCE per product (not once per chain), and
+// the MMA's n-dimension carries the eight chains' vectors exactly as in the likelihood's P1.  Per 32-row block: P1 (chunk
+// sums of two row tiles per warp) → barrier → 256 lanes add the chunk sums in order → y [chain][row].
+template <int G, int W>
+__device__ __noinline__ bool coop_matmul_pooled_tma(bool active, long chain, int tid, int grp, int ctid, int D,
+                                                    const double* __restrict__ Mp, unsigned char* shared, uint32_t& ring_n) {
+  constexpr int NT = 32 * W * G;
+  constexpr int NW = W * G;
+  constexpr int MW = 8;
+  int* cb_flags = reinterpret_cast<int*>(shared);
+  int* cb_chain = reinterpret_cast<int*>(shared + 32);
+  uint64_t* full = reinterpret_cast<uint64_t*>(shared + 64);
+  uint64_t* empty = full + kTmaStages;
+  const uint32_t sh = smem_u32(shared);
+  const uint32_t beta_a = sh + (uint32_t)tma_beta_off();
+  const uint32_t part_a = sh + (uint32_t)tma_eta_off(G);      // chunk sums [chunk][chain][kTmaES] of the current block
+  const uint32_t y_a = sh + (uint32_t)tma_y_off(G);
+  const uint32_t ring_a = sh + (uint32_t)tma_ring_off(G);
+  double* ring = reinterpret_cast<double*>(shared + tma_ring_off(G));
+  const int lane = ctid & 31, wq = ctid >> 5;
+  const int fr = lane >> 2, fk = lane & 3;
+  if (tid == 0) { cb_flags[grp] = active ? 1 : 0; cb_chain[grp] = (int)chain; }
+  __syncthreads();
+  unsigned amask = 0;
+#pragma unroll
+  for (int gg = 0; gg < G; ++gg)
+    if (cb_flags[gg]) amask |= 1u << gg;
+  if (amask == 0) return false;
+  const int XS = tma_xs(D);
+  const int nblk = (D + kTmaRows - 1) / kTmaRows;
+  const int ng = (D + 15) >> 4, nch = (D + DHMC_DOT_CHUNK - 1) / DHMC_DOT_CHUNK;
+  const uint32_t stage_bytes = (uint32_t)(sizeof(double) * kTmaRows * XS);
+  const bool producer = (wq == NW - 1) && (lane == 0);
+  const uint32_t n0 = ring_n;
+  const uint64_t pol = l2_policy_evict_first();
+  const double* Mg = Mp + (size_t)cb_chain[__ffs((int)amask) - 1] * (size_t)nblk * kTmaRows * XS;   // the group's metric (any active member's copy)
+  auto issue = [&](int b) {
+    const uint32_t n = n0 + (uint32_t)b;
+    const int s = (int)(n & 1u);
+    mbar_wait(empty + s, ((n >> 1) & 1u) ^ 1u);
+    mbar_expect_tx(full + s, stage_bytes);
+    const uint32_t piece = stage_bytes / kTmaPieces;
+    char* dst = reinterpret_cast<char*>(ring + (size_t)s * kTmaRows * XS);
+    const char* src = reinterpret_cast<const char*>(Mg + (size_t)b * kTmaRows * XS);
+#pragma unroll
+    for (int pc = 0; pc < kTmaPieces; ++pc) bulk_g2s_hint(dst + (size_t)pc * piece, src + (size_t)pc * piece, piece, full + s, pol);
+  };
+  if (producer) {
+    fence_proxy_async();
+    issue(0);
+    if (nblk > 1) issue(1);
+  }
+  __syncwarp();
+  const int pc1 = wq & 3, mp = (wq >> 2) & 1;
+  const int g0 = 4 * pc1, g1 = (4 * pc1 + 4 < ng) ? 4 * pc1 + 4 : ng;
+  const uint32_t p1_a = (uint32_t)(sizeof(double) * ((16 * mp + fr) * XS + fk)) + 128 * g0;
+  const uint32_t p1_b = beta_a + (uint32_t)(sizeof(double) * (fr * kTmaBS + fk)) + 128 * g0;     // B[k][n] = x of chain n
+  for (int b = 0; b < nblk; ++b) {
+    const uint32_t n = n0 + (uint32_t)b;
+    const int s = (int)(n & 1u);
+    mbar_wait(full + s, (n >> 1) & 1u);
+    if (wq < MW && g0 < g1) {
+      const uint32_t ap = ring_a + (uint32_t)s * stage_bytes + p1_a;
+      double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+      mma_chunk_2tiles(ap, ap + (uint32_t)(sizeof(double) * 8 * XS), p1_b, g1 - g0, c0, c1, d0, d1);
+      const uint32_t ea = part_a + (uint32_t)(sizeof(double) * (pc1 * G * kTmaES + 16 * mp + fr));
+      sts64(ea + (uint32_t)(sizeof(double) * (2 * fk) * kTmaES), c0);
+      sts64(ea + (uint32_t)(sizeof(double) * (2 * fk + 1) * kTmaES), c1);
+      sts64(ea + (uint32_t)(sizeof(double) * ((2 * fk) * kTmaES + 8)), d0);
+      sts64(ea + (uint32_t)(sizeof(double) * ((2 * fk + 1) * kTmaES + 8)), d1);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+    if (producer && b + 2 < nblk) issue(b + 2);
+    __syncwarp();
+    __syncthreads();                          // the chunk sums of this block are in place
+    for (int idx = ctid; idx < G * kTmaRows; idx += NT) {
+      const int gg = idx / kTmaRows, r = idx % kTmaRows, i = b * kTmaRows + r;
+      if (i < D) {
+        const uint32_t pa = part_a + (uint32_t)(sizeof(double) * (gg * kTmaES + r));
+        double y = lds64(pa);
+        for (int cc = 1; cc < nch; ++cc) y = y + lds64(pa + (uint32_t)(sizeof(double) * cc * G * kTmaES));
+        sts64(y_a + (uint32_t)(sizeof(double) * (gg * kTmaBS + i)), y);
+      }
+    }
+    __syncthreads();                          // … and consumed: the next block may overwrite them
   }
   ring_n = n0 + (uint32_t)nblk;
   return true;
@@ -720,6 +813,7 @@ struct DeviceBackend {
   // dense metric: this chain's M⁻¹ (symmetric, [D][D]), Wᵀ (column-major lower W), co-moment
   // accumulator (transposed lower) and the shared-memory staging vector
   const double* Mrow; const double* Wt; double* covt; double* xs;
+  double* mean_out;      // pooled Symmetric stage: where this chain's window mean goes (else null)
   // logistic regression: X [N][D], Xᵀ [D][lLd], y [N], residual scratch (per CTA [N]; packed groups [N][G])
   const double* lX; const double* lXt; const double* ly; double* lr; int lN; int lLd;   // lLd: leading dimension of Xᵀ
   // memory
@@ -1059,17 +1153,23 @@ struct DeviceBackend {
   }
   // packed groups, Symmetric metric, tensor-core build: y = M⁻¹x of all chains of the CTA (coop_matvec_tma)
   static constexpr bool kCoopMatvec = DENSE && PACK > 1 && MMA;
+  int pooled;                               // the dense metric is shared by the CTA's 8 chains (DHMC_METRIC_SYMMETRIC_POOLED)
+  __device__ __forceinline__ bool coop_matvec_call(bool act) {
+    if (pooled) return coop_matmul_pooled_tma<G, W>(act, chain, tid, grp, ctid, D, Mp, cb_shared, ring_n);
+    return coop_matvec_tma<G, W>(act, chain, tid, grp, ctid, D, Mp, cb_shared, ring_n);
+  }
   __device__ __forceinline__ void coop_matvec(const double (&x)[EPL], double (&y)[EPL]) {
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
       const int i = tid + e * T;
       if (i < D) cb_beta[(size_t)grp * kTmaBS + i] = x[e];
     }
-    coop_matvec_tma<G, W>(true, chain, tid, grp, ctid, D, Mp, cb_shared, ring_n);
+    coop_matvec_call(true);
+    const double* yb = pooled ? reinterpret_cast<const double*>(cb_shared + tma_y_off(G)) : cb_beta;
 #pragma unroll
     for (int e = 0; e < EPL; ++e) {
       const int i = tid + e * T;
-      y[e] = i < D ? cb_beta[(size_t)grp * kTmaBS + i] : 0.0;
+      y[e] = i < D ? yb[(size_t)grp * kTmaBS + i] : 0.0;
     }
   }
   // a warp without further chains keeps attending the CTA's cooperative calls, in the order a leapfrog step makes
@@ -1079,9 +1179,9 @@ struct DeviceBackend {
       double dummy_ll = 0.0;
       double dummy[EPL];
       if constexpr (kCoopMatvec) {
-        while (coop_matvec_tma<G, W>(false, 0, tid, grp, ctid, D, Mp, cb_shared, ring_n)) {
+        while (coop_matvec_call(false)) {
           coop_round(false, dummy_ll, dummy);
-          coop_matvec_tma<G, W>(false, 0, tid, grp, ctid, D, Mp, cb_shared, ring_n);
+          coop_matvec_call(false);
         }
       } else {
         while (coop_round(false, dummy_ll, dummy)) {}
@@ -1430,7 +1530,14 @@ struct DeviceBackend {
     }
   }
   __device__ __forceinline__ void metric_finish(int kind, int n) {
-    if (kind != DHMC_METRIC_DIAGONAL) return;   // Symmetric: finished by k_cov_finish + k_dense_factor
+    if (kind != DHMC_METRIC_DIAGONAL) {         // Symmetric: finished by k_cov_finish / k_cov_pool + k_dense_factor
+      if (mean_out) {                           // pooled stage: the group merge needs every chain's window mean
+        const double* m = slot(n_slots - 1);
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) if (valid(e)) mean_out[tid + e * T] = m[e * T];
+      }
+      return;
+    }
     const double* sv = slot(n_slots - 2);
     const double dn1 = (double)(n - 1);
 #pragma unroll

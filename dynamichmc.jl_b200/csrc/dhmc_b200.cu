@@ -132,6 +132,39 @@ __global__ void k_cov_finish(const double* covt, double* minv_dense, int n, doub
       }
   }
 }
+// Pooled metric of every group of 8 chains (DHMC_METRIC_SYMMETRIC_POOLED): the chains' streaming window means and co-moments
+// (n draws each) merged in the oracle's fixed order (pooled_regularized_cov), shrunk as regularize_M⁻¹, written to all 8 chains.
+__global__ void k_cov_pool(const double* covt, const double* means, double* minv_dense, int n, double lambda, int D, int B) {
+  extern __shared__ double gm[];              // group mean [D]
+  const size_t dd = (size_t)D * D;
+  const double dn = (double)n;
+  constexpr int G = 8;
+  for (int g = blockIdx.x; g < B / G; g += gridDim.x) {
+    const size_t c0 = (size_t)g * G;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+      double m = means[c0 * D + i];
+      for (int c = 1; c < G; ++c) m = m + means[(c0 + c) * D + i];
+      gm[i] = m / (double)G;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x)
+      for (int j = 0; j <= i; ++j) {
+        double acc = 0.0;
+        for (int c = 0; c < G; ++c) {
+          const double di = means[(c0 + c) * D + i] - gm[i], dj = means[(c0 + c) * D + j] - gm[j];
+          acc = acc + (covt[(c0 + c) * dd + (size_t)j * D + i] + (dn * di) * dj);
+        }
+        const double sij = acc / ((double)G * dn - 1.0);
+        double v = (1 - lambda) * sij;
+        if (i == j) v = v + lambda * sij;
+        for (int c = 0; c < G; ++c) {
+          double* out = minv_dense + (c0 + c) * dd;
+          out[(size_t)i * D + j] = v; out[(size_t)j * D + i] = v;
+        }
+      }
+    __syncthreads();
+  }
+}
 __global__ void k_broadcast_mat(double* dst, const double* src, size_t dd, size_t B) {
   const size_t n = dd * B;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
@@ -288,6 +321,8 @@ struct dhmc_handle {
   bool has_position = false, has_eps = false;
   bool dense = false;               // κ is a Symmetric (dense) metric
   double *minv_dense = nullptr, *wt = nullptr, *covt = nullptr, *dense_tmp = nullptr;
+  double* mean_pool = nullptr;      // pooled Symmetric stages: window mean of every chain [B][D]
+  bool pooled = false;              // the dense metric is shared by every group of 8 chains
   double* minv_pad = nullptr;       // packed groups on the tensor cores: zero-padded row blocks of every chain's M⁻¹
   double *lX = nullptr, *lXt = nullptr, *ly = nullptr, *lr = nullptr;   // logistic regression
   double* lXp = nullptr;            // … zero-padded row blocks of X for the tensor-core likelihood
@@ -402,7 +437,7 @@ static KArgs base_args(dhmc_handle* h) {
   a.levels = h->levels; a.ntab = h->ntab;
   a.counter = h->counter; a.total_steps = h->total_steps;
   a.chain_begin = 0; a.chain_end = (int)h->cfg.n_chains;
-  a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr; a.minv_pad = h->minv_pad;
+  a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr; a.minv_pad = h->minv_pad; a.mean_out = nullptr; a.pooled = h->pooled ? 1 : 0;
   a.xs_doubles = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? (int)((size_t)h->T * h->EPL) : 0;
   a.lX = h->lX; a.lXt = h->lXt; a.ly = h->ly; a.lr = h->lr; a.lN = h->lN; a.lLd = h->lLd; a.lXp = h->lXp;
   return a;
@@ -527,7 +562,7 @@ int dhmc_destroy(dhmc_handle* h) {
   cudaFree(h->q); cudaFree(h->g); cudaFree(h->lq); cudaFree(h->p); cudaFree(h->minv); cudaFree(h->eps);
   cudaFree(h->mparams); cudaFree(h->status); cudaFree(h->scratch); cudaFree(h->counter);
   cudaFree(h->total_steps);
-  cudaFree(h->minv_dense); cudaFree(h->wt); cudaFree(h->covt); cudaFree(h->dense_tmp); cudaFree(h->minv_pad);
+  cudaFree(h->minv_dense); cudaFree(h->wt); cudaFree(h->covt); cudaFree(h->dense_tmp); cudaFree(h->minv_pad); cudaFree(h->mean_pool);
   cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr); cudaFree(h->lXp);
   for (void* r : h->registered) cudaHostUnregister(r);
   if (h->comm) dhmc_comm_destroy(h);
@@ -761,6 +796,7 @@ int dhmc_set_metric_dense(dhmc_handle* h, const double* minv, int broadcast) {
   CK(cudaSetDevice(h->cfg.device));
   int rc = ensure_dense(h);
   if (rc != DHMC_OK) return rc;
+  h->pooled = false;
   const size_t B = (size_t)h->cfg.n_chains, dd = (size_t)h->cfg.dim * h->cfg.dim;
   if (broadcast) {
     double* tmp = nullptr;
@@ -802,6 +838,7 @@ int dhmc_set_metric(dhmc_handle* h, const double* minv, int broadcast) {
   }
   h->launches += 1;
   CK(cudaStreamSynchronize(h->stream));
+  h->pooled = false;
   if (h->dense) { h->dense = false; int rc = plan(h); if (rc != DHMC_OK) return rc; }
   return DHMC_OK;
 }
@@ -930,7 +967,7 @@ static bool host_mapped(const void* p, void** dev) {
 static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda, const double* p_over_host,
                     const uint32_t* dir_over_host, double* posterior, dhmc_tree_stats* stats,
                     double* eps_used, double* logdens, bool outputs_on_device, bool advance_t,
-                    const double* q_host = nullptr, int thin = 1) {
+                    const double* q_host = nullptr, int thin = 1, bool pool_metric = false) {
   if ((!h->has_position && !q_host) || !h->has_eps) { h->err = "set position and step size (or run the initial search) first"; return DHMC_EARG; }
   const auto tr0 = std::chrono::steady_clock::now();
   auto tr_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count(); };
@@ -1005,6 +1042,7 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   a.N = N; a.thin = thin; a.N_keep = (int)n; a.cfg = cfg; a.p_override = d_p; a.dir_override = d_dir;
   a.out_q = d_post; a.out_stats = d_stats; a.out_eps = d_eps; a.out_lq = d_ld;
   if (cfg.metric == DHMC_METRIC_SYMMETRIC) a.covt = h->covt;
+  if (pool_metric) a.mean_out = h->mean_pool;
   const size_t out_bytes = posterior ? sizeof(double) * B * n * D : 0;
   // chunks must stay many waves long, or the ragged tail of every chunk idles the SMs
   // chunks overlap the staged downloads (and the upload of q_host) with the sampling of the next chunk; with direct
@@ -1015,7 +1053,10 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   if (const char* ev = std::getenv("DHMC_E2E_CHUNKS")) { const int v = std::atoi(ev); if (v >= 1 && v <= 16 && !outputs_on_device) nchunks = v; }
   CKR(cudaMemsetAsync(h->status, 0, sizeof(int) * B, h->stream));   // status words describe the current call
   for (int ci = 0; ci < nchunks; ++ci) {
-    const size_t c0 = B * ci / nchunks, c1 = B * (ci + 1) / nchunks, nc = c1 - c0;
+    // (a pooled metric keeps its groups of 8 chains inside one chunk)
+    const size_t unit = h->pooled ? 8 : 1;
+    const size_t c0 = (B / unit) * ci / nchunks * unit, c1 = (B / unit) * (ci + 1) / nchunks * unit, nc = c1 - c0;
+    if (nc == 0) continue;
     a.chain_begin = (int)c0; a.chain_end = (int)c1;
     if (q_host) {
       // positions of this chunk: H2D on its own stream, then evaluate_ℓ(strict) on the compute
@@ -1082,15 +1123,19 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   if (h->trace) std::fprintf(stderr, "[dhmc trace] host: after status check %.2f ms\n", tr_ms());
   if (rc != DHMC_OK) return rc;
   if (cfg.metric == DHMC_METRIC_DIAGONAL && h->dense) {   // κ ← Diagonal: back to the diagonal kernels
-    h->dense = false;
+    h->dense = false; h->pooled = false;
     rc = plan(h);
     if (rc != DHMC_OK) return rc;
   }
   if (cfg.metric == DHMC_METRIC_SYMMETRIC) {
     // κ = GaussianKineticEnergy(regularize_M⁻¹(sample_M⁻¹(Symmetric, X), λ)) — mcmc.jl:282
     const int fgrid = (int)std::min<size_t>((size_t)h->sm_count * 4, (size_t)h->cfg.n_chains);
-    k_cov_finish<<<fgrid, 128, 0, h->stream>>>(h->covt, h->minv_dense, N, lambda, (int)h->cfg.dim, (int)h->cfg.n_chains);
+    if (pool_metric)
+      k_cov_pool<<<fgrid, 128, sizeof(double) * h->cfg.dim, h->stream>>>(h->covt, h->mean_pool, h->minv_dense, N, lambda, (int)h->cfg.dim, (int)h->cfg.n_chains);
+    else
+      k_cov_finish<<<fgrid, 128, 0, h->stream>>>(h->covt, h->minv_dense, N, lambda, (int)h->cfg.dim, (int)h->cfg.n_chains);
     h->launches += 1;
+    h->pooled = pool_metric;
     rc = factor_and_switch(h);
   }
   return rc;
@@ -1109,9 +1154,12 @@ int dhmc_warmup_stage(dhmc_handle* h, int32_t N, int32_t metric, const dhmc_dual
   // TuningNUTS @argchecks — mcmc.jl:191-192
   if (!(N >= 20)) { h->err = "N ≥ 20"; return DHMC_EARG; }
   if (!(lambda >= 0)) { h->err = "λ ≥ 0"; return DHMC_EARG; }
-  if (metric != DHMC_METRIC_NOTHING && metric != DHMC_METRIC_DIAGONAL && metric != DHMC_METRIC_SYMMETRIC) { h->err = "metric: Nothing, Diagonal or Symmetric"; return DHMC_EARG; }
+  if (metric != DHMC_METRIC_NOTHING && metric != DHMC_METRIC_DIAGONAL && metric != DHMC_METRIC_SYMMETRIC &&
+      metric != DHMC_METRIC_SYMMETRIC_POOLED) { h->err = "metric: Nothing, Diagonal, Symmetric (or the pooled Symmetric option)"; return DHMC_EARG; }
+  const bool pool = metric == DHMC_METRIC_SYMMETRIC_POOLED;
+  if (pool && (h->cfg.n_chains % 8 != 0 || h->cfg.chain_offset % 8 != 0)) { h->err = "pooled metric: n_chains and chain_offset must be multiples of 8"; return DHMC_EARG; }
   AdaptConfig cfg{};
-  cfg.metric = metric;
+  cfg.metric = pool ? DHMC_METRIC_SYMMETRIC : metric;
   if (da) {
     // DualAveraging @argchecks — stepsize.jl:108-111
     if (!(0 < da->delta && da->delta < 1) || !(da->gamma > 0) || !(0.5 < da->kappa && da->kappa <= 1) || !(da->t0 >= 0)) {
@@ -1119,8 +1167,9 @@ int dhmc_warmup_stage(dhmc_handle* h, int32_t N, int32_t metric, const dhmc_dual
     }
     cfg.adapt = 1; cfg.delta = da->delta; cfg.gamma = da->gamma; cfg.kappa = da->kappa; cfg.t0 = da->t0;
   }
-  if (metric == DHMC_METRIC_SYMMETRIC) { int rcd = ensure_dense(h); if (rcd != DHMC_OK) return rcd; }
-  return run_nuts(h, N, cfg, lambda, nullptr, nullptr, posterior, stats, eps_used, logdens, false, true);
+  if (cfg.metric == DHMC_METRIC_SYMMETRIC) { int rcd = ensure_dense(h); if (rcd != DHMC_OK) return rcd; }
+  if (pool && !h->mean_pool) CK(cudaMalloc(&h->mean_pool, sizeof(double) * (size_t)h->cfg.n_chains * (size_t)h->cfg.dim));
+  return run_nuts(h, N, cfg, lambda, nullptr, nullptr, posterior, stats, eps_used, logdens, false, true, nullptr, 1, pool);
 }
 
 int dhmc_mcmc(dhmc_handle* h, int32_t N, double* posterior, dhmc_tree_stats* stats, double* logdens) {

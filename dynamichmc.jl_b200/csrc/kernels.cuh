@@ -61,6 +61,8 @@ struct KArgs {
   int levels, ntab;             // deep kernels (max_depth > 12) only: stack entries per warp (max_depth + 1), slot-table entries;
                                 // all other kernels use the compile-time kStdLevels / kStdTab so that the offsets fold into immediates
   int thin, N_keep;             // draws: every thin-th transition is kept (N_keep = N / thin rows per chain)
+  double* mean_out;             // pooled Symmetric stage: the window mean of every chain [B][D] (else null)
+  int pooled;                   // the current dense metric is shared by every group of 8 chains (DHMC_METRIC_SYMMETRIC_POOLED)
   const double* minv_pad;       // tensor-core mat-vec: padded M⁻¹ [B][⌈D/32⌉·32][tma_xs(D)]
   unsigned long long* prof;     // profiling builds (-DDHMC_PROFILE_ROUNDS): [grid][32 warps][16] cycle counters
 };
@@ -96,7 +98,7 @@ __device__ __forceinline__ void setup_backend(DeviceBackend<EPL, FAM, W, DN, G, 
   b.lX = a.lX; b.lXt = a.lXt; b.ly = a.ly; b.lN = a.lN; b.lLd = a.lLd;
   b.lr = a.lr ? a.lr + (size_t)blockIdx.x * a.lN : nullptr;
   b.lll = nullptr; b.cb_flags = nullptr; b.cb_beta = b.cb_grad = b.cb_stage = nullptr;
-  b.cb_shared = nullptr; b.ring_n = 0; b.lXp = nullptr; b.Mp = a.minv_pad;
+  b.cb_shared = nullptr; b.ring_n = 0; b.lXp = nullptr; b.Mp = a.minv_pad; b.pooled = a.pooled;
   b.prof = a.prof ? a.prof + (size_t)blockIdx.x * 32 * 16 : nullptr;
   size_t group = blockIdx.x;
   if constexpr (G > 1) {
@@ -164,6 +166,16 @@ __device__ __forceinline__ int next_chain_group(B& b, unsigned* counter, int* s_
     return s_misc[0];
   }
 }
+// pooled metric: the whole CTA (8 chains = one metric group) takes group g; warp w runs chain begin + 8·g + w.  All warps
+// arrive here together (they left the previous group through coop_finish), so a CTA barrier is safe.
+template <class B>
+__device__ __forceinline__ int next_pooled_group(B& b, unsigned* counter, int begin) {
+  int* slot = reinterpret_cast<int*>(b.cb_shared + 96);
+  __syncthreads();
+  if (b.ctid == 0) *slot = (int)atomicAdd(counter, 1u);
+  __syncthreads();
+  return begin + 8 * (*slot) + b.grp;
+}
 __device__ __forceinline__ int next_chain(unsigned* counter, int* s_misc, int begin) {
   __syncthreads();
   if (threadIdx.x == 0) s_misc[0] = begin + (int)atomicAdd(counter, 1u);
@@ -190,6 +202,7 @@ __device__ __forceinline__ void load_chain(DeviceBackend<EPL, FAM, W, DN, G, MM,
   b.lq = a.lq[c];
   const size_t dd = (size_t)a.D * a.D;
   if (a.covt) b.covt = a.covt + (size_t)c * dd;
+  b.mean_out = a.mean_out ? a.mean_out + (size_t)c * a.D : nullptr;
   if constexpr (DN) {
     b.Mrow = a.minv_dense + (size_t)c * dd;
     b.Wt = a.wt + (size_t)c * dd;
@@ -245,8 +258,12 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nu
                                        smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles, DP ? a.levels : kStdLevels, DP ? a.ntab : kStdTab).misc_off);
   for (;;) {
     int c;
-    if constexpr (G > 1) c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
-    else c = next_chain(a.counter, s_misc, a.chain_begin);
+    if constexpr (G > 1) {
+      if (MM && a.pooled) c = next_pooled_group(b, a.counter, a.chain_begin);    // the CTA takes a whole metric group
+      else c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
+    } else {
+      c = next_chain(a.counter, s_misc, a.chain_begin);
+    }
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
     NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM, DP>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
@@ -264,6 +281,7 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_nu
       if (m.status) atomicOr(a.status + c, m.status);
       atomicAdd(a.total_steps, (unsigned long long)m.steps_out);
     }
+    if constexpr (G > 1 && MM) { if (a.pooled) b.coop_finish(); }     // pooled metric: the group leaves together, then the CTA takes the next one
   }
   b.coop_finish();
 #ifdef DHMC_PROFILE_ROUNDS
@@ -281,8 +299,12 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_se
                                        smem_layout(W, a.n_sm, b.stride, (size_t)a.xs_doubles, DP ? a.levels : kStdLevels, DP ? a.ntab : kStdTab).misc_off);
   for (;;) {
     int c;
-    if constexpr (G > 1) c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
-    else c = next_chain(a.counter, s_misc, a.chain_begin);
+    if constexpr (G > 1) {
+      if (MM && a.pooled) c = next_pooled_group(b, a.counter, a.chain_begin);
+      else c = next_chain_group(b, a.counter, s_misc, a.chain_begin);
+    } else {
+      c = next_chain(a.counter, s_misc, a.chain_begin);
+    }
     if (c >= a.chain_end) break;
     load_chain(b, a, c, false);
     NutsMachine<DeviceBackend<EPL, FAM, W, DN, G, MM, DP>> m(b, dm_make_key(a.seed, (uint64_t)(a.chain_offset + c)),
@@ -292,6 +314,7 @@ __global__ void __launch_bounds__(32 * W * G, G > 1 ? 1 : min_ctas(W, EPL)) k_se
       a.eps[c] = eps;
       if (m.status) atomicOr(a.status + c, m.status);
     }
+    if constexpr (G > 1 && MM) { if (a.pooled) b.coop_finish(); }
   }
   b.coop_finish();
 }

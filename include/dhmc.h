@@ -50,7 +50,13 @@ enum {
 };
 
 /* log-density family ids: see include/dhmc_models.h */
-enum { DHMC_METRIC_NOTHING = 0, DHMC_METRIC_DIAGONAL = 1, DHMC_METRIC_SYMMETRIC = 2 };
+enum { DHMC_METRIC_NOTHING = 0, DHMC_METRIC_DIAGONAL = 1, DHMC_METRIC_SYMMETRIC = 2,
+       /* NOT reference semantics (the reference adapts every chain on its own window, mcmc.jl:282): the optional exchange of
+        * SURVEY.md §8e.  Every group of 8 consecutive GLOBAL chains ends the window with ONE dense metric estimated from the
+        * pooled draws of the group (per-chain streaming moments merged in a fixed order, same shrinkage λ).  With a shared
+        * metric the packed kernels run M⁻¹·[8 vectors] as a true FP64 tensor-core GEMM and read the metric once per group.
+        * Needs n_chains and chain_offset to be multiples of 8. */
+       DHMC_METRIC_SYMMETRIC_POOLED = 3 };
 
 typedef struct dhmc_handle dhmc_handle;
 

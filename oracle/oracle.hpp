@@ -756,7 +756,10 @@ inline vec regularize_dense(const vec& S, int D, double lambda) {
 }
 
 enum StageKind { STAGE_NOTHING = 0, STAGE_STEPSIZE_SEARCH = 1, STAGE_TUNING = 2 };
-enum MetricKind { METRIC_NOTHING = 0, METRIC_DIAGONAL = 1, METRIC_SYMMETRIC = 2 };
+// METRIC_SYMMETRIC_POOLED is NOT in the reference (which adapts every chain on its own draws, mcmc.jl:282): the optional
+// exchange of SURVEY.md §8e — the eight chains of a group share one dense metric estimated from their pooled window.
+enum MetricKind { METRIC_NOTHING = 0, METRIC_DIAGONAL = 1, METRIC_SYMMETRIC = 2, METRIC_SYMMETRIC_POOLED = 3 };
+constexpr int kPoolGroup = 8;
 struct Stage {
   int kind = STAGE_TUNING; int N = 0; int metric = METRIC_NOTHING; bool dual_averaging = true;
   double lambda = 0;  // regularisation; identity for Diagonal (mcmc.jl:223)
@@ -801,7 +804,13 @@ inline void warmup_search(Sampler& S, const InitialStepsizeSearch& par, WarmupSt
 }
 
 // warmup(::TuningNUTS{M}) — mcmc.jl:258-286
-inline ChainOutput warmup_tuning(Sampler& S, const Stage& stage, WarmupState& st) {
+struct WelfordCov;
+inline ChainOutput warmup_tuning(Sampler& S, const Stage& stage, WarmupState& st, WelfordCov* pooled_out = nullptr);
+// Pooled window covariance of a chain group from the chains' streaming means / co-moments (each over n draws), with the
+// reference's shrinkage (regularize_M⁻¹, mcmc.jl:218-221).  Fixed order (chains 0…G−1, sequential) — what k_cov_pool does.
+inline vec pooled_regularized_cov(const std::vector<WelfordCov>& w, int D, double lambda);
+
+inline ChainOutput warmup_tuning(Sampler& S, const Stage& stage, WarmupState& st, WelfordCov* pooled_out) {
   if (!(stage.N >= 20)) throw ArgumentError("N ≥ 20");
   if (!(stage.lambda >= 0)) throw ArgumentError("λ ≥ 0");
   ChainOutput out;
@@ -810,7 +819,9 @@ inline ChainOutput warmup_tuning(Sampler& S, const Stage& stage, WarmupState& st
   double fixed_eps = st.eps;
   if (stage.dual_averaging) da = initial_adaptation_state(stage.da, st.eps);
   Welford wf(S.l.D);
-  WelfordCov wc(stage.metric == METRIC_SYMMETRIC ? S.l.D : 1);
+  const bool pooled = stage.metric == METRIC_SYMMETRIC_POOLED;
+  if (pooled && !pooled_out) throw ArgumentError("the pooled metric needs the whole chain group (mcmc_with_warmup_pooled)");
+  WelfordCov wc((stage.metric == METRIC_SYMMETRIC || pooled) ? S.l.D : 1);
   for (int i = 0; i < stage.N; ++i) {
     double eps = stage.dual_averaging ? current_eps(da) : fixed_eps;
     out.eps_used.push_back(eps);
@@ -820,7 +831,7 @@ inline ChainOutput warmup_tuning(Sampler& S, const Stage& stage, WarmupState& st
     st.Q = Q;
     out.posterior.push_back(Q.q); out.logdensities.push_back(Q.lq); out.stats.push_back(stats);
     if (stage.metric == METRIC_DIAGONAL && S.welford) wf.push(Q.q);
-    if (stage.metric == METRIC_SYMMETRIC && S.welford) wc.push(Q.q);
+    if ((stage.metric == METRIC_SYMMETRIC && S.welford) || pooled) wc.push(Q.q);
     if (stage.dual_averaging) da = adapt_stepsize(stage.da, da, stats.acceptance_rate);
   }
   if (stage.metric == METRIC_DIAGONAL) {
@@ -830,8 +841,30 @@ inline ChainOutput warmup_tuning(Sampler& S, const Stage& stage, WarmupState& st
     vec C = S.welford ? wc.covariance() : sample_cov_twopass(out.posterior);
     st.k = KineticEnergy::Dense(regularize_dense(C, S.l.D, stage.lambda), S.l.D);   // mcmc.jl:282
   }
+  if (pooled) *pooled_out = wc;            // κ of the whole group is set by the caller from the pooled moments
   st.eps = stage.dual_averaging ? final_eps(da) : fixed_eps;
   return out;
+}
+inline vec pooled_regularized_cov(const std::vector<WelfordCov>& w, int D, double lambda) {
+  const int G = (int)w.size();
+  const double n = (double)w[0].n;
+  vec mean(D);
+  for (int i = 0; i < D; ++i) {
+    double m = w[0].mean[i];
+    for (int c = 1; c < G; ++c) m = m + w[c].mean[i];
+    mean[i] = m / (double)G;
+  }
+  vec S((size_t)D * D);
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j <= i; ++j) {
+      double acc = 0.0;
+      for (int c = 0; c < G; ++c) {
+        const double di = w[c].mean[i] - mean[i], dj = w[c].mean[j] - mean[j];
+        acc = acc + (w[c].c[(size_t)i * D + j] + (n * di) * dj);
+      }
+      S[(size_t)i * D + j] = S[(size_t)j * D + i] = acc / ((double)G * n - 1.0);
+    }
+  return regularize_dense(S, D, lambda);
 }
 
 // mcmc — mcmc.jl:366-381
@@ -874,6 +907,38 @@ inline McmcResult mcmc_with_warmup(Sampler& S, int N, const std::vector<Stage>& 
   if (!st.has_eps) throw ArgumentError("mcmc needs a stepsize");
   ChainOutput inf = mcmc(S, N, st);
   return McmcResult{inf, st, wu};
+}
+
+// mcmc_with_warmup for a chain group with pooled Symmetric stages: the chains run stage by stage; a pooled stage ends with
+// one metric for the whole group.  Everything else is the per-chain reference flow.
+inline std::vector<McmcResult> mcmc_with_warmup_pooled(std::vector<Sampler>& S, int N, const std::vector<Stage>& stages) {
+  const int G = (int)S.size();
+  std::vector<WarmupState> st;
+  std::vector<std::vector<ChainOutput>> wu(G);
+  for (int c = 0; c < G; ++c) { S[c].alg.check(); st.push_back(initialize_warmup_state(S[c], nullptr, nullptr, nullptr)); }
+  for (const Stage& s : stages) {
+    if (s.kind == STAGE_NOTHING) { for (int c = 0; c < G; ++c) wu[c].push_back({}); continue; }
+    if (s.kind == STAGE_STEPSIZE_SEARCH) {
+      for (int c = 0; c < G; ++c) { warmup_search(S[c], s.search, st[c]); wu[c].push_back({}); }
+      continue;
+    }
+    std::vector<WelfordCov> w(G, WelfordCov(1));
+    for (int c = 0; c < G; ++c) {
+      if (!st[c].has_eps) throw ArgumentError("TuningNUTS needs a stepsize");
+      wu[c].push_back(warmup_tuning(S[c], s, st[c], s.metric == METRIC_SYMMETRIC_POOLED ? &w[c] : nullptr));
+    }
+    if (s.metric == METRIC_SYMMETRIC_POOLED) {
+      const vec M = pooled_regularized_cov(w, S[0].l.D, s.lambda);
+      const KineticEnergy k = KineticEnergy::Dense(M, S[0].l.D);
+      for (int c = 0; c < G; ++c) st[c].k = k;
+    }
+  }
+  std::vector<McmcResult> res;
+  for (int c = 0; c < G; ++c) {
+    ChainOutput inf = mcmc(S[c], N, st[c]);
+    res.push_back(McmcResult{inf, st[c], wu[c]});
+  }
+  return res;
 }
 
 }  // namespace orc

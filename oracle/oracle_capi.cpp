@@ -343,6 +343,32 @@ int orc_mcmc_with_warmup(int family, int D, const double* params, int T, int max
   });
 }
 
+// mcmc_with_warmup for the chain group [chain0, chain0 + 8) with pooled Symmetric stages (metric code 3).  Outputs for all
+// eight chains: posterior [8][N][D], stats [8][N], logdens [8][N], eps_out [8]; minv_out [D*D] is the (shared) final metric.
+int orc_mcmc_with_warmup_pooled(int family, int D, const double* params, int T, int max_depth, double min_delta,
+                                uint64_t seed, uint64_t chain0, int N, int n_stages, const int* kind, const int* stN,
+                                const int* metric, const int* da_on, const double* da4, const double* search3,
+                                double* posterior, TreeStatistics* stats, double* logdens, double* minv_out, double* eps_out) {
+  return guarded([&] {
+    auto stages = make_stages(n_stages, kind, stN, metric, da_on, da4, search3);
+    std::vector<Sampler> S(kPoolGroup);
+    for (int c = 0; c < kPoolGroup; ++c) {
+      S[c].l = make_model(family, D, params, nparams_of(family, D), T, 0);
+      S[c].alg = NUTS{max_depth, min_delta}; S[c].key = dm_make_key(seed, chain0 + (uint64_t)c); S[c].welford = true;
+    }
+    auto r = mcmc_with_warmup_pooled(S, N, stages);
+    for (int c = 0; c < kPoolGroup; ++c) {
+      for (int i = 0; i < N; ++i) {
+        if (posterior) std::memcpy(posterior + ((size_t)c * N + i) * D, r[c].inference.posterior[i].data(), sizeof(double) * D);
+        if (stats) stats[(size_t)c * N + i] = r[c].inference.stats[i];
+        if (logdens) logdens[(size_t)c * N + i] = r[c].inference.logdensities[i];
+      }
+      if (eps_out) eps_out[c] = r[c].final_state.eps;
+    }
+    if (minv_out) std::memcpy(minv_out, r[0].final_state.k.minv.data(), sizeof(double) * r[0].final_state.k.minv.size());
+  });
+}
+
 // Multi-threaded CPU baseline: n_chains chains, one per task, n_threads
 // std::threads (mirrors OhMyThreads.tcollect over mcmc_with_warmup calls,
 // test/sample-correctness_utilities.jl:17).  Fixed eps / fixed minv sampling

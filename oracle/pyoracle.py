@@ -387,6 +387,24 @@ def default_warmup_stages(init_steps=75, middle_steps=25, doubling_stages=5, ter
     return st
 
 
+METRIC_SYMMETRIC_POOLED = 3     # not in the reference: one dense metric per group of 8 chains (SURVEY §8e "optional exchange")
+
+
+def mcmc_with_warmup_pooled(family, D, N, seed, chain0, stages, params=None, T=32, max_depth=10, min_delta=-1000.0,
+                            da=(0.8, 0.05, 0.75, 10), search=(0.1, float(np.log(0.8)), 400)):
+    """The chain group [chain0, chain0 + 8) with pooled Symmetric stages: dict of posterior [8, N, D], tree_statistics [8, N],
+    logdensities [8, N], eps [8], minv [D, D] (the shared final metric)."""
+    (kind, stN, metric, da_on), ns = _stage_arrays(stages)
+    pr = _params(family, D, params)
+    post = np.empty((8, N, D)); stats = np.zeros((8, N), dtype=tree_stats_dtype); logd = np.empty((8, N))
+    minv = np.empty(D * D); eps = np.empty(8)
+    _check(lib().orc_mcmc_with_warmup_pooled(
+        C.c_int(family), C.c_int(D), _p(pr), C.c_int(T), C.c_int(max_depth), C.c_double(min_delta), C.c_uint64(seed),
+        C.c_uint64(chain0), C.c_int(N), C.c_int(ns), _p(kind), _p(stN), _p(metric), _p(da_on), _p(_d(da)), _p(_d(search)),
+        _p(post), _p(stats), _p(logd), _p(minv), _p(eps)))
+    return dict(posterior_matrix=post, tree_statistics=stats, logdensities=logd, eps=eps, minv=minv.reshape(D, D))
+
+
 def _stage_arrays(stages):
     arr = np.array(stages, dtype=np.int32).reshape(-1, 4) if len(stages) else np.zeros((0, 4), np.int32)
     cols = [np.ascontiguousarray(arr[:, k]) for k in range(4)]

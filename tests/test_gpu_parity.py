@@ -565,6 +565,37 @@ def test_logistic_mma_likelihood_equals_fma_loops(pkg, monkeypatch, N, p, K, war
         r["engine"].close()
 
 
+@pytest.mark.parametrize("family", ["diag_normal", "logistic", "logistic256"])
+def test_pooled_symmetric_metric_matches_oracle(pkg, po, family):
+    """The optional exchange of SURVEY §8e (NOT reference semantics, off by default): TuningNUTS(N, M = SymmetricPooled) ends
+    the window with ONE dense metric per group of 8 consecutive global chains, estimated from the group's pooled draws.  The
+    oracle implements the same option (mcmc_with_warmup_pooled); draws, integers, step sizes and the shared metric must be
+    equal — one chain per CTA (diag_normal) and the packed tensor-core kernels, whose M⁻¹·[8 vectors] is then a true GEMM."""
+    rng = np.random.default_rng(4)
+    if family == "diag_normal":
+        D = 24
+        ℓ = pkg.DiagNormal(rng.normal(size=D), rng.uniform(0.3, 3, D)); fam, params = po.FAMILY_DIAG_NORMAL, ℓ.params()
+    else:
+        N_, D = (500, 20) if family == "logistic" else (900, 256)
+        ℓ, _ = pkg.LogisticRegression.synthetic(N=N_, p=D, seed=11); fam, params = po.FAMILY_LOGISTIC, po.logistic_params(ℓ.X, ℓ.y)
+    K, N, seed, off = 24, 4, 2026, 40
+    stages = (pkg.InitialStepsizeSearch(), pkg.TuningNUTS(22, pkg.DualAveraging()),
+              pkg.TuningNUTS(28, pkg.DualAveraging(), pkg.SymmetricPooled), pkg.TuningNUTS(20, pkg.DualAveraging()))
+    r = pkg.mcmc_keep_warmup(seed, ℓ, N, chains=K, warmup_stages=stages, chain_offset=off, keep_warmup=False)
+    T, _ = r["engine"].layout()
+    ostages = [(po.STAGE_SEARCH, 0, 0, 0), (po.STAGE_TUNING, 22, 0, 1), (po.STAGE_TUNING, 28, po.METRIC_SYMMETRIC_POOLED, 1),
+               (po.STAGE_TUNING, 20, 0, 1)]
+    for g in range(K // 8):
+        o = po.mcmc_with_warmup_pooled(fam, D, N, seed, off + 8 * g, ostages, params=params, T=T)
+        for c in range(8):
+            res = r["inference"][8 * g + c]
+            assert res["κ"].dense and np.array_equal(res["κ"].minv, o["minv"]) and res["ϵ"] == o["eps"][c]
+            assert np.array_equal(res["posterior_matrix"].T, o["posterior_matrix"][c])
+            for f in INT_FIELDS:
+                assert np.array_equal(res["tree_statistics"][f], o["tree_statistics"][c][f])
+    r["engine"].close()
+
+
 def test_c4_shape_matches_oracle(pkg, po):
     """BASELINE.json configs[3] at its exact shape — logistic regression N = 10 000, p = 256, per-chain dense
     (Symmetric) metric — against the oracle: warm-up with a Symmetric stage (so M⁻¹, W and ϵ are the adapted ones),

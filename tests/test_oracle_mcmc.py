@@ -70,3 +70,25 @@ def test_adapted_metric_tracks_posterior_variance(po):
     params = np.concatenate([np.zeros(D), 1 / var])
     r = po.mcmc_with_warmup(po.FAMILY_DIAG_NORMAL, D, 200, seed=8, chain=0, params=params)
     assert np.all(np.abs(np.log(r["minv"] / var)) < 0.5)
+
+
+def test_pooled_metric_is_the_shrunk_covariance_of_the_pooled_window(po):
+    """The optional pooled-per-group metric (not reference semantics; include/dhmc.h DHMC_METRIC_SYMMETRIC_POOLED): the shared
+    M⁻¹ must be regularize_M⁻¹(cov(pooled draws of the 8 chains), λ) (mcmc.jl:211,218-221 applied to the pooled window) up to
+    rounding — here checked against numpy on the draws of a run whose LAST stage is the pooled window."""
+    D, Nw, seed, chain0 = 5, 40, 9, 24
+    stages = [(po.STAGE_SEARCH, 0, 0, 0), (po.STAGE_TUNING, 25, 0, 1), (po.STAGE_TUNING, Nw, po.METRIC_SYMMETRIC_POOLED, 1)]
+    r = po.mcmc_with_warmup_pooled(po.FAMILY_STD_NORMAL, D, 3, seed, chain0, stages, T=32)
+    # the window draws of every chain: rerun each chain alone with a per-chain Symmetric stage (same draws: the metric only
+    # changes AFTER the window) and collect the warm-up draws of that stage
+    st1 = [(po.STAGE_SEARCH, 0, 0, 0), (po.STAGE_TUNING, 25, 0, 1), (po.STAGE_TUNING, Nw, po.METRIC_SYMMETRIC, 1)]
+    window = []
+    for c in range(8):
+        o = po.mcmc_with_warmup(po.FAMILY_STD_NORMAL, D, 1, seed, chain0 + c, stages=st1, T=32, welford=True, keep_warmup=True)
+        window.append(o["warmup_posterior"][-Nw:])
+    X = np.concatenate(window)                                   # [8·Nw, D]
+    S = np.cov(X.T)
+    lam = 5.0 / Nw
+    expect = (1 - lam) * S + lam * np.diag(np.diag(S))
+    np.testing.assert_allclose(r["minv"], expect, rtol=1e-10, atol=1e-13)
+    assert np.all(r["eps"] > 0) and r["posterior_matrix"].shape == (8, 3, D)
