@@ -305,6 +305,10 @@ struct dhmc_handle {
   cudaEvent_t chunk_ev[16] = {};
   cudaEvent_t copy_ev[16] = {};
   bool trace = false;
+  double* tmp_b = nullptr;          // [B] scratch (phase log densities) and [B·D] momentum override / [D·D] broadcast source,
+  double* tmp_bd = nullptr;         // allocated once instead of per call
+  unsigned* tmp_dir = nullptr;
+  size_t tmp_bd_doubles = 0;
   std::vector<void*> registered;    // caller buffers page-locked on the fly (direct host writes of draws that exceed HBM)
   void* stage[4] = {nullptr, nullptr, nullptr, nullptr};   // grow-only device staging for host outputs
   size_t stage_bytes[4] = {0, 0, 0, 0};
@@ -421,6 +425,17 @@ static int kernel_part(const dhmc_handle* h, KernelId k, int G) {
   const bool heavy = (k == K_NUTS || k == K_SEARCH);
   if (heavy && h->deep) return 3;
   return G > 1 ? (h->coop_mma ? 2 : 1) : 0;
+}
+
+static int ensure_tmp(dhmc_handle* h, size_t doubles) {      // grow-only device scratch shared by the small entry points
+  if (!h->tmp_b) CK(cudaMalloc(&h->tmp_b, sizeof(double) * (size_t)h->cfg.n_chains));
+  if (!h->tmp_dir) CK(cudaMalloc(&h->tmp_dir, sizeof(unsigned) * (size_t)h->cfg.n_chains));
+  if (doubles > h->tmp_bd_doubles) {
+    cudaFree(h->tmp_bd); h->tmp_bd = nullptr; h->tmp_bd_doubles = 0;
+    CK(cudaMalloc(&h->tmp_bd, sizeof(double) * doubles));
+    h->tmp_bd_doubles = doubles;
+  }
+  return DHMC_OK;
 }
 
 static KArgs base_args(dhmc_handle* h) {
@@ -564,6 +579,7 @@ int dhmc_destroy(dhmc_handle* h) {
   cudaFree(h->total_steps);
   cudaFree(h->minv_dense); cudaFree(h->wt); cudaFree(h->covt); cudaFree(h->dense_tmp); cudaFree(h->minv_pad); cudaFree(h->mean_pool);
   cudaFree(h->lX); cudaFree(h->lXt); cudaFree(h->ly); cudaFree(h->lr); cudaFree(h->lXp);
+  cudaFree(h->tmp_b); cudaFree(h->tmp_bd); cudaFree(h->tmp_dir);
   for (void* r : h->registered) cudaHostUnregister(r);
   if (h->comm) dhmc_comm_destroy(h);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -799,13 +815,12 @@ int dhmc_set_metric_dense(dhmc_handle* h, const double* minv, int broadcast) {
   h->pooled = false;
   const size_t B = (size_t)h->cfg.n_chains, dd = (size_t)h->cfg.dim * h->cfg.dim;
   if (broadcast) {
-    double* tmp = nullptr;
-    CK(cudaMalloc(&tmp, sizeof(double) * dd));
-    CK(cudaMemcpyAsync(tmp, minv, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream));
-    k_broadcast_mat<<<1024, 256, 0, h->stream>>>(h->minv_dense, tmp, dd, B);
+    int rct = ensure_tmp(h, dd);
+    if (rct != DHMC_OK) return rct;
+    CK(cudaMemcpyAsync(h->tmp_bd, minv, sizeof(double) * dd, cudaMemcpyHostToDevice, h->stream));
+    k_broadcast_mat<<<1024, 256, 0, h->stream>>>(h->minv_dense, h->tmp_bd, dd, B);
     h->launches += 1;
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(tmp);
   } else {
     CK(cudaMemcpyAsync(h->minv_dense, minv, sizeof(double) * B * dd, cudaMemcpyHostToDevice, h->stream));
   }
@@ -827,12 +842,11 @@ int dhmc_set_metric(dhmc_handle* h, const double* minv, int broadcast) {
   if (!minv) {
     k_fill<<<1024, 256, 0, h->stream>>>(h->minv, 1.0, B * D);
   } else if (broadcast) {
-    double* tmp = nullptr;
-    CK(cudaMalloc(&tmp, sizeof(double) * D));
-    CK(cudaMemcpyAsync(tmp, minv, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
-    k_broadcast<<<1024, 256, 0, h->stream>>>(h->minv, tmp, D, B);
+    int rct = ensure_tmp(h, D);
+    if (rct != DHMC_OK) return rct;
+    CK(cudaMemcpyAsync(h->tmp_bd, minv, sizeof(double) * D, cudaMemcpyHostToDevice, h->stream));
+    k_broadcast<<<1024, 256, 0, h->stream>>>(h->minv, h->tmp_bd, D, B);
     CK(cudaStreamSynchronize(h->stream));
-    cudaFree(tmp);
   } else {
     CK(cudaMemcpyAsync(h->minv, minv, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
   }
@@ -907,18 +921,15 @@ int dhmc_phase_logdensity(dhmc_handle* h, double* out) {
   if (!h || !out) return DHMC_EARG;
   CK(cudaSetDevice(h->cfg.device));
   const size_t B = (size_t)h->cfg.n_chains;
-  double* d = nullptr;
-  CK(cudaMalloc(&d, sizeof(double) * B));
+  int rc = ensure_tmp(h, 0);
+  if (rc != DHMC_OK) return rc;
   KArgs a = base_args(h);
-  a.out_phase = d;
-  int rc = launch(h, K_PHASE, a, 0);
-  if (rc == DHMC_OK) {
-    cudaError_t e = cudaMemcpyAsync(out, d, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); rc = DHMC_ECUDA; }
-  }
-  cudaFree(d);
-  return rc;
+  a.out_phase = h->tmp_b;
+  rc = launch(h, K_PHASE, a, 0);
+  if (rc != DHMC_OK) return rc;
+  CK(cudaMemcpyAsync(out, h->tmp_b, sizeof(double) * B, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return DHMC_OK;
 }
 
 int dhmc_find_initial_stepsize(dhmc_handle* h, double initial_eps, double log_threshold, int32_t maxiter) {
@@ -979,7 +990,7 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
   dhmc_tree_stats* d_stats = nullptr;
   unsigned* d_dir = nullptr;
   int rc = DHMC_OK;
-  auto cleanup = [&] { cudaFree(d_p); cudaFree(d_dir); };
+  auto cleanup = [&] {};              // (the override buffers are the handle's grow-only scratch)
 #define CKR(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); return e_ == cudaErrorMemoryAllocation ? DHMC_ENOMEM : DHMC_ECUDA; } } while (0)
 #define CKS(call) do { int r_ = (call); if (r_ != DHMC_OK) { cleanup(); return r_; } } while (0)
   // Host outputs.  Page-locked (pinned) buffers are written by the kernel itself through their device alias — no staging
@@ -1029,12 +1040,13 @@ static int run_nuts(dhmc_handle* h, int N, const AdaptConfig& cfg, double lambda
       else { CKS(ensure_stage(h, 3, sizeof(double) * B * n)); d_ld = (double*)h->stage[3]; }
     }
   }
+  if (p_over_host || dir_over_host) CKS(ensure_tmp(h, p_over_host ? B * D : 0));
   if (p_over_host) {
-    CKR(cudaMalloc(&d_p, sizeof(double) * B * D));
+    d_p = h->tmp_bd;
     CKR(cudaMemcpyAsync(d_p, p_over_host, sizeof(double) * B * D, cudaMemcpyHostToDevice, h->stream));
   }
   if (dir_over_host) {
-    CKR(cudaMalloc(&d_dir, sizeof(unsigned) * B));
+    d_dir = h->tmp_dir;
     CKR(cudaMemcpyAsync(d_dir, dir_over_host, sizeof(unsigned) * B, cudaMemcpyHostToDevice, h->stream));
   }
   tr_pt[0] = tr_ms();
