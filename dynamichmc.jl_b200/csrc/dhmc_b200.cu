@@ -378,7 +378,7 @@ static int plan(dhmc_handle* h) {
   int& reg_ctas = h->reg_ctas[h->dense ? 1 : 0];
   if (reg_ctas == 0) {
     const void* fn = lookup_kernel(h->cfg.family, kernel_part(h, K_NUTS, G), h->W, h->EPL, K_NUTS, h->dense);
-    if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
+    if (!fn) { h->err = "dense metric: layout not built"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L0.total);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, fn, T * G, L0.total);
     if (e != cudaSuccess) { h->err = std::string("occupancy query: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
@@ -491,7 +491,7 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_st
 #endif
   {
     const void* fn = lookup_kernel(h->cfg.family, kernel_part(h, k, G), h->W, h->EPL, k, h->dense);
-    if (!fn) { h->err = "dense metric: layout not built (dim <= 512)"; return DHMC_EARG; }
+    if (!fn) { h->err = "dense metric: layout not built"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
     void* params[] = {(void*)&a};
@@ -551,7 +551,7 @@ static void choose_layout(int64_t D, int req_T, int* T, int* EPL) {
     *T = req_T;
     const int W = req_T / 32;
     int e = (int)((D + req_T - 1) / req_T);
-    e = e <= 1 ? 1 : e <= 2 ? 2 : e <= 4 ? 4 : e <= 8 ? 8 : 0;
+    e = e <= 1 ? 1 : e <= 2 ? 2 : e <= 4 ? 4 : e <= 8 ? 8 : e <= 16 ? 16 : e <= 32 ? 32 : 0;
     if (e && !layout_supported(W, e)) e = (e < 4 && layout_supported(W, 4)) ? 4 : (e < 8 && layout_supported(W, 8)) ? 8 : 0;
     *EPL = e;
     return;
@@ -563,6 +563,8 @@ static void choose_layout(int64_t D, int req_T, int* T, int* EPL) {
   else if (D <= 512) { *T = 128; *EPL = 4; }
   else if (D <= 1024) { *T = 128; *EPL = 8; }
   else if (D <= 2048) { *T = 256; *EPL = 8; }
+  else if (D <= 4096) { *T = 256; *EPL = 16; }
+  else if (D <= 8192) { *T = 256; *EPL = 32; }    // the vectors no longer fit the register file: correct, not fast
   else { *T = 0; *EPL = 0; }
 }
 
@@ -625,7 +627,7 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   // the FMA formulation (coop_core) — same results bit for bit
   const char* evm = std::getenv("DHMC_COOP_MMA");
   const bool coop_mma = pack > 1 && !(evm && std::atoi(evm) == 0);
-  if (T == 0 || EPL == 0) { g_create_err = "dim too large for this build (dim <= 8 * threads_per_chain <= 2048)"; return DHMC_EARG; }
+  if (T == 0 || EPL == 0) { g_create_err = "dim too large for this build (dim <= 32 * threads_per_chain, 32 only for 256 threads: dim <= 8192)"; return DHMC_EARG; }
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0) {
@@ -773,7 +775,7 @@ int dhmc_random_position(dhmc_handle* h) {
 
 static int ensure_dense(dhmc_handle* h) {
   if (h->minv_dense) return DHMC_OK;
-  if (h->cfg.dim > 512) { h->err = "dense (Symmetric) metric: dim <= 512 in this build"; return DHMC_EARG; }
+
   const size_t B = (size_t)h->cfg.n_chains, dd = (size_t)h->cfg.dim * h->cfg.dim;
   CK(cudaMalloc(&h->minv_dense, sizeof(double) * B * dd));
   CK(cudaMalloc(&h->wt, sizeof(double) * B * dd));

@@ -72,7 +72,7 @@ __host__ __device__ constexpr int min_ctas(int W, int EPL) {
 #ifndef DHMC_MINCTAS_W4E8
 #define DHMC_MINCTAS_W4E8 3
 #endif
-  return W == 1 ? 16 : W == 2 ? 8 : W == 4 ? (EPL >= 8 ? DHMC_MINCTAS_W4E8 : 4) : 2;
+  return W == 1 ? 16 : W == 2 ? 8 : W == 4 ? (EPL >= 8 ? DHMC_MINCTAS_W4E8 : 4) : EPL >= 16 ? 1 : 2;
 }
 
 // packed chain groups (G chains per CTA, one per warp): shared-memory bytes of the CTA-wide
@@ -398,11 +398,12 @@ enum KernelId { K_NUTS, K_SEARCH, K_LEAPFROG, K_EVAL, K_PHASE };
 // supported (warps per chain, elements per thread) layouts
 inline bool layout_supported(int W, int epl) {
   if (W == 1) return epl == 1 || epl == 2 || epl == 4 || epl == 8;
-  if (W == 2 || W == 4 || W == 8) return epl == 4 || epl == 8;
+  if (W == 2 || W == 4) return epl == 4 || epl == 8;
+  if (W == 8) return epl == 4 || epl == 8 || epl == 16 || epl == 32;       // dim <= 8192
   return false;
 }
-// dense (Symmetric metric) kernels are instantiated for the layouts of D <= 512
-constexpr bool dense_layout(int W, int EPL) { return W == 1 || (W == 2) || (W == 4 && EPL == 4); }
+// dense (Symmetric metric) kernels are instantiated for every layout (D <= 2048; memory: 3·D² doubles per chain)
+constexpr bool dense_layout(int W, int EPL) { return W >= 1 && EPL >= 1; }
 constexpr int kPack = 8;            // packed chain groups: chains per CTA (logistic family, dim <= 256)
 // packed layouts for dim <= 256: one warp per chain (up to 8 elements per lane) or two (dim 129…256)
 constexpr bool packed_layout(int W, int EPL) { return (W == 1) || (W == 2 && EPL == 4); }
@@ -455,17 +456,19 @@ const void* kernel_ptr(KernelId k, bool dense) {
 }
 template <int FAM, int PART>
 const void* family_kernel_ptr(int W, int epl, KernelId k, bool dense) {
-  switch (W * 16 + epl) {
-    case 1 * 16 + 1: return kernel_ptr<1, FAM, 1, PART>(k, dense);
-    case 1 * 16 + 2: return kernel_ptr<2, FAM, 1, PART>(k, dense);
-    case 1 * 16 + 4: return kernel_ptr<4, FAM, 1, PART>(k, dense);
-    case 1 * 16 + 8: return kernel_ptr<8, FAM, 1, PART>(k, dense);
-    case 2 * 16 + 4: return kernel_ptr<4, FAM, 2, PART>(k, dense);
-    case 2 * 16 + 8: return kernel_ptr<8, FAM, 2, PART>(k, dense);
-    case 4 * 16 + 4: return kernel_ptr<4, FAM, 4, PART>(k, dense);
-    case 4 * 16 + 8: return kernel_ptr<8, FAM, 4, PART>(k, dense);
-    case 8 * 16 + 4: return kernel_ptr<4, FAM, 8, PART>(k, dense);
-    case 8 * 16 + 8: return kernel_ptr<8, FAM, 8, PART>(k, dense);
+  switch (W * 64 + epl) {
+    case 1 * 64 + 1: return kernel_ptr<1, FAM, 1, PART>(k, dense);
+    case 1 * 64 + 2: return kernel_ptr<2, FAM, 1, PART>(k, dense);
+    case 1 * 64 + 4: return kernel_ptr<4, FAM, 1, PART>(k, dense);
+    case 1 * 64 + 8: return kernel_ptr<8, FAM, 1, PART>(k, dense);
+    case 2 * 64 + 4: return kernel_ptr<4, FAM, 2, PART>(k, dense);
+    case 2 * 64 + 8: return kernel_ptr<8, FAM, 2, PART>(k, dense);
+    case 4 * 64 + 4: return kernel_ptr<4, FAM, 4, PART>(k, dense);
+    case 4 * 64 + 8: return kernel_ptr<8, FAM, 4, PART>(k, dense);
+    case 8 * 64 + 4: return kernel_ptr<4, FAM, 8, PART>(k, dense);
+    case 8 * 64 + 8: return kernel_ptr<8, FAM, 8, PART>(k, dense);
+    case 8 * 64 + 16: return kernel_ptr<16, FAM, 8, PART>(k, dense);
+    case 8 * 64 + 32: return kernel_ptr<32, FAM, 8, PART>(k, dense);
   }
   return nullptr;
 }

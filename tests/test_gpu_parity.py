@@ -24,7 +24,7 @@ def _models(pkg, rng, D):
             (pkg.Funnel(D), 2, None)]
 
 
-@pytest.mark.parametrize("D", [2, 3, 10, 100, 200, 500, 1000, 2000])
+@pytest.mark.parametrize("D", [2, 3, 10, 100, 200, 500, 1000, 2000, 3000, 5000, 8192])
 def test_leapfrog_matches_oracle(pkg, po, D):
     rng = np.random.default_rng(D)
     K = 8
@@ -56,7 +56,7 @@ def test_leapfrog_matches_oracle(pkg, po, D):
         eng.close()
 
 
-@pytest.mark.parametrize("D,K", [(2, 64), (10, 96), (100, 48), (256, 16), (1000, 12), (2000, 6)])
+@pytest.mark.parametrize("D,K", [(2, 64), (10, 96), (100, 48), (256, 16), (1000, 12), (2000, 6), (3000, 4), (6000, 3)])
 def test_sample_tree_matches_oracle(pkg, po, D, K):
     rng = np.random.default_rng(1000 + D)
     for ℓ, fam, hasp in _models(pkg, rng, D):
@@ -369,7 +369,7 @@ def _spd(rng, D):
     return A @ A.T / D + np.diag(rng.uniform(0.5, 2.0, D))
 
 
-@pytest.mark.parametrize("D", [3, 10, 40, 100, 256, 400])
+@pytest.mark.parametrize("D", [3, 10, 40, 100, 256, 400, 700, 1100])
 def test_dense_metric_leapfrog_and_tree_match_oracle(pkg, po, D):
     """GaussianKineticEnergy(Symmetric M⁻¹) (hamiltonian.jl:73): W = cholesky(inv(M⁻¹)).L on
     device, p♯ = M⁻¹p mat-vec, rand_p = W·randn — against the oracle, bit for bit."""
@@ -410,6 +410,28 @@ def test_dense_metric_leapfrog_and_tree_match_oracle(pkg, po, D):
     assert not eng.metric_is_dense()
     eng.sample_tree()
     eng.close()
+
+
+def test_large_dims_full_warmup_matches_oracle(pkg, po):
+    """dim above 2048 (16 / 32 elements per thread) and a Symmetric metric above dim 512 through the whole default warm-up
+    (shortened) — bit-equal warm-up statistics, adapted metric, step size and draws."""
+    rng = np.random.default_rng(4242)
+    for D, M, code in ((2500, pkg.Diagonal, po.METRIC_DIAGONAL), (640, pkg.Symmetric, po.METRIC_SYMMETRIC)):
+        ℓ = pkg.DiagNormal(rng.normal(size=D), np.logspace(-0.5, 0.5, D))
+        K, N, seed = 4, 6, 31
+        kw = dict(init_steps=25, middle_steps=20, doubling_stages=1, terminating_steps=20)
+        r = pkg.mcmc_keep_warmup(seed, ℓ, N, chains=K, warmup_stages=pkg.default_warmup_stages(M=M, **kw))
+        T, _ = r["engine"].layout()
+        res = r["inference"]
+        for k in (0, K - 1):
+            o = po.mcmc_with_warmup(1, D, N, seed, k, stages=po.default_warmup_stages(M=code, **kw), params=ℓ.params(), T=T,
+                                    welford=True, keep_warmup=True)
+            w = np.concatenate([s["results"]["tree_statistics"][k] for s in r["warmup"] if s["results"]])
+            for f in INT_FIELDS:
+                assert np.array_equal(w[f], o["warmup_stats"][f]), (D, f)
+            assert np.array_equal(res[k]["κ"].minv, o["minv"]) and res[k]["ϵ"] == o["eps"]
+            assert np.array_equal(res[k]["posterior_matrix"].T, o["posterior_matrix"])
+        r["engine"].close()
 
 
 def test_dense_metric_not_positive_definite(pkg):
