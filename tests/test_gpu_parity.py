@@ -293,7 +293,7 @@ def test_error_conventions(pkg):
         eng.set_stepsize(-1.0)                         # stepsize.jl:135
     eng.close()
     with pytest.raises(pkg.ArgumentError):
-        pkg.Engine(pkg.StandardNormal(5000), chains=2)  # dim too large for this build
+        pkg.Engine(pkg.StandardNormal(9000), chains=2)  # dim too large for this build (dim <= 8192)
     # funnel with a huge step: divergent first leaf, chain stays put, others unaffected
     eng = _engine(pkg, pkg.Funnel(10), K)
     q = np.zeros((K, 10)); q[:, 0] = -8.0; q[:, 1:] = 5.0
