@@ -10,7 +10,7 @@ LIB_PATH = os.environ.get("DHMC_B200_LIB", os.path.join(_HERE, "csrc", "libdhmc_
 
 DHMC_OK, DHMC_EARG, DHMC_ENUMERIC, DHMC_ECUDA, DHMC_ENOMEM, DHMC_ENCCL = 0, 1, 2, 3, 4, 5
 COMM_ID_BYTES = 128
-FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL, FAMILY_LOGISTIC = 0, 1, 2, 3
+FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL, FAMILY_LOGISTIC, FAMILY_USER = 0, 1, 2, 3, 4
 METRIC_NOTHING, METRIC_DIAGONAL, METRIC_SYMMETRIC, METRIC_SYMMETRIC_POOLED = 0, 1, 2, 3
 
 tree_stats_dtype = np.dtype(
@@ -18,7 +18,7 @@ tree_stats_dtype = np.dtype(
      ("acceptance_rate", "<f8"), ("steps", "<i8"), ("directions", "<u4"), ("pad", "<u4")])
 
 EXPORTS = [
-    "dhmc_create", "dhmc_destroy", "dhmc_last_error", "dhmc_get_layout", "dhmc_set_problem",
+    "dhmc_create", "dhmc_destroy", "dhmc_last_error", "dhmc_get_layout", "dhmc_set_problem", "dhmc_user_family_name",
     "dhmc_set_position", "dhmc_random_position", "dhmc_set_metric", "dhmc_set_metric_dense",
     "dhmc_get_metric_dense", "dhmc_metric_is_dense", "dhmc_set_stepsize",
     "dhmc_set_momentum", "dhmc_get_state", "dhmc_chain_status", "dhmc_get_transition_count",
@@ -47,22 +47,24 @@ class MissingExtension(ImportError):
     pass
 
 
-_lib = None
+_libs = {}
 
 
-def lib():
-    """Load libdhmc_b200.so.  Fails loudly when the CUDA extension is missing:
-    there is no CPU fallback."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
+def lib(path=None):
+    """Load libdhmc_b200.so (or, with `path`, a user-model build of it: compile_user_model in api.py).  Fails loudly when
+    the CUDA extension is missing: there is no CPU fallback."""
+    path = os.path.abspath(path or LIB_PATH)
+    so = _libs.get(path)
+    if so is None:
+        if not os.path.exists(path):
             raise MissingExtension(
-                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; "
                 "g.build()'` (nvcc, sm_100a).  dynamichmc.jl_b200 has no CPU fallback.")
-        _lib = C.CDLL(LIB_PATH)
-        _lib.dhmc_last_error.restype = C.c_char_p
-        _lib.dhmc_last_error.argtypes = [C.c_void_p]
-    return _lib
+        so = C.CDLL(path)
+        so.dhmc_last_error.restype = C.c_char_p
+        so.dhmc_last_error.argtypes = [C.c_void_p]
+        _libs[path] = so
+    return so
 
 
 def ptr(a):

@@ -12,7 +12,10 @@ returns a `Results` whose `[k]` is the reference's NamedTuple for chain k
 (posterior_matrix [D, N], tree_statistics [N], logdensities [N], κ, ϵ).
 """
 import ctypes as C
+import hashlib
 import math
+import os
+import subprocess
 import unicodedata
 from dataclasses import dataclass, field
 from typing import Optional, Sequence
@@ -141,6 +144,70 @@ class LogisticRegression(DeviceLogDensity):
         return LogisticRegression(X, y), beta
 
 
+# ------------------------------------------------------------------ user models
+# The reference accepts ANY LogDensityProblems object; its only use of it is logdensity_and_gradient at hamiltonian.jl:204.
+# On the device the counterpart is a header of scalar formulas (include/dhmc_models.h, "the model header contract";
+# examples in include/models/) that is compiled — nvcc, sm_100a, same flags as the shipped families — into its own copy of
+# the library, where it is family DHMC_FAMILY_USER.
+_CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
+
+
+def compile_user_model(header, out_dir=None, force=False, jobs=2):
+    """Build (or reuse) the library that carries the model in `header` as family FAMILY_USER; returns its path.
+
+    The build is keyed by the header's content and the library sources' modification times, lives under
+    csrc/user_models/<name>-<hash>/ (in-tree, so that it travels with the package) unless `out_dir` is given, and needs nvcc
+    plus the object files of the stock library (`__graft_entry__.build()`); it takes a few minutes of CPU time."""
+    header = os.path.abspath(header)
+    if not os.path.exists(header):
+        raise ArgumentError(f"user model header {header} does not exist")
+    name = os.path.splitext(os.path.basename(header))[0]
+    srcs = [os.path.join(_CSRC, f) for f in ("family_tu.cu", "kernels.cuh", "device_backend.cuh", "nuts_machine.cuh",
+                                            "dhmc_b200.cu")]
+    srcs += [os.path.join(_CSRC, "..", "..", "include", f) for f in ("dhmc.h", "dhmc_math.h", "dhmc_models.h", "dhmc_tables.h")]
+    hsh = hashlib.sha256(open(header, "rb").read())
+    for f in srcs:
+        hsh.update(open(f, "rb").read())
+    tag = f"{name}-{hsh.hexdigest()[:12]}"
+    out_dir = os.path.abspath(out_dir or os.path.join(_CSRC, "user_models", tag))
+    so = os.path.join(out_dir, f"libdhmc_user_{name}.so")
+    if force or not os.path.exists(so):
+        os.makedirs(out_dir, exist_ok=True)
+        cmd = ["make", "-C", _CSRC, f"-j{jobs}", "user", f"USER_HEADER={header}", f"USER_LIB={so}",
+               f"USER_BUILD={os.path.join(out_dir, 'build')}"]
+        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0 or not os.path.exists(so):
+            raise RuntimeError(f"user model build failed ({' '.join(cmd)}):\n{r.stdout[-4000:]}")
+    return so
+
+
+class UserLogDensity(DeviceLogDensity):
+    """ℓ given as a model header (the device-side LogDensityProblems object).  `params` is the block of doubles the
+    header's formulas receive; `cpu` optionally is a callable q ↦ (ℓ(q), ∇ℓ(q)) so that the object also answers
+    logdensity_and_gradient on the host (like the shipped families' numpy forms).  `library` may name a prebuilt library."""
+    family = L.FAMILY_USER
+
+    def __init__(self, header, D, params=(), cpu=None, library=None):
+        self.header, self.D = os.path.abspath(header), int(D)
+        self._params = np.ascontiguousarray(params, float).ravel()
+        self._cpu = cpu
+        self.library_path = library or compile_user_model(self.header)
+
+    def params(self):
+        return self._params
+
+    def model_name(self):
+        buf = C.create_string_buffer(128)
+        rc = L.lib(self.library_path).dhmc_user_family_name(buf, C.c_size_t(128))
+        _argcheck(rc == L.DHMC_OK, f"{self.library_path} carries no user model")
+        return buf.value.decode()
+
+    def logdensity_and_gradient(self, q):
+        if self._cpu is None:
+            raise NotImplementedError("this UserLogDensity was created without a host-side `cpu` callable")
+        return self._cpu(np.asarray(q, float))
+
+
 # ------------------------------------------------------------------ algorithm structs
 @dataclass
 class NUTS:
@@ -246,7 +313,7 @@ class Engine:
         algorithm = algorithm or NUTS()
         _argcheck(ℓ.capabilities() >= 1, "capabilities(ℓ) ≥ LogDensityOrder(1)")   # hamiltonian.jl:146
         self.ℓ, self.K, self.D, self.algorithm = ℓ, int(chains), int(ℓ.dimension()), algorithm
-        self._lib = L.lib()
+        self._lib = L.lib(getattr(ℓ, "library_path", None))     # a user model lives in its own build of the library
         cfg = L.Config(device=device, family=ℓ.family, dim=self.D, n_chains=self.K,
                        chain_offset=chain_offset, seed=seed, max_depth=algorithm.max_depth,
                        threads_per_chain=threads_per_chain, min_delta=algorithm.min_Δ,

@@ -1189,6 +1189,70 @@ struct DeviceBackend {
     }
   }
 
+#ifdef DHMC_HAVE_USER_FAMILY
+  // USER family (include/dhmc_models.h, "the model header contract"): the chain's whole position is staged in shared
+  // memory so that an element's formulas may look at any other element, the K sums run through the canonical
+  // reduction, then every thread evaluates the gradient of its own elements.  Same flag / sanitising conventions as the
+  // shipped families below.
+  __device__ __forceinline__ void eval_user(bool with_p, double h, double qbad_in, double* ksum, int* flags) {
+    constexpr int K = DHMC_USER_NSUMS, M = DHMC_USER_NSCALARS;
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) xs[tid + e * T] = q[e];
+    group_sync();
+    double r1[K + 1];
+#pragma unroll
+    for (int k = 0; k < K; ++k) r1[k] = 0.0;
+    r1[K] = qbad_in;
+#if DHMC_USER_NSUMS > 0
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int i = tid + e * T;
+      if (i < D) {
+        double t[K];
+        dhmc_user_terms(i, D, xs, mparams, t);
+#pragma unroll
+        for (int k = 0; k < K; ++k) r1[k] = r1[k] + t[k];
+      }
+    }
+#endif
+    reduce(r1);
+    double S[K + M > 0 ? K + M : 1];
+    S[0] = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) S[k] = r1[k];
+#if DHMC_USER_NSCALARS > 0
+    dhmc_user_prepare(D, xs, S, mparams);
+#endif
+    double r2[2] = {0.0, 0.0};                     // Σ p·p♯, bad ∇ℓ
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int i = tid + e * T;
+      double ge = 0.0;
+      if (i < D) {
+        ge = dhmc_user_grad(i, D, xs, S, mparams);
+        if (!dm_isfinite(ge)) r2[1] = 1.0;
+      }
+      g[e] = ge;
+      if (with_p) {
+        p[e] = p[e] + h * ge;
+        if constexpr (!DENSE) {
+          double psv = minv[e] * p[e];
+          r2[0] = r2[0] + p[e] * psv;
+        }
+      }
+    }
+    double l = dhmc_user_logdensity(D, xs, S, mparams);
+    reduce(r2);
+    if (!((dm_isfinite(l) && r2[1] == 0.0) || l == -dm_inf())) *flags |= 4;
+    l = sanitise(l, r2[1] != 0.0);
+    if (r1[K] != 0.0) { *flags |= 1; l = -dm_inf(); }
+    if (r2[1] != 0.0) *flags |= 2;
+    lq = l;
+    *ksum = r2[0];
+    group_sync();                                  // the staging vector is rewritten by the next evaluation / mat-vec
+  }
+#endif
+
   // Model evaluation at the current q: fills g, sets lq (sanitised).  If
   // `with_p`, also performs the second momentum half-step p += h·∇ℓ(q′) and
   // returns Σ p·(M⁻¹p) through *ksum (fused into the same reductions).
@@ -1299,6 +1363,10 @@ struct DeviceBackend {
       if (r[3] != 0.0) *flags |= 2;
       lq = l;
       *ksum = r[4];
+#ifdef DHMC_HAVE_USER_FAMILY
+    } else if constexpr (FAM == DHMC_FAMILY_USER) {
+      eval_user(with_p, h, qbad_in, ksum, flags);
+#endif
     } else if (FAM == DHMC_FAMILY_FUNNEL) {
       double r1[3] = {0.0, 0.0, qbad_in};
 #pragma unroll

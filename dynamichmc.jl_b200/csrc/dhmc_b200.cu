@@ -41,6 +41,14 @@ using namespace dhmc;
 DHMC_DECL_TU(0, 0) DHMC_DECL_TU(1, 0) DHMC_DECL_TU(2, 0) DHMC_DECL_TU(3, 0) DHMC_DECL_TU(3, 1) DHMC_DECL_TU(3, 2)
 DHMC_DECL_TU(0, 3) DHMC_DECL_TU(1, 3) DHMC_DECL_TU(2, 3) DHMC_DECL_TU(3, 3)
 #undef DHMC_DECL_TU
+// USER family (include/dhmc_models.h): its two translation units exist only in a library built from a user model header
+// (`make user USER_HEADER=…`), hence weak references — in the stock library they are null and family 4 is refused.
+extern "C" {
+const void* dhmc_user_family_kernel_0(int W, int epl, int kernel, int dense) __attribute__((weak));
+const void* dhmc_user_family_kernel_3(int W, int epl, int kernel, int dense) __attribute__((weak));
+const char* dhmc_user_family_name_str(void) __attribute__((weak));
+int dhmc_user_family_min_dim(void) __attribute__((weak));
+}
 // part: 0 = one chain per CTA, 1 = packed chain groups with the FMA likelihood, 2 = packed groups on the tensor cores,
 // 3 = one chain per CTA with max_depth > 12 (persistent kernels only)
 static const void* lookup_kernel(int fam, int part, int W, int epl, KernelId k, bool dense) {
@@ -55,6 +63,8 @@ static const void* lookup_kernel(int fam, int part, int W, int epl, KernelId k, 
     case 7: return dhmc_family_kernel_1_3(W, epl, k, dense);
     case 11: return dhmc_family_kernel_2_3(W, epl, k, dense);
     case 15: return dhmc_family_kernel_3_3(W, epl, k, dense);
+    case 16: return dhmc_user_family_kernel_0 ? dhmc_user_family_kernel_0(W, epl, k, dense) : nullptr;
+    case 19: return dhmc_user_family_kernel_3 ? dhmc_user_family_kernel_3(W, epl, k, dense) : nullptr;
   }
   return nullptr;
 }
@@ -352,6 +362,10 @@ static std::string g_create_err;
   } while (0)
 
 static void set_l2_window(dhmc_handle* h, const void* ptr, size_t bytes);
+// a per-chain staging vector in shared memory: mat-vec input (Symmetric metric), β (logistic), the whole position (USER)
+static bool needs_staging(const dhmc_handle* h) {
+  return h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC || h->cfg.family == DHMC_FAMILY_USER;
+}
 static int kernel_part(const dhmc_handle* h, KernelId k, int G);
 
 // rows of N doubles in the logistic scratch: one per CTA of the light kernels, 2·G per CTA
@@ -367,7 +381,7 @@ static int plan(dhmc_handle* h) {
   const size_t B = (size_t)h->cfg.n_chains;
   const size_t slot_doubles = h->stride * (h->dense ? 2 : 1);
   const size_t slot_bytes = sizeof(double) * slot_doubles;
-  const size_t xs = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? h->stride : 0;
+  const size_t xs = needs_staging(h) ? h->stride : 0;
   const int G = h->G;
   auto heavy_smem = [&](int n_sm) -> size_t {
     return G > 1 ? (size_t)G * group_smem_bytes(h->W, n_sm, slot_doubles, xs, h->levels, h->ntab) + coop_smem_bytes(G, h->coop_mma, (int)h->cfg.dim)
@@ -453,7 +467,7 @@ static KArgs base_args(dhmc_handle* h) {
   a.counter = h->counter; a.total_steps = h->total_steps;
   a.chain_begin = 0; a.chain_end = (int)h->cfg.n_chains;
   a.minv_dense = h->minv_dense; a.wt = h->wt; a.covt = nullptr; a.minv_pad = h->minv_pad; a.mean_out = nullptr; a.pooled = h->pooled ? 1 : 0;
-  a.xs_doubles = (h->minv_dense || h->cfg.family == DHMC_FAMILY_LOGISTIC) ? (int)((size_t)h->T * h->EPL) : 0;
+  a.xs_doubles = needs_staging(h) ? (int)((size_t)h->T * h->EPL) : 0;
   a.lX = h->lX; a.lXt = h->lXt; a.ly = h->ly; a.lr = h->lr; a.lN = h->lN; a.lLd = h->lLd; a.lXp = h->lXp;
   return a;
 }
@@ -606,6 +620,10 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   if (cfg->dim < 1 || cfg->n_chains < 1 || cfg->n_chains > (1ll << 30)) { g_create_err = "dim >= 1, 1 <= n_chains <= 2^30"; return DHMC_EARG; }
   if (cfg->family < 0 || cfg->family >= DHMC_FAMILY_COUNT) { g_create_err = "unknown family"; return DHMC_EARG; }
   if (cfg->family == DHMC_FAMILY_FUNNEL && cfg->dim < 2) { g_create_err = "funnel needs dim >= 2"; return DHMC_EARG; }
+  if (cfg->family == DHMC_FAMILY_USER) {
+    if (!dhmc_user_family_kernel_0) { g_create_err = "this library was built without a user model (make user USER_HEADER=…; api.compile_user_model)"; return DHMC_EARG; }
+    if (dhmc_user_family_min_dim && cfg->dim < dhmc_user_family_min_dim()) { g_create_err = "dim below the user model's DHMC_USER_MIN_DIM"; return DHMC_EARG; }
+  }
   int T = 0, EPL = 0;
   const int rt = cfg->threads_per_chain;
   if (rt != 0 && !(rt == 32 || rt == 64 || rt == 128 || rt == 256)) { g_create_err = "threads_per_chain in {0,32,64,128,256}"; return DHMC_EARG; }
@@ -708,6 +726,13 @@ int dhmc_get_layout(dhmc_handle* h, int32_t* T, int32_t* epl) {
   return DHMC_OK;
 }
 
+int dhmc_user_family_name(char* name, size_t cap) {
+  if (!dhmc_user_family_name_str || !name || cap == 0) return DHMC_EARG;
+  std::strncpy(name, dhmc_user_family_name_str(), cap - 1);
+  name[cap - 1] = 0;
+  return DHMC_OK;
+}
+
 int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n) {
   if (!h) return DHMC_EARG;
   CK(cudaSetDevice(h->cfg.device));
@@ -741,6 +766,15 @@ int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n) {
       set_l2_window(h, h->lXp, sizeof(double) * rows * xs);
     }
     h->lN = (int)N; h->lLd = (int)ld;
+    CK(cudaStreamSynchronize(h->stream));
+    return DHMC_OK;
+  }
+  if (h->cfg.family == DHMC_FAMILY_USER) {      // any number of doubles, interpreted by the user's formulas
+    if (n && !params) { h->err = "dhmc_set_problem: null parameter block"; return DHMC_EARG; }
+    CK(cudaStreamSynchronize(h->stream));
+    cudaFree(h->mparams); h->mparams = nullptr;
+    CK(cudaMalloc(&h->mparams, sizeof(double) * std::max<size_t>(n, 1)));
+    if (n) CK(cudaMemcpyAsync(h->mparams, params, sizeof(double) * n, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return DHMC_OK;
   }

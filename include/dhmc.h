@@ -68,7 +68,7 @@ typedef struct {
   int64_t n_chains;          /* chains resident on this handle (local shard) */
   int64_t chain_offset;      /* global id of local chain 0 (RNG key), §8e */
   uint64_t seed;             /* RNG seed (stands in for the rng argument) */
-  int32_t max_depth;         /* NUTS.max_depth, 0 < . <= 12 in this build */
+  int32_t max_depth;         /* NUTS.max_depth, 0 < . <= 32 (MAX_DIRECTIONS_DEPTH, trees.jl:10) */
   int32_t threads_per_chain; /* 0 = auto; 32..256, power of two.  LOGISTIC, dim <= 256: auto also packs 8 chains
                               * per CTA (shared passes over X, same results); an explicit value keeps one chain per CTA */
   double min_delta;          /* NUTS.min_Δ < 0 */
@@ -100,8 +100,14 @@ const char* dhmc_last_error(dhmc_handle* h);
 int dhmc_get_layout(dhmc_handle* h, int32_t* threads_per_chain, int32_t* elems_per_thread);
 
 /* ---- problem: replaces the ℓ argument (LogDensityProblems object) ------ */
-/* params: DIAG_NORMAL [mu(D), prec(D)]; LOGISTIC [N, X row-major (N*D), y (N)]; STD_NORMAL / FUNNEL: n == 0. */
+/* params: DIAG_NORMAL [mu(D), prec(D)]; LOGISTIC [N, X row-major (N*D), y (N)]; STD_NORMAL / FUNNEL: n == 0;
+ * USER: any block of doubles, handed to the user's formulas as `params`. */
 int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n);
+/* The user's own ℓ (LogDensityProblems.logdensity_and_gradient, call site hamiltonian.jl:204) as device code: a library
+ * built from a model header (include/dhmc_models.h "the model header contract"; `make -C dynamichmc.jl_b200/csrc user
+ * USER_HEADER=… USER_LIB=…`) carries family DHMC_FAMILY_USER next to the shipped ones.  Copies the model's DHMC_USER_NAME
+ * (NUL-terminated, truncated to cap) and returns DHMC_OK, or DHMC_EARG in a library without a user model. */
+int dhmc_user_family_name(char* name, size_t cap);
 
 /* ---- state: initialization = (q, κ, ϵ), mcmc.jl:111-132 ---------------- */
 /* q: [D,B]; evaluates ℓ, ∇ℓ strictly (initialize_warmup_state, mcmc.jl:129-132). */

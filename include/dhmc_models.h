@@ -17,6 +17,10 @@
  *               grad = X' (y - sigma(eta)) - beta      (ll term and sigma share one exponential: dhmc_logit_ll_resid)
  *               params = [N, X row-major (N*p), y (N)];  (X' r)_j is a sequential chain of fused multiply-adds
  *               over n, eta_n a blocked one over j (dhmc_logit_eta), the two scalar sums use the canonical reduction.
+ *   USER        a log density supplied by the USER as a header of scalar formulas, compiled into its own copy of the
+ *               library (`make -C dynamichmc.jl_b200/csrc user USER_HEADER=…`, `compile_user_model` in api.py): the
+ *               device counterpart of handing DynamicHMC an arbitrary LogDensityProblems object (hamiltonian.jl:204).
+ *               Contract at the end of this file; examples under include/models/.
  */
 #ifndef DHMC_MODELS_H
 #define DHMC_MODELS_H
@@ -27,7 +31,8 @@ enum {
   DHMC_FAMILY_DIAG_NORMAL = 1,
   DHMC_FAMILY_FUNNEL = 2,
   DHMC_FAMILY_LOGISTIC = 3,
-  DHMC_FAMILY_COUNT = 4
+  DHMC_FAMILY_USER = 4,      /* present only in a library built with -DDHMC_USER_MODEL_HEADER=… */
+  DHMC_FAMILY_COUNT = 5
 };
 
 /* --- STD_NORMAL: term of the sum and gradient element */
@@ -92,5 +97,46 @@ DHMC_HD double dhmc_logit_ll(double y, double eta) { double l, r; dhmc_logit_ll_
 DHMC_HD double dhmc_logit_resid(double y, double eta) { double l, r; dhmc_logit_ll_resid(y, eta, &l, &r); return r; }
 DHMC_HD double dhmc_logit_lq(double sum_ll, double sum_b2) { return sum_ll - 0.5 * sum_b2; }
 DHMC_HD double dhmc_logit_grad(double xtr, double beta) { return xtr - beta; }
+
+/* --- USER: the model header contract ------------------------------------------------------------------------------
+ * A user model is ONE header that defines, with DHMC_HD (host + device, so that the CPU oracle checks the same
+ * formulas), a log density of the form "element-wise gradient with the whole position visible, plus up to 4 global
+ * sums" — the class that needs no data-parallel pass of its own (separable, neighbour-coupled / banded, hierarchical
+ * models; regression likelihoods over large data sets are what the LOGISTIC family's cooperative rounds are for):
+ *
+ *   #define DHMC_USER_NAME     "my_model"   // reported by dhmc_user_family_name
+ *   #define DHMC_USER_NSUMS    K            // 0 <= K <= 4 cross-element sums S[0..K-1]
+ *   #define DHMC_USER_NSCALARS M            // 0 <= M <= 4 derived scalars  S[K..K+M-1]   (optional, default 0)
+ *   #define DHMC_USER_MIN_DIM  d            // smallest valid dimension                   (optional, default 1)
+ *   // contribution of element i to the K sums (t[0..K-1]); q is the WHOLE position vector (read-only)
+ *   DHMC_HD void   dhmc_user_terms(int i, int D, const double* q, const double* params, double* t);
+ *   // scalars every element needs (e.g. exp(-q[0])), computed once per thread after the sums; writes S[K..K+M-1]
+ *   DHMC_HD void   dhmc_user_prepare(int D, const double* q, double* S, const double* params);   // only if M > 0
+ *   DHMC_HD double dhmc_user_logdensity(int D, const double* q, const double* S, const double* params);
+ *   DHMC_HD double dhmc_user_grad(int i, int D, const double* q, const double* S, const double* params);
+ *
+ * `params` is the block of doubles handed to dhmc_set_problem (any length).  The sums are taken in the canonical
+ * order; transcendental functions should come from dhmc_math.h (dm_exp, dm_log, dm_log1p, …) if the
+ * device results are to equal the oracle's bit for bit — libm / libdevice calls work, but differ in the last ulp.
+ * -Inf / non-finite values are handled by the sampler exactly as for the shipped families (hamiltonian.jl:202-217). */
+#ifdef DHMC_USER_MODEL_HEADER
+#include DHMC_USER_MODEL_HEADER
+#ifndef DHMC_USER_NSUMS
+#error "user model header: define DHMC_USER_NSUMS (0..4)"
+#endif
+#ifndef DHMC_USER_NSCALARS
+#define DHMC_USER_NSCALARS 0
+#endif
+#ifndef DHMC_USER_MIN_DIM
+#define DHMC_USER_MIN_DIM 1
+#endif
+#ifndef DHMC_USER_NAME
+#define DHMC_USER_NAME "user"
+#endif
+#if DHMC_USER_NSUMS < 0 || DHMC_USER_NSUMS > 4 || DHMC_USER_NSCALARS < 0 || DHMC_USER_NSCALARS > 4
+#error "user model header: 0 <= DHMC_USER_NSUMS <= 4 and 0 <= DHMC_USER_NSCALARS <= 4"
+#endif
+#define DHMC_HAVE_USER_FAMILY 1
+#endif
 
 #endif

@@ -136,6 +136,25 @@ struct Model {
         }
         return dhmc_logit_lq(sll, sb);
       }
+#ifdef DHMC_HAVE_USER_FAMILY
+      case DHMC_FAMILY_USER: {
+        // a user model header (include/dhmc_models.h "the model header contract"): K canonical sums over the elements,
+        // derived scalars, then ℓ and the element-wise gradient — what eval_user does on the device
+        constexpr int K = DHMC_USER_NSUMS, M = DHMC_USER_NSCALARS;
+        double S[K + M > 0 ? K + M : 1] = {0.0};
+        const double* qp = q.data();
+        const double* pr = params.data();
+#if DHMC_USER_NSUMS > 0
+        for (int k = 0; k < K; ++k)
+          S[k] = canon_sum(T, D, [&](int i) { double t[K]; dhmc_user_terms(i, D, qp, pr, t); return t[k]; });
+#endif
+#if DHMC_USER_NSCALARS > 0
+        dhmc_user_prepare(D, qp, S, pr);
+#endif
+        for (int i = 0; i < D; ++i) g[i] = dhmc_user_grad(i, D, qp, S, pr);
+        return dhmc_user_logdensity(D, qp, S, pr);
+      }
+#endif
     }
     throw ArgumentError("unknown family");
   }

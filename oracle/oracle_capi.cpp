@@ -27,8 +27,10 @@ Model make_model(int family, int D, const double* params, int nparams, int T, in
   return m;
 }
 thread_local int g_logistic_n = 0;   // N of the logistic-regression family (set by orc_set_logistic_n)
+thread_local int g_user_nparams = 0;  // length of the USER family's parameter block (set by orc_set_user_nparams)
 int nparams_of(int family, int D) {
   if (family == DHMC_FAMILY_LOGISTIC) return 1 + g_logistic_n * D + g_logistic_n;
+  if (family == DHMC_FAMILY_USER) return g_user_nparams;
   return family == DHMC_FAMILY_DIAG_NORMAL ? 2 * D : 0;
 }
 template <class F>
@@ -45,6 +47,15 @@ extern "C" {
 const char* orc_last_error() { return g_err.c_str(); }
 void orc_set_dense(int flag) { g_dense = flag; }
 void orc_set_logistic_n(int n) { g_logistic_n = n; }
+void orc_set_user_nparams(int n) { g_user_nparams = n; }
+// name of the user model compiled into this oracle library ("" in the stock liboracle.so)
+const char* orc_user_family_name() {
+#ifdef DHMC_HAVE_USER_FAMILY
+  return DHMC_USER_NAME;
+#else
+  return "";
+#endif
+}
 // W = cholesky(inv(M⁻¹)).L; returns 0 ok, 2 not positive definite
 int orc_dense_factor(int D, const double* minv, double* W) {
   vec w;

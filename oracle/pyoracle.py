@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL, FAMILY_LOGISTIC = 0, 1, 2, 3
+FAMILY_STD_NORMAL, FAMILY_DIAG_NORMAL, FAMILY_FUNNEL, FAMILY_LOGISTIC, FAMILY_USER = 0, 1, 2, 3, 4
 STAGE_NOTHING, STAGE_SEARCH, STAGE_TUNING = 0, 1, 2
 METRIC_NOTHING, METRIC_DIAGONAL, METRIC_SYMMETRIC = 0, 1, 2
 
@@ -53,20 +53,63 @@ def build(force=False):
     return so
 
 
+def _load(path):
+    so = C.CDLL(path)
+    so.orc_last_error.restype = C.c_char_p
+    so.orc_user_family_name.restype = C.c_char_p
+    so.orc_randexp.restype = C.c_double
+    so.orc_directions.restype = C.c_uint32
+    so.orc_canon_dot.restype = C.c_double
+    so.orc_logdensity_and_gradient.restype = C.c_double
+    so.orc_kinetic_energy.restype = C.c_double
+    so.orc_phase_logdensity.restype = C.c_double
+    so.orc_acceptance_rate.restype = C.c_double
+    so.orc_local_log_acceptance_ratio.restype = C.c_double
+    return so
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
-        _LIB.orc_last_error.restype = C.c_char_p
-        _LIB.orc_randexp.restype = C.c_double
-        _LIB.orc_directions.restype = C.c_uint32
-        _LIB.orc_canon_dot.restype = C.c_double
-        _LIB.orc_logdensity_and_gradient.restype = C.c_double
-        _LIB.orc_kinetic_energy.restype = C.c_double
-        _LIB.orc_phase_logdensity.restype = C.c_double
-        _LIB.orc_acceptance_rate.restype = C.c_double
-        _LIB.orc_local_log_acceptance_ratio.restype = C.c_double
+        _LIB = _load(build())
     return _LIB
+
+
+def build_user(header, force=False):
+    """liboracle with the user model `header` compiled in as family 4 (oracle/Makefile `user`): the checker of a
+    user-model library.  Built under oracle/_user/ (git-ignored); returns the path."""
+    header = os.path.abspath(header)
+    name = os.path.splitext(os.path.basename(header))[0]
+    out_dir = os.path.join(_HERE, "_user")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, f"liboracle_user_{name}.so")
+    srcs = [header] + [os.path.join(_HERE, f) for f in ("oracle_capi.cpp", "oracle.hpp")] + [
+        os.path.join(_HERE, "..", "include", f) for f in ("dhmc_math.h", "dhmc_models.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "user", f"USER_HEADER={header}", f"USER_LIB={so}"],
+                              stdout=subprocess.DEVNULL)
+    return so
+
+
+class user_model:
+    """`with pyoracle.user_model(header): …` — every oracle call inside the block goes to the oracle library that has the
+    user model compiled in (family FAMILY_USER; the shipped families are there too)."""
+    _cache = {}
+
+    def __init__(self, header):
+        self.path = build_user(header)
+
+    def __enter__(self):
+        global _LIB
+        self.prev = _LIB
+        if self.path not in user_model._cache:
+            user_model._cache[self.path] = _load(self.path)
+        _LIB = user_model._cache[self.path]
+        return _LIB
+
+    def __exit__(self, *exc):
+        global _LIB
+        _LIB = self.prev
 
 
 def _check(status):
@@ -137,6 +180,10 @@ def _params(family, D, params):
         assert params.size == 1 + N * D + N
         lib().orc_set_logistic_n(C.c_int(N))
         return params
+    if family == FAMILY_USER:
+        params = _d(params if params is not None else np.zeros(0))
+        lib().orc_set_user_nparams(C.c_int(params.size))
+        return params if params.size else np.zeros(1)
     return np.zeros(1)
 
 
