@@ -19,6 +19,7 @@ tree_stats_dtype = np.dtype(
 
 EXPORTS = [
     "dhmc_create", "dhmc_destroy", "dhmc_last_error", "dhmc_get_layout", "dhmc_set_problem", "dhmc_user_family_name",
+    "dhmc_family_available",
     "dhmc_set_position", "dhmc_random_position", "dhmc_set_metric", "dhmc_set_metric_dense",
     "dhmc_get_metric_dense", "dhmc_metric_is_dense", "dhmc_set_stepsize",
     "dhmc_set_momentum", "dhmc_get_state", "dhmc_chain_status", "dhmc_get_transition_count",

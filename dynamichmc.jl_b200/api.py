@@ -178,6 +178,9 @@ def compile_user_model(header, out_dir=None, force=False, jobs=2):
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0 or not os.path.exists(so):
             raise RuntimeError(f"user model build failed ({' '.join(cmd)}):\n{r.stdout[-4000:]}")
+        for f in os.listdir(os.path.join(out_dir, "build")):       # keep the ptxas logs, drop the objects (they are in the .so)
+            if f.endswith(".o"):
+                os.remove(os.path.join(out_dir, "build", f))
     return so
 
 

@@ -36,37 +36,44 @@
 
 using namespace dhmc;
 
-// kernel lookup, one function per (family, part) translation unit (family_tu.cu)
-#define DHMC_DECL_TU(f, p) const void* dhmc_family_kernel_##f##_##p(int W, int epl, int kernel, int dense);
+// kernel lookup, one function per (family, part) translation unit (family_tu.cu).  The references are WEAK: the stock
+// library links every shipped family, a user-model library (`make user`, include/dhmc_models.h) links the USER family's two
+// units only, and a family whose units are absent is refused by dhmc_create ("family not built into this library").
+// (hidden: never bound across two copies of the library loaded into one process)
+#define DHMC_TU_LINKAGE __attribute__((weak, visibility("hidden")))
+#define DHMC_DECL_TU(f, p) const void* dhmc_family_kernel_##f##_##p(int W, int epl, int kernel, int dense) DHMC_TU_LINKAGE;
 DHMC_DECL_TU(0, 0) DHMC_DECL_TU(1, 0) DHMC_DECL_TU(2, 0) DHMC_DECL_TU(3, 0) DHMC_DECL_TU(3, 1) DHMC_DECL_TU(3, 2)
 DHMC_DECL_TU(0, 3) DHMC_DECL_TU(1, 3) DHMC_DECL_TU(2, 3) DHMC_DECL_TU(3, 3)
 #undef DHMC_DECL_TU
-// USER family (include/dhmc_models.h): its two translation units exist only in a library built from a user model header
-// (`make user USER_HEADER=…`), hence weak references — in the stock library they are null and family 4 is refused.
 extern "C" {
-const void* dhmc_user_family_kernel_0(int W, int epl, int kernel, int dense) __attribute__((weak));
-const void* dhmc_user_family_kernel_3(int W, int epl, int kernel, int dense) __attribute__((weak));
-const char* dhmc_user_family_name_str(void) __attribute__((weak));
-int dhmc_user_family_min_dim(void) __attribute__((weak));
+const void* dhmc_user_family_kernel_0(int W, int epl, int kernel, int dense) DHMC_TU_LINKAGE;
+const void* dhmc_user_family_kernel_3(int W, int epl, int kernel, int dense) DHMC_TU_LINKAGE;
+const char* dhmc_user_family_name_str(void) DHMC_TU_LINKAGE;
+int dhmc_user_family_min_dim(void) DHMC_TU_LINKAGE;
 }
 // part: 0 = one chain per CTA, 1 = packed chain groups with the FMA likelihood, 2 = packed groups on the tensor cores,
 // 3 = one chain per CTA with max_depth > 12 (persistent kernels only)
-static const void* lookup_kernel(int fam, int part, int W, int epl, KernelId k, bool dense) {
+typedef const void* (*family_tu_fn)(int, int, int, int);
+static family_tu_fn family_tu(int fam, int part) {
   switch (fam * 4 + part) {
-    case 0: return dhmc_family_kernel_0_0(W, epl, k, dense);
-    case 4: return dhmc_family_kernel_1_0(W, epl, k, dense);
-    case 8: return dhmc_family_kernel_2_0(W, epl, k, dense);
-    case 12: return dhmc_family_kernel_3_0(W, epl, k, dense);
-    case 13: return dhmc_family_kernel_3_1(W, epl, k, dense);
-    case 14: return dhmc_family_kernel_3_2(W, epl, k, dense);
-    case 3: return dhmc_family_kernel_0_3(W, epl, k, dense);
-    case 7: return dhmc_family_kernel_1_3(W, epl, k, dense);
-    case 11: return dhmc_family_kernel_2_3(W, epl, k, dense);
-    case 15: return dhmc_family_kernel_3_3(W, epl, k, dense);
-    case 16: return dhmc_user_family_kernel_0 ? dhmc_user_family_kernel_0(W, epl, k, dense) : nullptr;
-    case 19: return dhmc_user_family_kernel_3 ? dhmc_user_family_kernel_3(W, epl, k, dense) : nullptr;
+    case 0: return dhmc_family_kernel_0_0;
+    case 4: return dhmc_family_kernel_1_0;
+    case 8: return dhmc_family_kernel_2_0;
+    case 12: return dhmc_family_kernel_3_0;
+    case 13: return dhmc_family_kernel_3_1;
+    case 14: return dhmc_family_kernel_3_2;
+    case 3: return dhmc_family_kernel_0_3;
+    case 7: return dhmc_family_kernel_1_3;
+    case 11: return dhmc_family_kernel_2_3;
+    case 15: return dhmc_family_kernel_3_3;
+    case 16: return dhmc_user_family_kernel_0;
+    case 19: return dhmc_user_family_kernel_3;
   }
   return nullptr;
+}
+static const void* lookup_kernel(int fam, int part, int W, int epl, KernelId k, bool dense) {
+  const family_tu_fn f = family_tu(fam, part);
+  return f ? f(W, epl, k, dense) : nullptr;
 }
 
 // ------------------------------------------------------------------ Symmetric metric
@@ -620,9 +627,14 @@ int dhmc_create(const dhmc_config* cfg, dhmc_handle** out) {
   if (cfg->dim < 1 || cfg->n_chains < 1 || cfg->n_chains > (1ll << 30)) { g_create_err = "dim >= 1, 1 <= n_chains <= 2^30"; return DHMC_EARG; }
   if (cfg->family < 0 || cfg->family >= DHMC_FAMILY_COUNT) { g_create_err = "unknown family"; return DHMC_EARG; }
   if (cfg->family == DHMC_FAMILY_FUNNEL && cfg->dim < 2) { g_create_err = "funnel needs dim >= 2"; return DHMC_EARG; }
-  if (cfg->family == DHMC_FAMILY_USER) {
-    if (!dhmc_user_family_kernel_0) { g_create_err = "this library was built without a user model (make user USER_HEADER=…; api.compile_user_model)"; return DHMC_EARG; }
-    if (dhmc_user_family_min_dim && cfg->dim < dhmc_user_family_min_dim()) { g_create_err = "dim below the user model's DHMC_USER_MIN_DIM"; return DHMC_EARG; }
+  if (cfg->family == DHMC_FAMILY_USER && !family_tu(DHMC_FAMILY_USER, 0)) {
+    g_create_err = "this library was built without a user model (make user USER_HEADER=…; api.compile_user_model)";
+    return DHMC_EARG;
+  }
+  if (!family_tu(cfg->family, 0)) { g_create_err = "family not built into this library (a user-model library carries the USER family only)"; return DHMC_EARG; }
+  if (cfg->family == DHMC_FAMILY_USER && dhmc_user_family_min_dim && cfg->dim < dhmc_user_family_min_dim()) {
+    g_create_err = "dim below the user model's DHMC_USER_MIN_DIM";
+    return DHMC_EARG;
   }
   int T = 0, EPL = 0;
   const int rt = cfg->threads_per_chain;
@@ -723,6 +735,12 @@ int dhmc_get_layout(dhmc_handle* h, int32_t* T, int32_t* epl) {
   if (!h) return DHMC_EARG;
   if (T) *T = h->T;
   if (epl) *epl = h->EPL;
+  return DHMC_OK;
+}
+
+int dhmc_family_available(int32_t family, int32_t* available) {
+  if (!available) return DHMC_EARG;
+  *available = (family >= 0 && family < DHMC_FAMILY_COUNT && family_tu(family, 0)) ? 1 : 0;
   return DHMC_OK;
 }
 

@@ -9,7 +9,7 @@
 #define DHMC_CAT3(a, b, c) a##b##_##c
 #define DHMC_TU_NAME(f, p) DHMC_CAT3(dhmc_family_kernel_, f, p)
 
-const void* DHMC_TU_NAME(DHMC_TU_FAM, DHMC_TU_PART)(int W, int epl, int kernel, int dense) {
+__attribute__((visibility("hidden"))) const void* DHMC_TU_NAME(DHMC_TU_FAM, DHMC_TU_PART)(int W, int epl, int kernel, int dense) {
   return dhmc::family_kernel_ptr<DHMC_TU_FAM, DHMC_TU_PART>(W, epl, (dhmc::KernelId)kernel, dense != 0);
 }
 
@@ -20,13 +20,13 @@ const void* DHMC_TU_NAME(DHMC_TU_FAM, DHMC_TU_PART)(int W, int epl, int kernel, 
 #error "family 4 is the USER family: compile with -DDHMC_USER_MODEL_HEADER='\"/path/to/model.h\"'"
 #endif
 #if DHMC_TU_PART == 0
-extern "C" const void* dhmc_user_family_kernel_0(int W, int epl, int kernel, int dense) {
+extern "C" __attribute__((visibility("hidden"))) const void* dhmc_user_family_kernel_0(int W, int epl, int kernel, int dense) {
   return dhmc::family_kernel_ptr<DHMC_FAMILY_USER, 0>(W, epl, (dhmc::KernelId)kernel, dense != 0);
 }
-extern "C" const char* dhmc_user_family_name_str(void) { return DHMC_USER_NAME; }
-extern "C" int dhmc_user_family_min_dim(void) { return DHMC_USER_MIN_DIM; }
+extern "C" __attribute__((visibility("hidden"))) const char* dhmc_user_family_name_str(void) { return DHMC_USER_NAME; }
+extern "C" __attribute__((visibility("hidden"))) int dhmc_user_family_min_dim(void) { return DHMC_USER_MIN_DIM; }
 #elif DHMC_TU_PART == 3
-extern "C" const void* dhmc_user_family_kernel_3(int W, int epl, int kernel, int dense) {
+extern "C" __attribute__((visibility("hidden"))) const void* dhmc_user_family_kernel_3(int W, int epl, int kernel, int dense) {
   return dhmc::family_kernel_ptr<DHMC_FAMILY_USER, 3>(W, epl, (dhmc::KernelId)kernel, dense != 0);
 }
 #endif

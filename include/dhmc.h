@@ -105,9 +105,12 @@ int dhmc_get_layout(dhmc_handle* h, int32_t* threads_per_chain, int32_t* elems_p
 int dhmc_set_problem(dhmc_handle* h, const double* params, size_t n);
 /* The user's own ℓ (LogDensityProblems.logdensity_and_gradient, call site hamiltonian.jl:204) as device code: a library
  * built from a model header (include/dhmc_models.h "the model header contract"; `make -C dynamichmc.jl_b200/csrc user
- * USER_HEADER=… USER_LIB=…`) carries family DHMC_FAMILY_USER next to the shipped ones.  Copies the model's DHMC_USER_NAME
+ * USER_HEADER=… USER_LIB=…`) carries family DHMC_FAMILY_USER (and only that family).  Copies the model's DHMC_USER_NAME
  * (NUL-terminated, truncated to cap) and returns DHMC_OK, or DHMC_EARG in a library without a user model. */
 int dhmc_user_family_name(char* name, size_t cap);
+/* Whether this library carries the kernels of `family` (the stock library: the four shipped families; a user-model
+ * library: DHMC_FAMILY_USER only).  dhmc_create refuses an absent family with DHMC_EARG. */
+int dhmc_family_available(int32_t family, int32_t* available);
 
 /* ---- state: initialization = (q, κ, ϵ), mcmc.jl:111-132 ---------------- */
 /* q: [D,B]; evaluates ℓ, ∇ℓ strictly (initialize_warmup_state, mcmc.jl:129-132). */

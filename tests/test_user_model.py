@@ -139,9 +139,24 @@ def test_user_library_builds_and_reports_its_model(pkg):
     ℓ = pkg.UserLogDensity(_hdr("rosenbrock"), 12, params=[1.0, 5.0], cpu=lambda q: rosenbrock_np(q, 1.0, 5.0))
     assert ℓ.model_name() == "rosenbrock" and ℓ.dimension() == 12 and ℓ.capabilities() == 1
     assert ℓ.logdensity_and_gradient(np.zeros(12))[0] == -11.0
-    # SASS of the user kernels: the same instruction families as the shipped ones (FP64 FMA pipe, no tensor / TMA needed)
     stock = pkg._lib.lib()
     assert stock.dhmc_user_family_name(buf, C.c_size_t(64)) == pkg._lib.DHMC_EARG
+    # which kernel families each library carries (weak references to the per-family translation units, resolved at link
+    # time): the stock library the four shipped ones, the user-model library family 4 only
+    def available(so):
+        out = []
+        for fam in range(6):
+            v = C.c_int32(-1)
+            assert so.dhmc_family_available(C.c_int32(fam), C.byref(v)) == pkg._lib.DHMC_OK
+            out.append(v.value)
+        return out
+    assert available(stock) == [1, 1, 1, 1, 0, 0]
+    assert available(lib) == [0, 0, 0, 0, 1, 0]
+    cfg = pkg._lib.Config(device=0, family=pkg._lib.FAMILY_STD_NORMAL, dim=4, n_chains=2, chain_offset=0, seed=1, max_depth=10,
+                          threads_per_chain=0, min_delta=-1000.0, ctas_per_sm=0, reserved=0)
+    h = C.c_void_p()
+    assert lib.dhmc_create(C.byref(cfg), C.byref(h)) == pkg._lib.DHMC_EARG
+    assert b"family not built into this library" in lib.dhmc_last_error(None)
 
 
 def test_stock_library_refuses_the_user_family(pkg):
