@@ -79,9 +79,53 @@ struct LogisticRegression <: DeviceLogDensity
         new(X, y)
     end
 end
+"""
+The user's own ℓ as device code: a model header (include/dhmc_models.h, "the model header contract"; examples in
+include/models/) compiled into its own build of the library, where it is family 4 (USER).  `params` is the block of doubles
+the header's formulas receive; `cpu` optionally is `q -> (ℓ(q), ∇ℓ(q))` for host-side use of the same object.
+A user-model library carries the USER family only, and `LIB` is a per-module constant, so such a model is run through a copy
+of this module bound to its library:
+
+    lib = B200HMC.compile_user_model("include/models/rosenbrock.h")       # make user USER_HEADER=… (nvcc, sm_100a)
+    M = B200HMC.bind_user_library(lib)                                     # a copy of B200HMC with LIB = lib
+    results = M.mcmc_with_warmup(2026, M.UserModel(100, [1.0, 5.0]), 1000; chains = 65_536)
+"""
+struct UserModel{F} <: DeviceLogDensity
+    D::Int; params::Vector{Float64}; cpu::F
+end
+UserModel(D::Integer, params = Float64[]; cpu = nothing) = UserModel(Int(D), Vector{Float64}(params), cpu)
 family(::StandardNormal) = Int32(0); family(::DiagNormal) = Int32(1); family(::Funnel) = Int32(2)
-family(::LogisticRegression) = Int32(3)
+family(::LogisticRegression) = Int32(3); family(::UserModel) = Int32(4)
 params(::DeviceLogDensity) = Float64[]
+params(ℓ::UserModel) = ℓ.params
+LogDensityProblems.dimension(ℓ::UserModel) = ℓ.D
+LogDensityProblems.logdensity_and_gradient(ℓ::UserModel, q) =
+    ℓ.cpu === nothing ? error("this UserModel was created without a host-side `cpu` function") : ℓ.cpu(q)
+"DHMC_USER_NAME of the model compiled into LIB (dhmc_user_family_name); `nothing` for the stock library."
+function user_family_name()
+    buf = zeros(UInt8, 128)
+    rc = ccall((:dhmc_user_family_name, LIB), Cint, (Ptr{UInt8}, Csize_t), buf, length(buf))
+    rc == OK ? unsafe_string(pointer(buf)) : nothing
+end
+"Whether LIB carries the kernels of `family` (dhmc_family_available): the stock library 0…3, a user-model library 4."
+family_available(fam::Integer) = (v = Ref{Int32}(0);
+    ccall((:dhmc_family_available, LIB), Cint, (Int32, Ref{Int32}), fam, v) == OK && v[] != 0)
+"Build the library that carries the model in `header` (csrc/Makefile target `user`); returns its path."
+function compile_user_model(header::AbstractString; csrc = joinpath(@__DIR__, "..", "dynamichmc.jl_b200", "csrc"),
+                            out_dir = joinpath(csrc, "user_models", splitext(basename(header))[1]))
+    so = joinpath(abspath(out_dir), "libdhmc_user_" * splitext(basename(header))[1] * ".so")
+    mkpath(out_dir)
+    run(`make -C $csrc -j2 user USER_HEADER=$(abspath(header)) USER_LIB=$so USER_BUILD=$(joinpath(abspath(out_dir), "build"))`)
+    so
+end
+"A copy of this module whose ccalls go to the user-model library `path`."
+function bind_user_library(path::AbstractString; name = Symbol("B200HMC_", replace(splitext(basename(path))[1], r"\W" => "_")))
+    withenv("DHMC_B200_LIB" => abspath(path)) do
+        outer = Module(name)
+        Base.include(outer, @__FILE__)            # evaluates `module B200HMC … end` again, with LIB = path
+        getfield(outer, :B200HMC)
+    end
+end
 params(ℓ::DiagNormal) = vcat(ℓ.μ, 1 ./ ℓ.σ²)
 params(ℓ::LogisticRegression) = vcat(Float64(size(ℓ.X, 1)), vec(permutedims(ℓ.X)), ℓ.y)   # [N, X row-major, y]
 LogDensityProblems.capabilities(::Type{<:DeviceLogDensity}) = LogDensityProblems.LogDensityOrder{1}()
