@@ -252,6 +252,42 @@ def bind_to_gpu_numa_node(local_rank):
         return None
 
 
+def user_model_leg(pkg, wl, K, D, n, args, local_rank, chain_offset, draws, stats, logd, ref_steps, ref_ms):
+    """The C2 step once more with ℓ supplied as a USER model header (include/models/std_normal_user.h compiled into its own
+    build of the library): same seed, same setup, same number of warm-up and timed steps, so the chains are
+    the shipped family's bit for bit (`same_trees`) and the two rates compare the kernels alone.  Never fails the bench:
+    an error is reported in the returned dict."""
+    try:
+        hdr = os.path.join(ROOT, "include", "models", "std_normal_user.h")
+        t0 = time.perf_counter()
+        ℓ = pkg.UserLogDensity(hdr, D)
+        build_s = time.perf_counter() - t0
+        eng = pkg.Engine(ℓ, chains=K, seed=2026, device=local_rank, chain_offset=chain_offset,
+                         threads_per_chain=args.threads_per_chain, ctas_per_sm=args.ctas_per_sm)
+        try:
+            eng.random_position()
+            eng.find_initial_stepsize()
+            for st in wl["stages"]:
+                eng.warmup_stage(st)
+            steps, ms = 0, 0.0
+            for i in range(args.warmup + args.steps):
+                eng.mcmc_dev(n, draws.data_ptr(), stats.data_ptr(), logd.data_ptr())
+                if i >= args.warmup:
+                    steps += eng.last_total_steps(); ms += eng.last_kernel_ms()
+            launches = eng.kernel_launches()
+        finally:
+            eng.close()
+        return {"model": ℓ.model_name(), "header": "include/models/std_normal_user.h", "library": os.path.relpath(ℓ.library_path, ROOT),
+                "value": steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / args.steps,
+                "relative_to_shipped_family": (steps / ms) / (ref_steps / ref_ms), "same_trees": bool(steps == ref_steps),
+                "gpu_launches": int(launches), "library_lookup_seconds": build_s,
+                "what": "the timed C2 step with the log density given as a model header (user formulas behind the contract of "
+                        "include/dhmc_models.h, position staged in shared memory once per gradient), same chains as the shipped "
+                        "STD_NORMAL kernels; device-timed like `value`, run after the timed region"}
+    except Exception as e:          # auxiliary leg: report, do not lose the bench line
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -390,6 +426,12 @@ def main():
             print("[bench trace] e2e loop %.1f ms, with closing barrier %.1f ms" % (1e3 * t_loop, 1e3 * e_wall), file=sys.stderr)
         e2e = (e_steps, e_wall, K * D * 8, K * n * D * 8 + K * n * 56 + K * n * 8)
 
+    # ---------------- the same step with the log density supplied as a USER model (after timing; C2, one GPU) ----------------
+    user_leg = None
+    if world == 1 and args.config == "C2" and not os.environ.get("DHMC_BENCH_NO_USER_MODEL"):
+        user_leg = user_model_leg(pkg, wl, K, D, n, args, local_rank, chain_offset, draws, stats, logd,
+                                  tot_steps, dev_ms)
+
     # ---------------- multi-GPU: one NCCL all-gather of the draws (library communicator), after timing ----------------
     gather = None
     if world > 1:
@@ -501,6 +543,8 @@ def main():
                            "how": "dhmc_mcmc_from with page-locked NUMA-local host buffers (node %s): positions uploaded, draws / statistics / "
                                   "log densities downloaded, both pipelined by chain chunks against the sampling of the next chunk (draws "
                                   "that do not fit in HBM would be written by the kernel directly)" % numa}
+        if user_leg:
+            line["user_model"] = user_leg
         if gather:
             bw = K * D * 8 * (world - 1) / (mx[7].item() * 1e-3) / 1e9
             line["allgather"] = {"ms": mx[7].item(), "first_call_ms": gather[0], "bytes_per_rank": K * D * 8,

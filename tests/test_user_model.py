@@ -79,6 +79,20 @@ def test_funnel_as_user_model_equals_shipped_family_in_the_oracle(po, D, T):
     assert po.lib().orc_user_family_name().decode() == ""         # back on the stock oracle
 
 
+@pytest.mark.parametrize("D,T", [(1, 32), (100, 32), (1000, 128)])
+def test_std_normal_as_user_model_equals_shipped_family_in_the_oracle(po, D, T):
+    rng = np.random.default_rng(D)
+    st = po.default_warmup_stages(init_steps=25, middle_steps=20, doubling_stages=1, terminating_steps=20)
+    with po.user_model(_hdr("std_normal_user")):
+        q = rng.normal(size=D)
+        assert po.logdensity_and_gradient(po.FAMILY_USER, q, None, T)[0] == po.logdensity_and_gradient(po.FAMILY_STD_NORMAL, q, None, T)[0]
+        a = po.mcmc_with_warmup(po.FAMILY_USER, D, 8, 3, 1, stages=st, T=T, welford=True, keep_warmup=True)
+        b = po.mcmc_with_warmup(po.FAMILY_STD_NORMAL, D, 8, 3, 1, stages=st, T=T, welford=True, keep_warmup=True)
+    assert np.array_equal(a["posterior_matrix"], b["posterior_matrix"]) and a["eps"] == b["eps"]
+    for f in INT_FIELDS:
+        assert np.array_equal(a["warmup_stats"][f], b["warmup_stats"][f])
+
+
 def test_funnel_as_user_model_whole_warmup_in_the_oracle(po):
     D, N = 10, 25
     st = po.default_warmup_stages(init_steps=30, middle_steps=20, doubling_stages=2, terminating_steps=20)
@@ -194,6 +208,22 @@ def test_funnel_as_user_model_equals_shipped_family_on_device(pkg):
         a, b = ra["inference"][k], rb["inference"][k]
         assert np.array_equal(a["posterior_matrix"], b["posterior_matrix"]) and a["ϵ"] == b["ϵ"]
         assert np.array_equal(a["κ"].minv, b["κ"].minv) and np.array_equal(a["logdensities"], b["logdensities"])
+        for f in INT_FIELDS:
+            assert np.array_equal(a["tree_statistics"][f], b["tree_statistics"][f])
+    ra["engine"].close(); rb["engine"].close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("D,K", [(100, 40), (1000, 16)])
+def test_std_normal_as_user_model_equals_shipped_family_on_device(pkg, D, K):
+    """The model bench.py times as `user_model`: identical chains to the shipped STD_NORMAL kernels (same layout)."""
+    stages = pkg.default_warmup_stages(init_steps=25, middle_steps=20, doubling_stages=1, terminating_steps=20)
+    ra = pkg.mcmc_keep_warmup(17, pkg.UserLogDensity(_hdr("std_normal_user"), D), 6, chains=K, warmup_stages=stages)
+    rb = pkg.mcmc_keep_warmup(17, pkg.StandardNormal(D), 6, chains=K, warmup_stages=stages)
+    assert ra["engine"].layout() == rb["engine"].layout()
+    for k in range(K):
+        a, b = ra["inference"][k], rb["inference"][k]
+        assert np.array_equal(a["posterior_matrix"], b["posterior_matrix"]) and a["ϵ"] == b["ϵ"]
         for f in INT_FIELDS:
             assert np.array_equal(a["tree_statistics"][f], b["tree_statistics"][f])
     ra["engine"].close(); rb["engine"].close()
