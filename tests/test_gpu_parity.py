@@ -169,6 +169,29 @@ def test_full_warmup_matches_oracle(pkg, po, fam, D):
     r["engine"].close()
 
 
+def test_c1_exact_config_matches_oracle(pkg, po):
+    """BASELINE.json configs[0] verbatim on the device: 100-dim standard MvNormal, 4 chains, the default warm-up (900
+    transitions, diagonal metric windows) and 1000 draws — every chain equals the oracle (integers, ϵ, metric, draws), and
+    the pooled posterior has the N(0, I) moments within sampling error (test_mcmc.jl:18-26 style)."""
+    D, K, N, seed = 100, 4, 1000, 1
+    r = pkg.mcmc_keep_warmup(seed, pkg.StandardNormal(D), N, chains=K)
+    T, _ = r["engine"].layout()
+    for k in range(K):
+        o = po.mcmc_with_warmup(po.FAMILY_STD_NORMAL, D, N, seed, k, T=T, welford=True, keep_warmup=True)
+        w = np.concatenate([s["results"]["tree_statistics"][k] for s in r["warmup"] if s["results"]])
+        assert w.size == 900
+        for f in INT_FIELDS:
+            assert np.array_equal(w[f], o["warmup_stats"][f]), f
+        res = r["inference"][k]
+        assert res["ϵ"] == o["eps"] and np.array_equal(res["κ"].minv, o["minv"])
+        assert np.array_equal(res["posterior_matrix"].T, o["posterior_matrix"])
+        for f in INT_FIELDS:
+            assert np.array_equal(res["tree_statistics"][f], o["tree_statistics"][f])
+    pooled = pkg.pool_posterior_matrices(r["inference"])            # [D, N·K]
+    assert np.abs(pooled.mean(axis=1)).max() < 0.12 and np.abs(pooled.var(axis=1) - 1).max() < 0.25
+    r["engine"].close()
+
+
 def _c5_model(pkg, D=1000):
     """BASELINE.json configs[4]: MvNormal with σᵢ² = 10^{4(i−1)/(D−1)} (κ = 10⁴), SURVEY.md §8d."""
     return pkg.DiagNormal(np.zeros(D), 10.0 ** (4.0 * np.arange(D) / (D - 1)))
