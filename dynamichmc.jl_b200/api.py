@@ -152,8 +152,9 @@ class LogisticRegression(DeviceLogDensity):
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 
 
-def compile_user_model(header, out_dir=None, force=False, jobs=2):
+def compile_user_model(header, out_dir=None, force=False, jobs=2, deep=False):
     """Build (or reuse) the library that carries the model in `header` as family FAMILY_USER; returns its path.
+    `deep=True` also compiles the kernels for NUTS(max_depth > 12) (up to the reference's limit 32; twice the build time).
 
     The build is keyed by the header's content and the library sources' modification times, lives under
     csrc/user_models/<name>-<hash>/ (in-tree, so that it travels with the package) unless `out_dir` is given, and needs nvcc
@@ -168,13 +169,13 @@ def compile_user_model(header, out_dir=None, force=False, jobs=2):
     hsh = hashlib.sha256(open(header, "rb").read())
     for f in srcs:
         hsh.update(open(f, "rb").read())
-    tag = f"{name}-{hsh.hexdigest()[:12]}"
+    tag = f"{name}-{hsh.hexdigest()[:12]}" + ("-deep" if deep else "")
     out_dir = os.path.abspath(out_dir or os.path.join(_CSRC, "user_models", tag))
     so = os.path.join(out_dir, f"libdhmc_user_{name}.so")
     if force or not os.path.exists(so):
         os.makedirs(out_dir, exist_ok=True)
         cmd = ["make", "-C", _CSRC, f"-j{jobs}", "user", f"USER_HEADER={header}", f"USER_LIB={so}",
-               f"USER_BUILD={os.path.join(out_dir, 'build')}"]
+               f"USER_BUILD={os.path.join(out_dir, 'build')}", "USER_PARTS=" + ("0 3" if deep else "0")]
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0 or not os.path.exists(so):
             raise RuntimeError(f"user model build failed ({' '.join(cmd)}):\n{r.stdout[-4000:]}")
@@ -187,14 +188,15 @@ def compile_user_model(header, out_dir=None, force=False, jobs=2):
 class UserLogDensity(DeviceLogDensity):
     """ℓ given as a model header (the device-side LogDensityProblems object).  `params` is the block of doubles the
     header's formulas receive; `cpu` optionally is a callable q ↦ (ℓ(q), ∇ℓ(q)) so that the object also answers
-    logdensity_and_gradient on the host (like the shipped families' numpy forms).  `library` may name a prebuilt library."""
+    logdensity_and_gradient on the host (like the shipped families' numpy forms).  `library` may name a prebuilt library;
+    `deep=True` builds the kernels for NUTS(max_depth > 12) as well."""
     family = L.FAMILY_USER
 
-    def __init__(self, header, D, params=(), cpu=None, library=None):
+    def __init__(self, header, D, params=(), cpu=None, library=None, deep=False):
         self.header, self.D = os.path.abspath(header), int(D)
         self._params = np.ascontiguousarray(params, float).ravel()
         self._cpu = cpu
-        self.library_path = library or compile_user_model(self.header)
+        self.library_path = library or compile_user_model(self.header, deep=deep)
 
     def params(self):
         return self._params

@@ -399,7 +399,7 @@ static int plan(dhmc_handle* h) {
   int& reg_ctas = h->reg_ctas[h->dense ? 1 : 0];
   if (reg_ctas == 0) {
     const void* fn = lookup_kernel(h->cfg.family, kernel_part(h, K_NUTS, G), h->W, h->EPL, K_NUTS, h->dense);
-    if (!fn) { h->err = "dense metric: layout not built"; return DHMC_EARG; }
+    if (!fn) { h->err = "kernel not built into this library for this layout (max_depth > 12 needs a user-model library built with its deep part: USER_PARTS=\"0 3\" / deep=True)"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L0.total);
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&reg_ctas, fn, T * G, L0.total);
     if (e != cudaSuccess) { h->err = std::string("occupancy query: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
@@ -512,7 +512,7 @@ static int launch(dhmc_handle* h, KernelId k, KArgs a, int timing, bool reset_st
 #endif
   {
     const void* fn = lookup_kernel(h->cfg.family, kernel_part(h, k, G), h->W, h->EPL, k, h->dense);
-    if (!fn) { h->err = "dense metric: layout not built"; return DHMC_EARG; }
+    if (!fn) { h->err = "kernel not built into this library for this layout (max_depth > 12 needs a user-model library built with its deep part: USER_PARTS=\"0 3\" / deep=True)"; return DHMC_EARG; }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return DHMC_ECUDA; }
     void* params[] = {(void*)&a};

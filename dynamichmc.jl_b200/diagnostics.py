@@ -135,8 +135,7 @@ def ess_rhat(draws, max_lag=0):
     n = N // 2
     L = max_lag if max_lag > 0 else 64
     L = max(1, min(L, n - 2))
-    seq = np.concatenate([x[:, :n], x[:, n:2 * n]], axis=1).reshape(2 * K, n, D) if False else \
-        np.stack([x[:, :n], x[:, n:2 * n]], axis=1).reshape(2 * K, n, D)
+    seq = np.stack([x[:, :n], x[:, n:2 * n]], axis=1).reshape(2 * K, n, D)     # sequence 2c = first half of chain c, 2c+1 = second
     m = 2 * K
     mu = seq.mean(axis=1)                                      # [m, D]
     xc = seq - mu[:, None, :]

@@ -112,10 +112,11 @@ family_available(fam::Integer) = (v = Ref{Int32}(0);
     ccall((:dhmc_family_available, LIB), Cint, (Int32, Ref{Int32}), fam, v) == OK && v[] != 0)
 "Build the library that carries the model in `header` (csrc/Makefile target `user`); returns its path."
 function compile_user_model(header::AbstractString; csrc = joinpath(@__DIR__, "..", "dynamichmc.jl_b200", "csrc"),
-                            out_dir = joinpath(csrc, "user_models", splitext(basename(header))[1]))
+                            out_dir = joinpath(csrc, "user_models", splitext(basename(header))[1]), deep::Bool = false)
     so = joinpath(abspath(out_dir), "libdhmc_user_" * splitext(basename(header))[1] * ".so")
     mkpath(out_dir)
-    run(`make -C $csrc -j2 user USER_HEADER=$(abspath(header)) USER_LIB=$so USER_BUILD=$(joinpath(abspath(out_dir), "build"))`)
+    parts = deep ? "0 3" : "0"                    # "0 3": also the kernels for NUTS(max_depth > 12)
+    run(`make -C $csrc -j2 user USER_HEADER=$(abspath(header)) USER_LIB=$so USER_BUILD=$(joinpath(abspath(out_dir), "build")) USER_PARTS=$parts`)
     so
 end
 "A copy of this module whose ccalls go to the user-model library `path`."

@@ -47,8 +47,6 @@ def test_leapfrog_matches_oracle(pkg, po, D):
                 assert np.array_equal(st["q"][k], qo) and np.array_equal(st["p"][k], p_o)
                 assert np.array_equal(st["grad"][k], go) and st["lq"][k] == lqo
             q, p = st["q"], st["p"]
-        for k in range(K):   # logdensity(H, z) before stepping
-            pass
         lq0 = [po.logdensity_and_gradient(fam, qq, params, T)[0] for qq in q]
         H1 = eng.phase_logdensity()
         for k in range(K):

@@ -141,7 +141,7 @@ def test_eight_schools_oracle_values(po):
 # ------------------------------------------------------------------ CPU: the user-model build of the library
 def test_user_library_builds_and_reports_its_model(pkg):
     """nvcc cross-compiles the model for sm_100a (no GPU needed); the result carries the whole C ABI plus the model."""
-    so = pkg.compile_user_model(_hdr("rosenbrock"))
+    so = pkg.compile_user_model(_hdr("rosenbrock"), deep=True)        # the build __graft_entry__.build() prepares
     lib = pkg._lib.lib(so)
     for name in pkg._lib.EXPORTS:
         assert hasattr(lib, name), name
@@ -149,8 +149,8 @@ def test_user_library_builds_and_reports_its_model(pkg):
     assert lib.dhmc_user_family_name(buf, C.c_size_t(64)) == pkg._lib.DHMC_OK and buf.value == b"rosenbrock"
     small = C.create_string_buffer(5)
     assert lib.dhmc_user_family_name(small, C.c_size_t(5)) == pkg._lib.DHMC_OK and small.value == b"rose"
-    assert pkg.compile_user_model(_hdr("rosenbrock")) == so                     # cached by content hash
-    ℓ = pkg.UserLogDensity(_hdr("rosenbrock"), 12, params=[1.0, 5.0], cpu=lambda q: rosenbrock_np(q, 1.0, 5.0))
+    assert pkg.compile_user_model(_hdr("rosenbrock"), deep=True) == so          # cached by content hash
+    ℓ = pkg.UserLogDensity(_hdr("rosenbrock"), 12, params=[1.0, 5.0], cpu=lambda q: rosenbrock_np(q, 1.0, 5.0), deep=True)
     assert ℓ.model_name() == "rosenbrock" and ℓ.dimension() == 12 and ℓ.capabilities() == 1
     assert ℓ.logdensity_and_gradient(np.zeros(12))[0] == -11.0
     stock = pkg._lib.lib()
@@ -186,7 +186,7 @@ def test_stock_library_refuses_the_user_family(pkg):
 
 
 def test_user_library_enforces_min_dim(pkg):
-    so = pkg.compile_user_model(_hdr("rosenbrock"))
+    so = pkg.compile_user_model(_hdr("rosenbrock"), deep=True)
     cfg = pkg._lib.Config(device=0, family=pkg._lib.FAMILY_USER, dim=1, n_chains=2, chain_offset=0, seed=1, max_depth=10,
                           threads_per_chain=0, min_delta=-1000.0, ctas_per_sm=0, reserved=0)
     h = C.c_void_p()
@@ -243,7 +243,7 @@ def test_user_models_leapfrog_and_trees_match_oracle(pkg, po):
     rng = np.random.default_rng(17)
     for name, D, pr in _user_cases(pkg):
         K = 12
-        ℓ = pkg.UserLogDensity(_hdr(name), D, params=pr)
+        ℓ = pkg.UserLogDensity(_hdr(name), D, params=pr, deep=(name == "rosenbrock"))
         eng = pkg.Engine(ℓ, chains=K, seed=77)
         T, _ = eng.layout()
         q, p = rng.normal(size=(K, D)) * 0.5, rng.normal(size=(K, D))
@@ -299,7 +299,7 @@ def test_user_model_full_warmup_matches_oracle(pkg, po, M):
             assert np.array_equal(res["posterior_matrix"].T, o["posterior_matrix"])
     r["engine"].close()
     if M == "Diagonal":      # max_depth > 12: the deep kernel instantiations of the user family
-        eng = pkg.Engine(pkg.UserLogDensity(_hdr("rosenbrock"), 3, params=[1.0, 5.0]), chains=6, seed=9, algorithm=pkg.NUTS(max_depth=15))
+        eng = pkg.Engine(pkg.UserLogDensity(_hdr("rosenbrock"), 3, params=[1.0, 5.0], deep=True), chains=6, seed=9, algorithm=pkg.NUTS(max_depth=15))
         T, _ = eng.layout()
         rng = np.random.default_rng(1)
         q = rng.normal(size=(6, 3)) * 0.3
