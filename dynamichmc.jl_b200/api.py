@@ -677,15 +677,27 @@ def _initialize(engine: Engine, initialization):
         engine.set_stepsize(init["ϵ"])
 
 
+def _report(reporter, message, **kw):
+    """The reporter hook (src/reporting.jl; `report(reporter, …)` call sites mcmc.jl:279,378): the reference reports per
+    transition, this engine once per batch of transitions between two library calls.  `reporter` is None
+    (NoProgressReport) or a callable `reporter(message, **fields)`; a failing reporter never aborts sampling."""
+    if reporter is None:
+        return
+    try:
+        reporter(message, **kw)
+    except Exception:
+        pass
+
+
 def mcmc_keep_warmup(seed, ℓ, N, chains=1, initialization=None, warmup_stages=None,
-                     algorithm=None, keep_warmup=True, device=0, chain_offset=0, engine_opts=None):
+                     algorithm=None, keep_warmup=True, device=0, chain_offset=0, engine_opts=None, reporter=None):
     """src/mcmc.jl:521-532 for `chains` chains at once."""
     stages = default_warmup_stages() if warmup_stages is None else warmup_stages
     eng = Engine(ℓ, chains, seed=seed, algorithm=algorithm, device=device, chain_offset=chain_offset,
                  **(engine_opts or {}))
     _initialize(eng, initialization)
     warm = []
-    for stage in stages:                                     # _warmup fold, mcmc.jl:450-457
+    for i, stage in enumerate(stages):                       # _warmup fold, mcmc.jl:450-457
         if stage is None:                                    # no-op stage, mcmc.jl:99-101
             warm.append(dict(stage=None, results=None))
         elif isinstance(stage, InitialStepsizeSearch):
@@ -695,7 +707,10 @@ def mcmc_keep_warmup(seed, ℓ, N, chains=1, initialization=None, warmup_stages=
             warm.append(dict(stage=stage, results=eng.warmup_stage(stage, keep=keep_warmup)))
         else:
             raise ArgumentError(f"unknown warmup stage {stage!r}")
+        _report(reporter, "warmup stage finished", stage=i + 1, of=len(stages), kind=type(stage).__name__,
+                transitions=getattr(stage, "N", 0), chains=chains)
     inf = eng.mcmc(N)
+    _report(reporter, "inference finished", transitions=N, chains=chains)
     st = eng.get_state(("minv", "eps"))
     minv = eng.get_metric_dense() if eng.metric_is_dense() else st["minv"]
     results = Results(inf["posterior_matrix"], inf["tree_statistics"], inf["logdensities"],
@@ -704,10 +719,36 @@ def mcmc_keep_warmup(seed, ℓ, N, chains=1, initialization=None, warmup_stages=
 
 
 def mcmc_with_warmup(seed, ℓ, N, chains=1, initialization=None, warmup_stages=None, algorithm=None,
-                     device=0, chain_offset=0, engine_opts=None):
+                     device=0, chain_offset=0, engine_opts=None, reporter=None):
     """src/mcmc.jl:575-584 for `chains` chains at once → Results."""
     r = mcmc_keep_warmup(seed, ℓ, N, chains=chains, initialization=initialization,
                          warmup_stages=warmup_stages, algorithm=algorithm, keep_warmup=False,
-                         device=device, chain_offset=chain_offset, engine_opts=engine_opts)
+                         device=device, chain_offset=chain_offset, engine_opts=engine_opts, reporter=reporter)
     r["engine"].close()
     return r["inference"]
+
+
+class MCMCSteps:
+    """src/mcmc.jl:335-346 — the sampler frozen at the adapted (κ, ϵ) of a finished warm-up, for stepwise sampling:
+        r = mcmc_keep_warmup(seed, ℓ, 0, chains=K); steps = mcmc_steps(r["engine"]); Q = steps.Q
+        Q, stats = mcmc_next_step(steps, Q)
+    `Q` is the [K, D] matrix of positions (the reference's EvaluatedLogDensity per chain; ℓ and ∇ℓ are re-evaluated
+    strictly on upload, hamiltonian.jl:202-217)."""
+
+    def __init__(self, engine: Engine):
+        self.engine = engine
+
+    @property
+    def Q(self):
+        return self.engine.get_state(("q",))["q"]
+
+
+def mcmc_steps(engine: Engine) -> MCMCSteps:
+    """mcmc_steps(sampling_logdensity, warmup_state) — src/mcmc.jl:335-346; the warm-up state lives in the engine."""
+    return MCMCSteps(engine)
+
+
+def mcmc_next_step(steps: MCMCSteps, Q):
+    """One NUTS transition of every chain from the positions Q → (Q′, tree_statistics [K]) — src/mcmc.jl:348-351."""
+    out = steps.engine.mcmc_from(np.asarray(Q, float), 1)
+    return out["posterior_matrix"][:, 0, :], out["tree_statistics"][:, 0]

@@ -903,6 +903,24 @@ def test_mcmc_from_host_positions(pkg):
     b.close()
 
 
+def test_stepwise_sampling_equals_mcmc(pkg):
+    """mcmc_steps / mcmc_next_step (mcmc.jl:335-351): N single transitions from the returned positions are the N draws of
+    one mcmc call (same RNG counter, ℓ and ∇ℓ re-evaluated from the uploaded positions)."""
+    D, K, N = 30, 200, 4
+    ℓ = pkg.DiagNormal(np.linspace(-1, 1, D), np.logspace(-1, 1, D))
+    stages = pkg.default_warmup_stages(init_steps=25, middle_steps=20, doubling_stages=1, terminating_steps=20)
+    ra = pkg.mcmc_keep_warmup(8, ℓ, N, chains=K, warmup_stages=stages)
+    rb = pkg.mcmc_keep_warmup(8, ℓ, 0, chains=K, warmup_stages=stages)
+    steps = pkg.mcmc_steps(rb["engine"])
+    Q = steps.Q
+    for n in range(N):
+        Q, stats = pkg.mcmc_next_step(steps, Q)
+        for k in (0, 57, K - 1):
+            assert np.array_equal(Q[k], ra["inference"][k]["posterior_matrix"][:, n])
+            assert stats[k] == ra["inference"][k]["tree_statistics"][n]
+    ra["engine"].close(); rb["engine"].close()
+
+
 # --------------------------------------------------------------- reference integration tests (test/test_mcmc.jl)
 def _rhat(x):
     """split-R̂ per parameter; x: [draw, chain, param] (stack_posterior_matrices layout)."""

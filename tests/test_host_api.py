@@ -132,6 +132,39 @@ def test_warmup_fold_calls_the_engine_in_stage_order(pkg, api):
         api.mcmc_keep_warmup(1, ℓ, 5, warmup_stages=("bogus",))
 
 
+def test_reporter_hook_and_stepwise_sampling(pkg, api):
+    """`reporter` (mcmc.jl:279,378 call sites; one report per batch here) and mcmc_steps / mcmc_next_step (mcmc.jl:335-351)."""
+    ℓ = pkg.StandardNormal(4)
+    seen = []
+    stages = (pkg.InitialStepsizeSearch(), pkg.TuningNUTS(20), None)
+    api.mcmc_with_warmup(3, ℓ, 9, chains=2, warmup_stages=stages, reporter=lambda msg, **kw: seen.append((msg, kw)))
+    assert [m for m, _ in seen] == ["warmup stage finished"] * 3 + ["inference finished"]
+    assert seen[1][1] == dict(stage=2, of=3, kind="TuningNUTS", transitions=20, chains=2)
+    assert seen[3][1] == dict(transitions=9, chains=2)
+    # a reporter that raises never aborts sampling
+    api.mcmc_with_warmup(3, ℓ, 2, chains=2, warmup_stages=(), reporter=lambda *a, **k: 1 / 0)
+
+    class StepEngine(RecordingEngine):
+        def mcmc_from(self, q, N, out=None):
+            self.log.append(("mcmc_from", np.array(q), N))
+            K, D = self.K, self.D
+            st = np.zeros((K, N), dtype=[("depth", "<i8")]); st["depth"] = 3
+            return dict(posterior_matrix=np.repeat(np.asarray(q)[:, None, :] + 1.0, N, axis=1), tree_statistics=st,
+                        logdensities=np.zeros((K, N)))
+
+        def get_state(self, fields):
+            return {"q": np.full((self.K, self.D), 0.5)} if tuple(fields) == ("q",) else super().get_state(fields)
+
+    eng = StepEngine(ℓ, 3)
+    steps = api.mcmc_steps(eng)
+    assert isinstance(steps, api.MCMCSteps) and np.array_equal(steps.Q, np.full((3, 4), 0.5))
+    Q1, stats = api.mcmc_next_step(steps, steps.Q)
+    assert Q1.shape == (3, 4) and np.all(Q1 == 1.5) and stats.shape == (3,) and np.all(stats["depth"] == 3)
+    assert eng.log[-1][0] == "mcmc_from" and eng.log[-1][2] == 1
+    Q2, _ = api.mcmc_next_step(steps, Q1)
+    assert np.all(Q2 == 2.5)
+
+
 def test_initialization_fields(pkg, api):
     ℓ = pkg.StandardNormal(3)
     κ = pkg.GaussianKineticEnergy(np.array([1.0, 2.0, 3.0]))
