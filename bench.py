@@ -288,6 +288,52 @@ def user_model_leg(pkg, wl, K, D, n, args, local_rank, chain_offset, draws, stat
         return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
 
+def c4_probe_leg(pkg, torch, dev, local_rank, sm_max_mhz, chains=4736, warm=(20, 40, 20), draws=4):
+    """The tensor-core kernel of BASELINE.json configs[3] (logistic N=10 000, p=256, per-chain dense metric) inside the default
+    run, at a REDUCED chain count (4 736 = 4 waves of 148 SMs x 8 chains per CTA instead of 32 768, so that the default bench
+    stays short): search + TuningNUTS(20) + TuningNUTS(40, Symmetric) + TuningNUTS(20), then `draws` timed transitions with the
+    adapted dense metric.  The full-size line is `bench.py --config C4` (profiles/r02_bench_c4.json).  Never fails the bench."""
+    try:
+        N, p = 10000, 256
+        ℓ, _ = pkg.LogisticRegression.synthetic(N=N, p=p, seed=7)
+        flops = 4.0 * N * p + 2 * 2.0 * p * p
+        t0 = time.perf_counter()
+        eng = pkg.Engine(ℓ, chains=chains, seed=2026, device=local_rank)
+        try:
+            eng.random_position()
+            eng.find_initial_stepsize()
+            w_steps, w_ms = 0, 0.0
+            stages = [pkg.TuningNUTS(warm[0], pkg.DualAveraging()), pkg.TuningNUTS(warm[1], pkg.DualAveraging(), pkg.Symmetric),
+                      pkg.TuningNUTS(warm[2], pkg.DualAveraging())]
+            for st in stages:
+                eng.warmup_stage(st)
+                w_steps += eng.last_total_steps(); w_ms += eng.last_kernel_ms()
+            post = torch.empty((chains, 1, p), dtype=torch.float64, device=dev)
+            stats = torch.empty((chains, 1, 56), dtype=torch.uint8, device=dev)
+            logd = torch.empty((chains, 1), dtype=torch.float64, device=dev)
+            steps, ms = 0, 0.0
+            for i in range(1 + draws):
+                eng.mcmc_dev(1, post.data_ptr(), stats.data_ptr(), logd.data_ptr())
+                if i >= 1:
+                    steps += eng.last_total_steps(); ms += eng.last_kernel_ms()
+            summary = eng.tree_summary_dev(stats.data_ptr(), 1, ebfmi=False)
+        finally:
+            eng.close()
+        peak_tf = DMMA_FMA_PER_CLK_SM * 2 * 148 * sm_max_mhz * 1e6 / 1e12
+        rate, wrate = steps / (ms * 1e-3), w_steps / (w_ms * 1e-3)
+        return {"workload": "C4 kernel probe: logistic regression N=%d p=%d, %d chains (full size: 32768), per-chain dense metric adapted by "
+                            "search + TuningNUTS(%d) + TuningNUTS(%d, Symmetric) + TuningNUTS(%d); likelihood and M^-1 p on DMMA.8x8x4"
+                            % ((N, p, chains) + tuple(warm)),
+                "value": rate, "unit": UNIT, "tflops_fp64": rate * flops / 1e12, "frac_of_dmma_peak": rate * flops / 1e12 / peak_tf,
+                "warmup_value": wrate, "warmup_tflops_fp64": wrate * flops / 1e12, "dmma_peak_tflops": peak_tf,
+                "leapfrogs_per_transition": steps / (draws * chains), "a_mean": summary["a_mean"],
+                "depth_counts": summary["depth_counts"], "seconds": time.perf_counter() - t0,
+                "what": "device-timed like `value`, run after the timed region of the default workload; 4736 of the 32768 C4 chains, so "
+                        "tail effects of the last wave weigh more than at full size"}
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -432,6 +478,11 @@ def main():
         user_leg = user_model_leg(pkg, wl, K, D, n, args, local_rank, chain_offset, draws, stats, logd,
                                   tot_steps, dev_ms)
 
+    # ---------------- BASELINE.json configs[3] on its own kernel at a reduced chain count (after timing; C2 default run) ------
+    c4_leg = None
+    if world == 1 and args.config == "C2" and not args.chains and not args.dim and not os.environ.get("DHMC_BENCH_NO_C4_PROBE"):
+        c4_leg = c4_probe_leg(pkg, torch, dev, local_rank, peaks()[1])
+
     # ---------------- multi-GPU: one NCCL all-gather of the draws (library communicator), after timing ----------------
     gather = None
     if world > 1:
@@ -545,6 +596,8 @@ def main():
                                   "that do not fit in HBM would be written by the kernel directly)" % numa}
         if user_leg:
             line["user_model"] = user_leg
+        if c4_leg:
+            line["c4_probe"] = c4_leg
         if gather:
             bw = K * D * 8 * (world - 1) / (mx[7].item() * 1e-3) / 1e9
             line["allgather"] = {"ms": mx[7].item(), "first_call_ms": gather[0], "bytes_per_rank": K * D * 8,
