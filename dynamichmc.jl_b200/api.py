@@ -173,15 +173,21 @@ def compile_user_model(header, out_dir=None, force=False, jobs=2, deep=False):
     out_dir = os.path.abspath(out_dir or os.path.join(_CSRC, "user_models", tag))
     so = os.path.join(out_dir, f"libdhmc_user_{name}.so")
     if force or not os.path.exists(so):
+        import fcntl
         os.makedirs(out_dir, exist_ok=True)
-        cmd = ["make", "-C", _CSRC, f"-j{jobs}", "user", f"USER_HEADER={header}", f"USER_LIB={so}",
-               f"USER_BUILD={os.path.join(out_dir, 'build')}", "USER_PARTS=" + ("0 3" if deep else "0")]
-        r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-        if r.returncode != 0 or not os.path.exists(so):
-            raise RuntimeError(f"user model build failed ({' '.join(cmd)}):\n{r.stdout[-4000:]}")
-        for f in os.listdir(os.path.join(out_dir, "build")):       # keep the ptxas logs, drop the objects (they are in the .so)
-            if f.endswith(".o"):
-                os.remove(os.path.join(out_dir, "build", f))
+        with open(os.path.join(out_dir, ".lock"), "w") as lock:        # several ranks / test workers may ask for the same model
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if force or not os.path.exists(so):
+                tmp = so + ".tmp%d" % os.getpid()                       # linked under a private name, published by rename
+                cmd = ["make", "-C", _CSRC, f"-j{jobs}", "user", f"USER_HEADER={header}", f"USER_LIB={tmp}",
+                       f"USER_BUILD={os.path.join(out_dir, 'build')}", "USER_PARTS=" + ("0 3" if deep else "0")]
+                r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                if r.returncode != 0 or not os.path.exists(tmp):
+                    raise RuntimeError(f"user model build failed ({' '.join(cmd)}):\n{r.stdout[-4000:]}")
+                os.replace(tmp, so)
+                for f in os.listdir(os.path.join(out_dir, "build")):   # keep the ptxas logs, drop the objects (they are in the .so)
+                    if f.endswith(".o"):
+                        os.remove(os.path.join(out_dir, "build", f))
     return so
 
 
