@@ -138,6 +138,24 @@ def test_eight_schools_oracle_values(po):
     assert -5 < o["posterior_matrix"][:, 0].mean() < 15
 
 
+def test_model_without_sums_oracle_values(po):
+    """DHMC_USER_NSUMS 0 (ℓ straight from the position): the 2-d banana, against the direct formula and finite differences."""
+    s_, b = 3.0, 0.1
+
+    def f(q):
+        u = q[1] + b * q[0] ** 2 - b * s_ * s_
+        return -0.5 * (q[0] ** 2 / s_ ** 2 + u * u), np.array([-q[0] / s_ ** 2 - 2 * b * q[0] * u, -u])
+    rng = np.random.default_rng(0)
+    with po.user_model(_hdr("banana2d")):
+        for _ in range(6):
+            q = rng.normal(size=2) * 2
+            l, g = po.logdensity_and_gradient(po.FAMILY_USER, q, np.array([s_, b]), 32)
+            assert l == pytest.approx(f(q)[0], rel=1e-13, abs=1e-15) and np.allclose(g, f(q)[1], rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(g, _fd_grad(f, q), rtol=1e-5, atol=1e-6)
+        o = po.mcmc_with_warmup(po.FAMILY_USER, 2, 200, 1, 0, params=np.array([s_, b]))
+    assert np.all(np.isfinite(o["posterior_matrix"])) and o["tree_statistics"]["depth"].max() <= 10
+
+
 # ------------------------------------------------------------------ CPU: the user-model build of the library
 def test_user_library_builds_and_reports_its_model(pkg):
     """nvcc cross-compiles the model for sm_100a (no GPU needed); the result carries the whole C ABI plus the model."""
