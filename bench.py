@@ -334,6 +334,42 @@ def c4_probe_leg(pkg, torch, dev, local_rank, sm_max_mhz, chains=4736, warm=(20,
         return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
 
 
+def c3_probe_leg(pkg, torch, dev, local_rank, chains=262144, draws=10):
+    """BASELINE.json configs[2] at FULL size inside the default run: Neal's funnel D=10, 262 144 chains, the default warm-up
+    (900 transitions, ragged tree depths), then `draws` timed transitions.  Same code as `bench.py --config C3`
+    (profiles/r02_bench_c3.json).  Never fails the bench."""
+    try:
+        t0 = time.perf_counter()
+        eng = pkg.Engine(pkg.Funnel(10), chains=chains, seed=2026, device=local_rank)
+        try:
+            eng.random_position()
+            eng.find_initial_stepsize()
+            w_steps, w_ms = 0, 0.0
+            for st in list(pkg.default_warmup_stages())[1:]:
+                eng.warmup_stage(st)
+                w_steps += eng.last_total_steps(); w_ms += eng.last_kernel_ms()
+            post = torch.empty((chains, draws, 10), dtype=torch.float64, device=dev)
+            stats = torch.empty((chains, draws, 56), dtype=torch.uint8, device=dev)
+            logd = torch.empty((chains, draws), dtype=torch.float64, device=dev)
+            steps, ms = 0, 0.0
+            for i in range(1 + 3):
+                eng.mcmc_dev(draws, post.data_ptr(), stats.data_ptr(), logd.data_ptr())
+                if i >= 1:
+                    steps += eng.last_total_steps(); ms += eng.last_kernel_ms()
+            summary = eng.tree_summary_dev(stats.data_ptr(), draws, ebfmi=False)
+        finally:
+            eng.close()
+        return {"workload": "C3: Neal's funnel D=10, %d chains, default_warmup_stages() (900 transitions), %d draws per timed launch" % (chains, draws),
+                "value": steps / (ms * 1e-3), "unit": UNIT, "warmup_value": w_steps / (w_ms * 1e-3), "warmup_kernel_seconds": w_ms * 1e-3,
+                "leapfrogs_per_transition": steps / (3 * draws * chains), "a_mean": summary["a_mean"],
+                "termination_counts": summary["termination_counts"], "depth_counts": summary["depth_counts"],
+                "seconds": time.perf_counter() - t0,
+                "what": "device-timed like `value`, run after the timed region of the default workload; latency / divergence-bound "
+                        "(480 B of state per leapfrog step), so no HBM fraction is quoted"}
+    except Exception as e:
+        return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -478,10 +514,12 @@ def main():
         user_leg = user_model_leg(pkg, wl, K, D, n, args, local_rank, chain_offset, draws, stats, logd,
                                   tot_steps, dev_ms)
 
-    # ---------------- BASELINE.json configs[3] on its own kernel at a reduced chain count (after timing; C2 default run) ------
-    c4_leg = None
-    if world == 1 and args.config == "C2" and not args.chains and not args.dim and not os.environ.get("DHMC_BENCH_NO_C4_PROBE"):
+    # ---------------- the other BASELINE.json configurations inside the default run (after timing; one GPU): configs[3] on its
+    # own kernel at a reduced chain count, configs[2] at full size.  DHMC_BENCH_NO_PROBES=1 skips them.
+    c4_leg = c3_leg = None
+    if world == 1 and args.config == "C2" and not args.chains and not args.dim and not os.environ.get("DHMC_BENCH_NO_PROBES"):
         c4_leg = c4_probe_leg(pkg, torch, dev, local_rank, peaks()[1])
+        c3_leg = c3_probe_leg(pkg, torch, dev, local_rank)
 
     # ---------------- multi-GPU: one NCCL all-gather of the draws (library communicator), after timing ----------------
     gather = None
@@ -598,6 +636,8 @@ def main():
             line["user_model"] = user_leg
         if c4_leg:
             line["c4_probe"] = c4_leg
+        if c3_leg:
+            line["c3_probe"] = c3_leg
         if gather:
             bw = K * D * 8 * (world - 1) / (mx[7].item() * 1e-3) / 1e9
             line["allgather"] = {"ms": mx[7].item(), "first_call_ms": gather[0], "bytes_per_rank": K * D * 8,
