@@ -32,3 +32,29 @@ def test_reference_arm_other_ranks_exit_quietly():
                           "--steps", "1", "--warmup", "0", "--dim", "40", "--ref-seconds", "0.1"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_b200_arm_orchestration_emits_one_contract_line_with_stub_engine():
+    """The b200 arm cannot run without a GPU; its ORCHESTRATION can: tests/bench_stub_driver.py replaces torch's CUDA entry
+    points and the engine by stand-ins and runs bench.main() with the default configuration.  Checked: exactly one JSON line on
+    stdout with every key of the contract, the roofline / cpu_baseline / e2e objects, and the three auxiliary legs
+    (user_model, c4_probe, c3_probe) present without an error.  (The numbers are the stand-in's and mean nothing.)"""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "bench_stub_driver.py"), "--steps", "2", "--warmup", "3",
+                          "--cpu-baseline-seconds", "0.2"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    r = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "gpu_launches", "clocks", "roofline", "cpu_baseline", "e2e"):
+        assert k in r, k
+    assert r["metric"] == "leapfrog_steps_per_sec" and r["n_gpus"] == 1 and r["steps"] == 2 and r["warmup"] == 3
+    assert r["higher_is_better"] is True and r["scaling"] == "weak" and r["dtype"] == "f64" and r["vs_baseline"] is None
+    assert "workload" in r["config"] and r["config"]["chains_per_gpu"] == 65536 and r["config"]["dim"] == 1000
+    assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(r["roofline"]) and r["roofline"]["bound"] == "hbm"
+    assert set(("value", "unit", "cores", "kind", "sample")) <= set(r["cpu_baseline"]) and r["cpu_baseline"]["kind"] == "port"
+    assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(r["e2e"])
+    assert r["e2e"]["h2d_bytes_per_step"] == 65536 * 1000 * 8 and r["e2e"]["d2h_bytes_per_step"] == 65536 * 2 * (1000 * 8 + 56 + 8)
+    for leg in ("user_model", "c4_probe", "c3_probe"):
+        assert leg in r and "error" not in r[leg] and r[leg]["value"] > 0 and r[leg]["unit"] == r["unit"], (leg, r.get(leg))
+    assert r["user_model"]["model"] == "std_normal_user" and r["user_model"]["same_trees"] is True
