@@ -204,6 +204,21 @@ class UserLogDensity(DeviceLogDensity):
         self._cpu = cpu
         self.library_path = library or compile_user_model(self.header, deep=deep)
 
+    @classmethod
+    def from_source(cls, source, name, D, params=(), **kw):
+        """The model given as the TEXT of its header (e.g. generated by the caller): written to
+        csrc/user_models/src/<name>-<hash>.h and handled like a header file."""
+        _argcheck(name.isidentifier(), "name: a valid identifier (it becomes a file name)")
+        src_dir = os.path.join(_CSRC, "user_models", "src")
+        os.makedirs(src_dir, exist_ok=True)
+        path = os.path.join(src_dir, f"{name}-{hashlib.sha256(source.encode()).hexdigest()[:12]}.h")
+        if not os.path.exists(path):
+            tmp = path + ".tmp%d" % os.getpid()
+            with open(tmp, "w") as f:
+                f.write(source)
+            os.replace(tmp, path)
+        return cls(path, D, params=params, **kw)
+
     def params(self):
         return self._params
 

@@ -124,6 +124,31 @@ def leapfrog_trajectory(ℓ, q, ϵ, positions, κ=None, p=None, seed=0, device=0
     return [out[i] for i in sorted(out)]
 
 
+def check_gradient(ℓ, q, h=1e-6, device=0):
+    """∇ℓ of a device log density against central finite differences of its ℓ — both evaluated ON THE DEVICE (the first
+    thing to run on a new user model header, include/dhmc_models.h): 2·D + 1 chains of one engine hold q and q ± h·eᵢ.
+    Returns dict(grad=[D], fd=[D], max_abs_err, max_rel_err, lq).  (The reference leaves this to the user's AD backend.)"""
+    from . import api
+    q = np.asarray(q, float).ravel()
+    D = q.size
+    Q = np.repeat(q[None, :], 2 * D + 1, axis=0)
+    for i in range(D):
+        Q[1 + 2 * i, i] += h
+        Q[2 + 2 * i, i] -= h
+    eng = api.Engine(ℓ, chains=2 * D + 1, seed=0, device=device)
+    try:
+        eng.set_position(Q)                                     # strict evaluate_ℓ at every point (hamiltonian.jl:202-217)
+        st = eng.get_state(("lq", "grad"))
+    finally:
+        eng.close()
+    lq = np.asarray(st["lq"], float)
+    fd = (lq[1::2] - lq[2::2]) / (2 * h)
+    g = np.asarray(st["grad"][0], float)
+    err = np.abs(g - fd)
+    return dict(grad=g, fd=fd, lq=float(lq[0]), max_abs_err=float(err.max()),
+                max_rel_err=float((err / np.maximum(np.abs(fd), 1e-300)).max()))
+
+
 def ess_rhat(draws, max_lag=0):
     """Numpy mirror of dhmc_ess_rhat_dev (include/dhmc.h): split-R̂ and ESS per parameter of `draws` [chains, N, D].
     Every chain is split in two halves (m = 2·chains sequences of n = N // 2 draws); W = mean within-sequence variance,

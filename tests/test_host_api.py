@@ -165,6 +165,35 @@ def test_reporter_hook_and_stepwise_sampling(pkg, api):
     assert np.all(Q2 == 2.5)
 
 
+def test_user_model_from_source_and_gradient_check_host_logic(pkg, api, monkeypatch, tmp_path):
+    """UserLogDensity.from_source writes the header once (content-addressed); diagnostics.check_gradient lays out q, q ± h eᵢ
+    as 2·D + 1 chains and differences the returned ℓ values (engine replaced by a closed-form stand-in)."""
+    monkeypatch.setattr(api, "_CSRC", str(tmp_path))
+    src = "#define DHMC_USER_NSUMS 0\n/* ... */\n"
+    a = api.UserLogDensity.from_source(src, "toy", 3, params=[1.0], library="prebuilt.so")
+    b = api.UserLogDensity.from_source(src, "toy", 3, library="prebuilt.so")
+    assert a.header == b.header and open(a.header).read() == src and a.library_path == "prebuilt.so"
+    assert a.dimension() == 3 and list(a.params()) == [1.0] and a.family == pkg._lib.FAMILY_USER
+    with pytest.raises(pkg.ArgumentError):
+        api.UserLogDensity.from_source(src, "not a name", 3, library="x")
+
+    class QuadEngine:                                       # ℓ(q) = -½ Σ c_i q_i², ∇ℓ = -c q  (c = 1, 2, 3)
+        def __init__(self, ℓ, chains, **kw):
+            self.K = chains
+        def set_position(self, Q):
+            c = np.array([1.0, 2.0, 3.0])
+            self.lq = -0.5 * (np.asarray(Q) ** 2 @ c)
+            self.g = -np.asarray(Q) * c
+        def get_state(self, fields):
+            return {"lq": self.lq, "grad": self.g}
+        def close(self):
+            self.closed = True
+    monkeypatch.setattr(api, "Engine", QuadEngine)
+    r = pkg.diagnostics.check_gradient(a, [0.5, -1.0, 2.0])
+    assert np.allclose(r["grad"], [-0.5, 2.0, -6.0]) and np.allclose(r["fd"], r["grad"], rtol=1e-8)
+    assert r["max_abs_err"] < 1e-8 and r["lq"] == pytest.approx(-0.5 * (0.25 + 2.0 + 12.0))
+
+
 def test_initialization_fields(pkg, api):
     ℓ = pkg.StandardNormal(3)
     κ = pkg.GaussianKineticEnergy(np.array([1.0, 2.0, 3.0]))

@@ -366,3 +366,16 @@ def test_dense_mvnormal_user_model_on_device(pkg, po):
     assert np.max(np.abs(Z.mean(0) - mu) / sd) < 0.1
     assert np.max(np.abs(np.cov(Z.T) - Sigma) / np.outer(sd, sd)) < 0.15
     r["engine"].close()
+
+
+@pytest.mark.gpu
+def test_check_gradient_on_device(pkg):
+    """diagnostics.check_gradient: ∇ℓ of a user model against central differences of its ℓ, both evaluated by the device."""
+    rng = np.random.default_rng(4)
+    r = pkg.diagnostics.check_gradient(pkg.UserLogDensity(_hdr("rosenbrock"), 9, params=[1.0, 5.0], deep=True), rng.normal(size=9) * 0.7)
+    assert r["max_abs_err"] < 1e-5
+    q = rng.normal(size=10)
+    r = pkg.diagnostics.check_gradient(pkg.UserLogDensity(_hdr("eight_schools"), 10, params=np.concatenate([SCHOOLS_Y, SCHOOLS_S])), q)
+    assert r["max_abs_err"] < 1e-5
+    ln, gn = eight_schools_np(q, SCHOOLS_Y, SCHOOLS_S)
+    assert r["lq"] == pytest.approx(ln, rel=1e-12) and np.allclose(r["grad"], gn, rtol=1e-10, atol=1e-12)
