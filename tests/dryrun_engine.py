@@ -99,6 +99,11 @@ class DryRunEngine:
         return self.mcmc(N)
 
     def get_state(self, fields=("q", "lq", "grad", "minv", "eps", "p")):
+        if set(fields) <= {"q", "lq", "grad"} and not self.stages and self.q0 is not None:   # evaluate_ℓ at the set positions
+            with self._ctx():
+                ev = [self.po.logdensity_and_gradient(self.family, q, self.params, self.T) for q in self.q0]
+            full = {"q": self.q0.copy(), "lq": np.array([e[0] for e in ev]), "grad": np.stack([e[1] for e in ev])}
+            return {f: full[f] for f in fields}
         out = self._last if self._last is not None and self.n_drawn else self._run(self.n_drawn)
         st = {}
         for f in fields:
