@@ -6,7 +6,7 @@
 # Usage next to the real package:
 #     using DynamicHMC, B200HMC
 #     ℓ = B200HMC.StandardNormal(1000)                  # a DeviceLogDensity
-#     results = B200HMC.mcmc_with_warmup(2026, ℓ, 1000; chains = 65_536)
+#     results = B200HMC.mcmc_with_warmup(2026, ℓ, 10; chains = 65_536)     # draws are D·N·chains·8 B on the host (5.2 GB here)
 #     results[k].posterior_matrix, results[k].tree_statistics, results[k].κ, results[k].ϵ
 # `results[k]` has the fields of DynamicHMC.mcmc_with_warmup's NamedTuple (src/mcmc.jl:575-584), so
 # stack_posterior_matrices / pool_posterior_matrices (src/mcmc.jl:602-617) and DynamicHMC.Diagnostics
@@ -88,7 +88,7 @@ of this module bound to its library:
 
     lib = B200HMC.compile_user_model("include/models/rosenbrock.h")       # make user USER_HEADER=… (nvcc, sm_100a)
     M = B200HMC.bind_user_library(lib)                                     # a copy of B200HMC with LIB = lib
-    results = M.mcmc_with_warmup(2026, M.UserModel(100, [1.0, 5.0]), 1000; chains = 65_536)
+    results = M.mcmc_with_warmup(2026, M.UserModel(100, [1.0, 5.0]), 100; chains = 65_536)
 """
 struct UserModel{F} <: DeviceLogDensity
     D::Int; params::Vector{Float64}; cpu::F
