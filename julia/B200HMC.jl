@@ -219,6 +219,18 @@ function _mcmc(h::Handle, N::Integer)                             # mcmc — src
     posterior, stats, logd
 end
 
+"N transitions of every chain, every `thin`-th kept (dhmc_mcmc_thinned; output contract of `mcmc`, src/mcmc.jl:366-381, with
+N ÷ thin draws): what a many-chain run uses instead of keeping D·N·K doubles.  Returns (posterior [D, N÷thin, K], stats, logd)."
+function mcmc_thinned(h::Handle, N::Integer, thin::Integer)
+    n = N ÷ thin
+    posterior = Array{Float64}(undef, h.D, n, h.K)
+    stats = Matrix{TreeStatisticsNUTS}(undef, n, h.K)
+    logd = Matrix{Float64}(undef, n, h.K)
+    _ck(h, ccall((:dhmc_mcmc_thinned, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int32, Int32, Ptr{Float64}, Ptr{Cvoid}, Ptr{Float64}),
+                 h.ptr, C_NULL, N, thin, posterior, stats, logd))
+    posterior, stats, logd
+end
+
 # ---- mcmc_keep_warmup(rng, ℓ, N; …) — src/mcmc.jl:521-532 ---------------------
 "Returns, per chain, `(; initial_warmup_state, warmup, final_warmup_state, inference)` plus the handle (`sampling_logdensity`)."
 function mcmc_keep_warmup(seed::Integer, ℓ::DeviceLogDensity, N::Integer; chains::Integer = 1,
