@@ -469,6 +469,33 @@ class Engine:
     def transition_count(self, t):
         self._ck(self._lib.dhmc_set_transition_count(self._h, C.c_uint32(t)))
 
+    # -- checkpoint / resume: WarmupState(Q, κ, ϵ) (mcmc.jl:72-79) + the RNG counter is everything a fresh handle needs
+    def checkpoint(self):
+        """dict(q [K, D], minv ([K, D] diagonal or [K, D, D] Symmetric), dense, eps [K], transition_count, K, D)."""
+        st = self.get_state(("q", "minv", "eps"))
+        dense = self.metric_is_dense()
+        return dict(q=st["q"], eps=st["eps"], dense=bool(dense), minv=self.get_metric_dense() if dense else st["minv"],
+                    transition_count=int(self.transition_count), K=self.K, D=self.D)
+
+    def restore(self, ck):
+        """Continue the chains of `ck` (from `checkpoint()` / `load_checkpoint`) on this handle: same seed and chain_offset
+        give the same draws as the handle that was checkpointed (the Philox counter is (chain, transition, …))."""
+        _argcheck(int(ck["K"]) == self.K and int(ck["D"]) == self.D, "checkpoint of a different shape (chains, dimension)")
+        if bool(ck["dense"]):
+            self.set_metric_dense(ck["minv"])
+        else:
+            self.set_metric(ck["minv"])
+        self.set_position(ck["q"])
+        self.set_stepsize(ck["eps"])
+        self.transition_count = int(ck["transition_count"])
+
+    def save_checkpoint(self, path):
+        np.savez(path, **self.checkpoint())
+
+    def load_checkpoint(self, path):
+        with np.load(path) as f:
+            self.restore({k: f[k] for k in f.files})
+
     # -- fine-grained path
     def leapfrog(self, n_steps=1, sign=1):
         self._ck(self._lib.dhmc_leapfrog(self._h, C.c_int32(n_steps), C.c_int32(sign)))

@@ -863,6 +863,27 @@ def test_checkpoint_and_resume(pkg):
     assert np.array_equal(got, ref["posterior_matrix"])
 
 
+@pytest.mark.parametrize("M", ["Diagonal", "Symmetric"])
+def test_checkpoint_file_round_trip(pkg, tmp_path, M):
+    """Engine.save_checkpoint / load_checkpoint: a fresh handle restored from the file continues the same chains (diagonal
+    and Symmetric κ)."""
+    D, K = 12, 40
+    ℓ = pkg.DiagNormal(np.zeros(D), np.linspace(0.5, 4, D))
+    a = _engine(pkg, ℓ, K, seed=5)
+    a.random_position(); a.find_initial_stepsize()
+    a.warmup_stage(pkg.TuningNUTS(40, pkg.DualAveraging(), getattr(pkg, M)))
+    path = str(tmp_path / "ck.npz")
+    a.save_checkpoint(path)
+    ref = a.mcmc(5)
+    a.close()
+    b = _engine(pkg, ℓ, K, seed=5)
+    b.load_checkpoint(path)
+    got = b.mcmc(5)
+    b.close()
+    assert np.array_equal(got["posterior_matrix"], ref["posterior_matrix"])
+    assert np.array_equal(got["tree_statistics"], ref["tree_statistics"])
+
+
 def test_many_chains_per_cta_single_transition(pkg, po):
     """Regression: with more chains than resident CTAs and N = 1, every chain must use its own
     randexp stream (the 32-wide batch is per chain)."""

@@ -194,6 +194,36 @@ def test_user_model_from_source_and_gradient_check_host_logic(pkg, api, monkeypa
     assert r["max_abs_err"] < 1e-8 and r["lq"] == pytest.approx(-0.5 * (0.25 + 2.0 + 12.0))
 
 
+def test_checkpoint_and_restore_host_logic(pkg, api, tmp_path):
+    """Engine.checkpoint / restore / save_checkpoint / load_checkpoint: (Q, κ, ϵ, RNG counter), diagonal and Symmetric κ,
+    through a file; the primitives are replaced by recorders (the device round trip: test_gpu_parity.py)."""
+    class FakeEngine(pkg.Engine):                           # the real class (the `api` fixture swaps api.Engine for a recorder)
+        def __init__(self, K, D, dense):
+            self.K, self.D, self._dense, self.log, self._t = K, D, dense, [], 7
+        def get_state(self, fields):
+            return {"q": np.arange(self.K * self.D, dtype=float).reshape(self.K, self.D), "minv": np.full((self.K, self.D), 2.0),
+                    "eps": np.linspace(0.1, 0.2, self.K)}
+        def metric_is_dense(self): return self._dense
+        def get_metric_dense(self): return np.tile(np.eye(self.D) * 3.0, (self.K, 1, 1))
+        def set_metric(self, m): self.log.append(("set_metric", np.array(m)))
+        def set_metric_dense(self, m): self.log.append(("set_metric_dense", np.array(m)))
+        def set_position(self, q): self.log.append(("set_position", np.array(q)))
+        def set_stepsize(self, e): self.log.append(("set_stepsize", np.array(e)))
+        transition_count = property(lambda self: self._t, lambda self, t: self.log.append(("transition_count", t)))
+        def close(self): pass
+    for dense in (False, True):
+        a = FakeEngine(3, 4, dense)
+        path = str(tmp_path / f"ck{int(dense)}.npz")
+        a.save_checkpoint(path)
+        b = FakeEngine(3, 4, dense)
+        b.load_checkpoint(path)
+        assert [c[0] for c in b.log] == ["set_metric_dense" if dense else "set_metric", "set_position", "set_stepsize", "transition_count"]
+        assert b.log[0][1].shape == ((3, 4, 4) if dense else (3, 4)) and np.array_equal(b.log[1][1], a.get_state(("q",))["q"])
+        assert np.array_equal(b.log[2][1], np.linspace(0.1, 0.2, 3)) and b.log[3][1] == 7
+        with pytest.raises(pkg.ArgumentError):
+            FakeEngine(5, 4, dense).load_checkpoint(path)
+
+
 def test_initialization_fields(pkg, api):
     ℓ = pkg.StandardNormal(3)
     κ = pkg.GaussianKineticEnergy(np.array([1.0, 2.0, 3.0]))
